@@ -1,0 +1,146 @@
+/* e1b200.h -- C-ABI of the B200-native Galileo E1B/C baseband synthesiser.
+ *
+ * The reference (harshadms/galileo-sdr-sim) has no plugin/FFI seam: its IQ synthesis is the
+ * body of one loop nest inside galileo_task() (src/galileo-sdr.cpp:438-564).  This header is
+ * the seam a maintainer would cut there (INTEGRATION.md shows the patch):
+ *
+ *   reference                                             this ABI
+ *   ---------------------------------------------------   -----------------------------------
+ *   sim constants SAMP_RATE / NUM_IQ_SAMPLES / MAX_CHAN    e1b200_config      (create)
+ *     (include/constants.h:10,75,96)
+ *   allocateChannel(): chan[i].prn, .carr_phase            e1b200_set_channel / clear_channel
+ *     (src/channel.cpp:69-99, 112-119)
+ *   computeCodePhase(): f_carr, f_code, code_phase, ibit   e1b200_restate  -> e1_epoch_rec
+ *     (src/gal-sig.cpp:308-347)
+ *   chan[i].page + generateINavMsg() called in-loop        e1_epoch_rec.page_cur / page_next
+ *     (src/galileo-sdr.cpp:497-506, src/inav-msg.cpp:28)
+ *   sample loop + (short) store into iq_buff               e1b200_synth_epochs*
+ *     (src/galileo-sdr.cpp:481-539)
+ *   chan[i].carr_phase carried across blocks               e1b200_get/set_carrier_phase
+ *     (src/galileo-sdr.cpp:531-532)
+ *
+ * Conventions: plain C linkage, no exceptions cross the boundary, every call returns 0 or a
+ * negative E1B200_E* code, the opaque context owns all device memory, the caller owns every
+ * host buffer it passes in.  One producer thread per context (the reference's generator is
+ * single-threaded too).  There is NO CPU fallback: if no CUDA device is usable, create fails.
+ */
+#ifndef E1B200_H
+#define E1B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E1_CODE_LEN        4092  /* chips per primary code      (CA_SEQ_LEN_E1,  constants.h:121) */
+#define E1_SYM_PER_PAGE    500   /* nav symbols per 2 s page    (N_SYM_PAGE,     constants.h:32)  */
+#define E1_SEC_CODE_LEN    25    /* E1-C secondary code length  (constants.h:173,213)             */
+#define E1_N_PRN_CODES     50
+#define E1_PAGE_BYTES      64    /* 500 symbol bits, bit k -> byte k>>3, bit k&7; rest zero       */
+#define E1B200_MAX_CHAN    64    /* upper bound on config.max_chan                                */
+
+/* error codes */
+#define E1B200_OK           0
+#define E1B200_EINVAL     (-1)   /* bad argument / record                                          */
+#define E1B200_ENODEV     (-2)   /* no usable CUDA device (there is no CPU fallback)               */
+#define E1B200_ECUDA      (-3)   /* CUDA runtime error, see e1b200_last_error()                    */
+#define E1B200_ENOMEM     (-4)
+#define E1B200_ESTATE     (-5)   /* call sequence error                                            */
+
+/* e1_epoch_rec.flags */
+#define E1_REC_SET_PHASE   1u    /* load carr_phase_init into the slot before sample 0 of this
+                                    epoch (what allocateChannel does, src/channel.cpp:98-99)       */
+
+/* One record per (epoch, channel slot): everything the reference's sample loop reads from
+ * channel_t (include/structures.h:140-162) at the top of a 0.1 s block, after
+ * computeCodePhase().  The carrier phase is NOT in the record: it is integrated across
+ * epochs by the synthesiser, exactly like chan[i].carr_phase.                              */
+typedef struct e1_epoch_rec {
+    int32_t  prn;              /* 1..50, 0 = slot idle this epoch            (channel_t.prn)      */
+    int32_t  ibit0;            /* nav symbol index at sample 0, 0..499       (channel_t.ibit)     */
+    uint32_t flags;            /* E1_REC_*                                                        */
+    uint32_t reserved;
+    double   code_phase0;      /* chips, [0,4092)                            (channel_t.code_phase)*/
+    double   f_code;           /* chips/s                                    (channel_t.f_code)   */
+    double   f_carr;           /* Hz                                         (channel_t.f_carr)   */
+    double   carr_phase_init;  /* cycles, used iff E1_REC_SET_PHASE                               */
+    uint8_t  page_cur[E1_PAGE_BYTES];   /* symbols in force at sample 0      (channel_t.page)     */
+    uint8_t  page_next[E1_PAGE_BYTES];  /* symbols after ibit passes 499 inside this epoch        */
+} e1_epoch_rec;                /* 176 bytes */
+
+/* Device-side restate input (BASELINE config 4): pseudoranges instead of phases; the kernel
+ * evaluates computeCodePhase (src/gal-sig.cpp:308-347) itself.                              */
+typedef struct e1_range_rec {
+    int32_t  prn;
+    uint32_t flags;
+    double   rho_prev;         /* chan->rho0.range  [m]                                           */
+    double   rho_cur;          /* rho1.range        [m]                                           */
+    double   grx_sec;          /* receiver time of this epoch [s of week]                         */
+    double   carr_phase_init;
+    uint8_t  page_cur[E1_PAGE_BYTES];
+    uint8_t  page_next[E1_PAGE_BYTES];
+} e1_range_rec;                /* 168 bytes */
+
+typedef struct e1b200_config {
+    double   fs_hz;            /* sample rate; the reference uses (double)(float)SAMP_RATE        */
+    int32_t  samples_per_epoch;/* NUM_IQ_SAMPLES = fs/10                                          */
+    int32_t  max_chan;         /* MAX_CHAN, 1..E1B200_MAX_CHAN                                    */
+    int32_t  device;           /* CUDA device ordinal                                             */
+    uint32_t flags;            /* E1B200_CFG_*                                                    */
+    double   dt_epoch;         /* receiver-time step per epoch; 0 -> reference's 0.100000023142   */
+} e1b200_config;
+
+#define E1B200_CFG_SERIAL_PLANNER 1u  /* carrier planner: single chain per channel (debug/compare) */
+
+typedef struct e1b200_ctx e1b200_ctx;
+
+typedef struct e1b200_timing {
+    float plan_ms;             /* planner kernels of the last synth call (CUDA events)            */
+    float synth_ms;            /* sample-synthesis kernel(s) of the last synth call               */
+    float total_ms;            /* first launch -> last launch complete, incl. copies if any       */
+    int32_t kernel_launches;   /* kernels launched by the last synth call                         */
+    int32_t synth_launches;
+} e1b200_timing;
+
+int  e1b200_create(const e1b200_config *cfg, e1b200_ctx **out);
+int  e1b200_destroy(e1b200_ctx *ctx);
+
+int  e1b200_set_channel(e1b200_ctx *ctx, int slot, int prn, double carr_phase0);
+int  e1b200_clear_channel(e1b200_ctx *ctx, int slot);
+int  e1b200_get_carrier_phase(e1b200_ctx *ctx, int slot, double *out);
+int  e1b200_set_carrier_phase(e1b200_ctx *ctx, int slot, double phase);
+
+/* Host-buffer entry point (what the patched galileo_task() calls): copies recs H2D,
+ * synthesises n_epochs * samples_per_epoch samples, copies int16 I/Q D2H into out.
+ * recs is [n_epochs][max_chan]; out is [n_epochs * samples_per_epoch * 2] int16.       */
+int  e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, int16_t *out);
+
+/* Device-resident variant: d_recs and d_out are device pointers on cfg.device.  Runs on the
+ * context's stream; returns after the work is enqueued and e1b200_sync() waits for it.     */
+int  e1b200_synth_epochs_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *d_recs, int16_t *d_out);
+int  e1b200_sync(e1b200_ctx *ctx);
+
+/* Same two, from pseudoranges (restate evaluated on the device).                            */
+int  e1b200_synth_ranges(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *recs, int16_t *out);
+int  e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *d_recs, int16_t *d_out);
+
+/* Host restatement of computeCodePhase for callers that keep the restate on the CPU.       */
+int  e1b200_restate(double rho_prev, double rho_cur, double dt, double grx_sec,
+                    double *f_carr, double *f_code, double *code_phase0, int32_t *ibit0, int32_t *ipage);
+
+int  e1b200_get_timing(e1b200_ctx *ctx, e1b200_timing *out);
+void *e1b200_stream(e1b200_ctx *ctx);          /* cudaStream_t the context launches on           */
+const char *e1b200_last_error(e1b200_ctx *ctx);
+const char *e1b200_version(void);
+
+/* pinned host allocation helpers so the reference's fwrite/FIFO memcpy consumers
+ * (src/galileo-sdr.cpp:542,588) can stay unchanged while D2H runs at full PCIe rate        */
+int  e1b200_host_alloc(void **p, size_t bytes);
+int  e1b200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E1B200_H */

@@ -1,0 +1,207 @@
+/* e1_oracle.c -- see e1_oracle.h.  TEST INFRASTRUCTURE, not product code.
+ *
+ * A from-scratch restatement of what the reference computes, written from the behavioural
+ * spec in SURVEY.md Appendix A.  Every function names the reference lines it follows.
+ * Build with -O2 -ffp-contract=off: the reference's phases are plain (unfused) IEEE double
+ * operations and a fused multiply-add changes the output.
+ */
+#include "e1_oracle.h"
+#include "../galileo-sdr-sim_b200/data/e1_prn_codes.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- a3: carrier tables (include/constants.h:216-284) ------------------------------------
+ * The shipped tables are round(250*cos(2*pi*(i+1/2)/512)) (same for sin) except at the four
+ * places per table where the exact value is +-105.5 and the shipped entry is +-105.       */
+void e1o_carrier_lut(int cos_out[512], int sin_out[512])
+{
+    static const int cos_fix[4] = {92, 163, 348, 419};
+    static const int sin_fix[4] = {35, 220, 291, 476};
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < 512; i++) {
+        double a = two_pi * ((double)i + 0.5) / 512.0;
+        cos_out[i] = (int)lround(250.0 * cos(a));
+        sin_out[i] = (int)lround(250.0 * sin(a));
+    }
+    for (int k = 0; k < 4; k++) {
+        cos_out[cos_fix[k]] = cos_out[cos_fix[k]] > 0 ? 105 : -105;
+        sin_out[sin_fix[k]] = sin_out[sin_fix[k]] > 0 ? 105 : -105;
+    }
+}
+
+/* ---- a11: hex -> chips -> BOC(1,1) half-chips (src/gal-sig.cpp:9-233) ----------------------
+ * chip j = +1 for logic 0, -1 for logic 1, MSB of each hex digit first; each chip becomes two
+ * half-chips and sboc() negates every even-indexed entry: E[2j] = -chip, E[2j+1] = +chip.  */
+void e1o_halfchip_table(int prn, int is_e1c, short *out)
+{
+    const uint32_t *w = is_e1c ? E1C_PRN_WORDS[prn - 1] : E1B_PRN_WORDS[prn - 1];
+    for (int j = 0; j < E1_CODE_LEN; j++) {
+        int bit = (w[j >> 5] >> (31 - (j & 31))) & 1u;
+        short chip = bit ? -1 : 1;
+        out[2 * j] = (short)-chip;
+        out[2 * j + 1] = chip;
+    }
+}
+
+/* ---- a8: computeCodePhase (src/gal-sig.cpp:308-347) ------------------------------------- */
+void e1o_restate(double rho_prev, double rho_cur, double dt, double grx_sec,
+                 double *f_carr, double *f_code, double *code_phase0, int *ibit0, int *ipage_out)
+{
+    const double lambda_e1 = 0.1902936727983649;       /* LAMBDA_E1, constants.h:119       */
+    const double carr_to_code = 0.0006493506493506494; /* CARR_TO_CODE_E1, constants.h:125 */
+    const double c_light = 2.99792458e8;               /* SPEED_OF_LIGHT, constants.h:60   */
+    double rhorate = (rho_cur - rho_prev) / dt;                    /* :315 */
+    double fc = -rhorate / lambda_e1;                              /* :318 */
+    *f_carr = fc;
+    *f_code = 1.023e6 + fc * carr_to_code;                         /* :320 */
+    double ms = (grx_sec - rho_cur / c_light) * 1000.0;            /* :322 */
+    int ipage = (int)(ms / 2000.0);                                /* :324 */
+    ms -= ipage * 2000;                                            /* :326 */
+    int ibit = (int)((unsigned int)ms / 4);                        /* :328 */
+    ms -= ibit * 4;                                                /* :329 */
+    *code_phase0 = ms / 4 * E1_CODE_LEN;                           /* :330 */
+    *ibit0 = (ibit + E1_SYM_PER_PAGE / 2) % E1_SYM_PER_PAGE;       /* :334 */
+    *ipage_out = ipage % 360;                                      /* :339 */
+}
+
+/* ---- a1..a7: the sample loop (src/galileo-sdr.cpp:481-539) --------------------------------- */
+static const unsigned char SEC25[E1_SEC_CODE_LEN] = /* GALILEO_E1_SECONDARY_CODE, constants.h:213 */
+    {0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 1, 0, 1, 1, 0, 1, 1, 0, 0, 1, 0};
+
+typedef struct {
+    short b[2 * E1_CODE_LEN];
+    short c[2 * E1_CODE_LEN];
+} code_pair;
+
+static int g_lut_ready = 0;
+static int g_cos[512], g_sin[512];
+static code_pair *g_codes[E1_N_PRN_CODES + 1];
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static const code_pair *codes_for(int prn)
+{
+    pthread_mutex_lock(&g_lock);
+    if (!g_lut_ready) {
+        e1o_carrier_lut(g_cos, g_sin);
+        g_lut_ready = 1;
+    }
+    if (!g_codes[prn]) {
+        code_pair *p = (code_pair *)malloc(sizeof *p);
+        e1o_halfchip_table(prn, 0, p->b);
+        e1o_halfchip_table(prn, 1, p->c);
+        g_codes[prn] = p;
+    }
+    pthread_mutex_unlock(&g_lock);
+    return g_codes[prn];
+}
+
+static inline int page_bit(const uint8_t *pg, int k) { return (pg[k >> 3] >> (k & 7)) & 1; }
+
+/* one epoch, channels [c0,c1): adds into acc[2*n_samp] (int32 I,Q) */
+static void synth_epoch_channels(double delt, int n_samp, const e1_epoch_rec *rec, int c0, int c1,
+                                 double *carr_phase, int *acc)
+{
+    for (int ch = c0; ch < c1; ch++) {
+        const e1_epoch_rec *r = &rec[ch];
+        if (r->prn <= 0)
+            continue;
+        const code_pair *cp = codes_for(r->prn);
+        if (r->flags & E1_REC_SET_PHASE)
+            carr_phase[ch] = r->carr_phase_init;
+        double code_phase = r->code_phase0;
+        double phi = carr_phase[ch];
+        int ibit = r->ibit0;
+        const uint8_t *page = r->page_cur;
+        const double f_code = r->f_code, f_carr = r->f_carr;
+        for (int k = 0; k < n_samp; k++) {
+            if (code_phase >= E1_CODE_LEN) {               /* :491-507 */
+                code_phase -= E1_CODE_LEN;
+                ibit++;
+                if (ibit >= E1_SYM_PER_PAGE) {
+                    ibit = 0;
+                    page = r->page_next;                   /* generateINavMsg() result */
+                }
+            }
+            int it = ((int)(511 * phi)) & 511;             /* :509-510 */
+            int cosv = g_cos[it], sinv = g_sin[it];
+            int icode = (int)(code_phase * 2);             /* :512 */
+            int eb = cp->b[icode], ec = cp->c[icode];      /* :514-515 */
+            int databit = page_bit(page, ibit) ? -1 : 1;   /* :517 */
+            int sec = SEC25[ibit % E1_SEC_CODE_LEN] ? -1 : 1; /* :518 */
+            int m = eb * databit - ec * sec;               /* :520-521 */
+            acc[2 * k] += m * cosv;                        /* :524-525 */
+            acc[2 * k + 1] += m * sinv;
+            code_phase += f_code * delt;                   /* :528 */
+            phi += f_carr * delt;                          /* :531 */
+            phi -= (long)phi;                              /* :532 */
+        }
+        carr_phase[ch] = phi;
+    }
+}
+
+void e1o_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs,
+                      const e1_epoch_rec *recs, double *carr_phase, int16_t *out)
+{
+    const double delt = 1.0 / fs_hz;                       /* :162 */
+    int *acc = (int *)malloc(sizeof(int) * 2 * (size_t)n_samp);
+    for (int e = 0; e < n_epochs; e++) {
+        memset(acc, 0, sizeof(int) * 2 * (size_t)n_samp);
+        synth_epoch_channels(delt, n_samp, recs + (size_t)e * max_chan, 0, max_chan, carr_phase, acc);
+        int16_t *o = out + (size_t)e * n_samp * 2;
+        for (int k = 0; k < 2 * n_samp; k++)
+            o[k] = (short)acc[k];                          /* :536-537 */
+    }
+    free(acc);
+}
+
+/* ---- multi-threaded variant: the reference is single-threaded; this spreads channels over
+ * host threads so the CPU baseline can use every core the box has.                         */
+typedef struct {
+    double delt;
+    int n_samp, max_chan, n_epochs, c0, c1;
+    const e1_epoch_rec *recs;
+    double *carr_phase;
+    int *acc; /* [n_epochs][2*n_samp] private */
+} mt_job;
+
+static void *mt_worker(void *arg)
+{
+    mt_job *j = (mt_job *)arg;
+    for (int e = 0; e < j->n_epochs; e++)
+        synth_epoch_channels(j->delt, j->n_samp, j->recs + (size_t)e * j->max_chan, j->c0, j->c1,
+                             j->carr_phase, j->acc + (size_t)e * 2 * j->n_samp);
+    return NULL;
+}
+
+void e1o_synth_epochs_mt(double fs_hz, int n_samp, int max_chan, int n_epochs,
+                         const e1_epoch_rec *recs, double *carr_phase, int16_t *out, int n_threads)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > max_chan) n_threads = max_chan;
+    size_t per = (size_t)n_epochs * 2 * n_samp;
+    mt_job *jobs = (mt_job *)calloc((size_t)n_threads, sizeof *jobs);
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof *th);
+    for (int t = 0; t < n_threads; t++) {
+        mt_job *j = &jobs[t];
+        j->delt = 1.0 / fs_hz; j->n_samp = n_samp; j->max_chan = max_chan; j->n_epochs = n_epochs;
+        j->c0 = (int)((long)max_chan * t / n_threads);
+        j->c1 = (int)((long)max_chan * (t + 1) / n_threads);
+        j->recs = recs; j->carr_phase = carr_phase;
+        j->acc = (int *)calloc(per, sizeof(int));
+        pthread_create(&th[t], NULL, mt_worker, j);
+    }
+    for (int t = 0; t < n_threads; t++)
+        pthread_join(th[t], NULL);
+    for (size_t k = 0; k < per; k++) {
+        int s = 0;
+        for (int t = 0; t < n_threads; t++)
+            s += jobs[t].acc[k];
+        out[k] = (short)s;
+    }
+    for (int t = 0; t < n_threads; t++)
+        free(jobs[t].acc);
+    free(jobs); free(th);
+}
