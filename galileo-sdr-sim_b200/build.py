@@ -1,0 +1,44 @@
+"""Builds libe1b200.so (the C-ABI + sm_100a kernels) in-tree with nvcc.
+
+    python galileo-sdr-sim_b200/build.py [--force]
+
+The library lands in galileo-sdr-sim_b200/lib/ (git-ignored, shipped to the GPU box by gpurun).
+nvcc cross-compiles for sm_100a, so this works on a machine without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+SRC = PKG / "csrc" / "e1b200_capi.cu"
+DEPS = [SRC, PKG / "csrc" / "e1_kernels.cuh", PKG / "csrc" / "e1_core.h", PKG / "data" / "e1_prn_codes.h",
+        PKG.parent / "include" / "e1b200.h"]
+LIB = PKG / "lib" / "libe1b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # the exact paths use explicit __dadd_rn/__dmul_rn; switch contraction off everywhere anyway
+    "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def build_lib(force=False, verbose=False):
+    if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
+        return LIB
+    LIB.parent.mkdir(exist_ok=True)
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB), str(SRC)]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

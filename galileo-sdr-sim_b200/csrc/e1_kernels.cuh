@@ -1,0 +1,251 @@
+/* e1_kernels.cuh -- sm_100a kernels of the Galileo E1B/C synthesiser.
+ *
+ *   e1_restate_kernel     computeCodePhase (src/gal-sig.cpp:308-347) per (epoch, channel)
+ *   e1_plan_code_kernel   exact code-phase / symbol checkpoints per (epoch, tile, channel)
+ *   e1_plan_carr_kernel   exact carrier-phase checkpoints per (epoch, tile, channel)
+ *   e1_synth_kernel       the sample loop (src/galileo-sdr.cpp:481-539): per sample, all
+ *                         channels, int32 accumulate, packed int16 I/Q, 128-bit stores
+ *
+ * HBM layout
+ *   recs   e1_epoch_rec[n_epochs][max_chan]                         176 B each (caller / H2D)
+ *   ck     e1_tile_ck[n_epochs][tiles_per_epoch][max_chan]           32 B each (scratch)
+ *   out    int16 I,Q interleaved, sample (epoch*N + k) at byte 4*(epoch*N + k)
+ *   codes  uint32[50][256]: chip c of PRN p -> bits 2*(c&15) (E1-B) and 2*(c&15)+1 (E1-C)
+ *          of word p*256 + c/16; a set bit means chip level -1        51 200 B, smem-resident
+ *   lut    int32[1024]: 2*(cos + 65536*sin) for index i (first 512) and for index (-i)&511
+ *          (second 512, used while the carrier phase is negative)      4 096 B, smem-resident
+ */
+#ifndef E1_KERNELS_CUH
+#define E1_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include "../../include/e1b200.h"
+#include "e1_core.h"
+
+#define E1_CODE_WORDS_PER_PRN E1C_CODE_WORDS_PER_PRN
+#define E1_CODES_BYTES (E1C_N_PRN * E1_CODE_WORDS_PER_PRN * 4)
+#define E1_LUT_ENTRIES 1024
+#define E1_LUT_BYTES (E1_LUT_ENTRIES * 4)
+#define E1_SYNTH_THREADS 256
+#define E1_RUN E1C_RUN
+#define E1_GROUP (E1_SYNTH_THREADS * E1_RUN)
+
+struct e1_synth_args {
+    const e1_epoch_rec *recs;
+    const e1_tile_ck *ck;
+    const uint32_t *codes;
+    const int32_t *lut;
+    int16_t *out;
+    unsigned long long *counters; /* [0] ambiguous samples resolved exactly, [1] planner errors */
+    double delt;
+    int n_epochs, n_samp, max_chan, tile, tiles_per_epoch;
+    uint32_t thr_carr, thr_code;
+    int vec_ok, use_bulk;
+};
+
+/* ------------------------------------------------------------------ restate (a8) */
+__global__ void e1_restate_kernel(const e1_range_rec *rr, e1_epoch_rec *recs, int n, double dt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const e1_range_rec r = rr[i];
+    e1_epoch_rec o;
+    o.prn = r.prn;
+    o.flags = r.flags;
+    o.reserved = 0;
+    o.carr_phase_init = r.carr_phase_init;
+    const double lambda_e1 = 0.1902936727983649;       /* constants.h:119 */
+    const double carr_to_code = 0.0006493506493506494; /* constants.h:125 */
+    const double c_light = 2.99792458e8;               /* constants.h:60  */
+    double rhorate = __ddiv_rn(__dadd_rn(r.rho_cur, -r.rho_prev), dt);       /* :315 */
+    double fc = __ddiv_rn(-rhorate, lambda_e1);                               /* :318 */
+    o.f_carr = fc;
+    o.f_code = __dadd_rn(1.023e6, __dmul_rn(fc, carr_to_code));               /* :320 */
+    double ms = __dmul_rn(__dadd_rn(r.grx_sec, -__ddiv_rn(r.rho_cur, c_light)), 1000.0); /* :322 */
+    int ipage = __double2int_rz(__ddiv_rn(ms, 2000.0));                       /* :324 */
+    ms = __dadd_rn(ms, -(double)(ipage * 2000));                              /* :326 */
+    int ibit = (int)(__double2uint_rz(ms) / 4u);                              /* :328 */
+    ms = __dadd_rn(ms, -(double)(ibit * 4));                                  /* :329 */
+    o.code_phase0 = __dmul_rn(__ddiv_rn(ms, 4.0), (double)E1C_CODE_LEN);      /* :330 */
+    o.ibit0 = (ibit + E1C_SYM_PER_PAGE / 2) % E1C_SYM_PER_PAGE;               /* :334 */
+#pragma unroll
+    for (int k = 0; k < E1_PAGE_BYTES; k++) {
+        o.page_cur[k] = r.page_cur[k];
+        o.page_next[k] = r.page_next[k];
+    }
+    recs[i] = o;
+}
+
+/* ------------------------------------------------------------------ planners */
+/* one thread per (epoch, channel) */
+__global__ void e1_plan_code_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, int n_epochs, int max_chan,
+                                    int n_samp, int tile, int tiles_per_epoch, double delt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_epochs * max_chan)
+        return;
+    int e = i / max_chan, ch = i - e * max_chan;
+    e1_plan_code_epoch(&recs[i], ck + (size_t)e * tiles_per_epoch * max_chan + ch, max_chan, n_samp, tile,
+                       tiles_per_epoch, delt);
+}
+
+/* one thread per channel, serial over the epochs of the call */
+__global__ void e1_plan_carr_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, double *phase, int n_epochs,
+                                    int max_chan, int n_samp, int tile, int tiles_per_epoch, double delt)
+{
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= max_chan)
+        return;
+    double phi = phase[ch];
+    for (int e = 0; e < n_epochs; e++)
+        phi = e1_plan_carr_epoch(&recs[(size_t)e * max_chan + ch], ck + (size_t)e * tiles_per_epoch * max_chan + ch,
+                                 max_chan, phi, n_samp, tile, tiles_per_epoch, delt);
+    phase[ch] = phi;
+}
+
+/* ------------------------------------------------------------------ synthesis */
+__device__ __forceinline__ uint32_t e1_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier. */
+__device__ __forceinline__ void e1_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :
+                 : "r"(e1_smem_u32(dst)), "l"(src), "r"(bytes), "r"(e1_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void e1_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" : : "r"(e1_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void e1_mbar_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" : : "r"(e1_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void e1_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tE1_WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra E1_WAIT_%=;\n\t}"
+                 :
+                 : "r"(e1_smem_u32(bar)), "r"(parity)
+                 : "memory");
+}
+
+template <int G>
+__global__ void __launch_bounds__(E1_SYNTH_THREADS) e1_synth_kernel(const e1_synth_args A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
+    int32_t *s_lut = reinterpret_cast<int32_t *>(smem_raw + E1_CODES_BYTES);
+    e1_chan_par *s_par = reinterpret_cast<e1_chan_par *>(smem_raw + E1_CODES_BYTES + E1_LUT_BYTES);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_nact;
+    __shared__ unsigned long long s_cnt[2];
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_cnt[0] = 0;
+        s_cnt[1] = 0;
+    }
+    /* tables: one bulk copy each through the TMA unit, once per (persistent) CTA */
+    if (A.use_bulk) {
+        if (tid == 0) {
+            e1_mbar_init(&s_bar, 1);
+            e1_mbar_expect(&s_bar, E1_CODES_BYTES + E1_LUT_BYTES);
+            e1_bulk_g2s(s_codes, A.codes, E1_CODES_BYTES, &s_bar);
+            e1_bulk_g2s(s_lut, A.lut, E1_LUT_BYTES, &s_bar);
+        }
+        __syncthreads();
+        e1_mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = tid; i < E1_CODES_BYTES / 4; i += E1_SYNTH_THREADS)
+            s_codes[i] = A.codes[i];
+        for (int i = tid; i < E1_LUT_ENTRIES; i += E1_SYNTH_THREADS)
+            s_lut[i] = A.lut[i];
+    }
+
+    const int total_tiles = A.n_epochs * A.tiles_per_epoch;
+    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
+        const int e = tile_id / A.tiles_per_epoch, t = tile_id - e * A.tiles_per_epoch;
+        __syncthreads(); /* previous tile done with s_par */
+        if (tid == 0)
+            s_nact = 0;
+        __syncthreads();
+        if (tid < A.max_chan) {
+            const e1_tile_ck c = A.ck[(size_t)tile_id * A.max_chan + tid];
+            if (c.sym & E1_CK_ACTIVE) {
+                e1_chan_par p;
+                e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + tid], A.delt, A.tile, &p);
+                if (c.sym & E1_CK_ERROR)
+                    atomicAdd(&s_cnt[1], 1ull);
+                s_par[atomicAdd(&s_nact, 1)] = p;
+            }
+        }
+        __syncthreads();
+        const int nact = s_nact;
+        const int n_valid = min(A.tile, A.n_samp - t * A.tile);
+
+        int acc[G][E1_RUN];
+#pragma unroll
+        for (int g = 0; g < G; g++)
+#pragma unroll
+            for (int i = 0; i < E1_RUN; i++)
+                acc[g][i] = 0;
+        uint32_t amb = 0;
+        for (int a = 0; a < nact; a++) {
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                amb |= e1_channel_run(&s_par[a], s_codes, s_lut, g * E1_GROUP + tid * E1_RUN, acc[g], A.thr_carr,
+                                      A.thr_code, 0, nullptr);
+        }
+        if (amb) { /* rare: redo this thread's samples, resolving ambiguous ones exactly */
+            unsigned long long n_exact = 0;
+#pragma unroll
+            for (int g = 0; g < G; g++)
+#pragma unroll
+                for (int i = 0; i < E1_RUN; i++)
+                    acc[g][i] = 0;
+            for (int a = 0; a < nact; a++) {
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    e1_channel_run(&s_par[a], s_codes, s_lut, g * E1_GROUP + tid * E1_RUN, acc[g], A.thr_carr,
+                                   A.thr_code, 1, &n_exact);
+            }
+            atomicAdd(&s_cnt[0], n_exact);
+        }
+        /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
+        int16_t *out_tile = A.out + ((size_t)e * A.n_samp + (size_t)t * A.tile) * 2;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int j0 = g * E1_GROUP + tid * E1_RUN;
+            uint32_t w[E1_RUN];
+#pragma unroll
+            for (int i = 0; i < E1_RUN; i++)
+                w[i] = e1_pack_iq(acc[g][i]);
+            if (A.vec_ok && j0 + E1_RUN <= n_valid) {
+                *reinterpret_cast<uint4 *>(out_tile + (size_t)j0 * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < E1_RUN; i++)
+                    if (j0 + i < n_valid)
+                        *reinterpret_cast<uint32_t *>(out_tile + (size_t)(j0 + i) * 2) = w[i];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && A.counters) {
+        if (s_cnt[0])
+            atomicAdd(&A.counters[0], s_cnt[0]);
+        if (s_cnt[1])
+            atomicAdd(&A.counters[1], s_cnt[1]);
+    }
+}
+
+#endif /* E1_KERNELS_CUH */

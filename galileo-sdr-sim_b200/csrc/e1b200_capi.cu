@@ -1,0 +1,537 @@
+/* e1b200_capi.cu -- the C-ABI declared in include/e1b200.h over the sm_100a kernels.
+ *
+ * Replaces the body of the reference's 0.1 s block loop (src/galileo-sdr.cpp:481-539): the
+ * caller (a patched galileo_task(), or this repo's own host driver) hands over the channel
+ * state it computed for each block and gets the int16 I/Q samples back.  No CPU fallback:
+ * without a usable CUDA device e1b200_create() fails with E1B200_ENODEV.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/e1b200.h"
+#include "../data/e1_prn_codes.h"
+#include "e1_kernels.cuh"
+
+#define E1B200_VERSION "e1b200 0.1 (sm_100a)"
+
+struct e1b200_ctx {
+    e1b200_config cfg;
+    double delt;        /* 1/fs, as the reference computes it (src/galileo-sdr.cpp:162) */
+    int tile;           /* samples per planner checkpoint / synthesis tile              */
+    int groups;         /* tile / 1024                                                  */
+    int tiles_per_epoch;
+    int batch_epochs;   /* epochs per internal pass (bounds scratch)                    */
+    int sm_count, ctas_per_sm, smem_bytes;
+    int use_bulk, amb_scale;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t ev_buf[2], ev_copy[2];
+    std::vector<cudaEvent_t> ev_pass; /* 3 per pass of the current call: plan start, plan end, synth end */
+    int n_pass;
+    uint32_t *d_codes;
+    int32_t *d_lut;
+    double *d_phase;
+    unsigned long long *d_counters;
+    e1_tile_ck *d_ck;
+    e1_epoch_rec *d_recs;     /* staging for the host entry points / restate output */
+    e1_range_rec *d_ranges;
+    int16_t *d_out[2];        /* staging for the host entry points */
+    size_t out_cap;           /* bytes per staging buffer */
+    e1b200_timing timing;
+    unsigned long long counters[2];
+    char err[256];
+};
+
+static int fail(e1b200_ctx *c, int code, const char *what, cudaError_t ce)
+{
+    if (c) {
+        if (ce != cudaSuccess)
+            snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(ce));
+        else
+            snprintf(c->err, sizeof c->err, "%s", what);
+    }
+    return code;
+}
+#define CK(call)                                                                                                       \
+    do {                                                                                                               \
+        cudaError_t ce_ = (call);                                                                                      \
+        if (ce_ != cudaSuccess)                                                                                        \
+            return fail(ctx, E1B200_ECUDA, #call, ce_);                                                                \
+    } while (0)
+
+/* include/constants.h:216-284: round(250*cos(2*pi*(i+1/2)/512)), except the four entries per
+ * table whose exact value is +-105.5, which the reference stores as +-105 */
+static void build_lut(int32_t *lut)
+{
+    static const int cos_fix[4] = {92, 163, 348, 419}, sin_fix[4] = {35, 220, 291, 476};
+    int c[512], s[512];
+    for (int i = 0; i < 512; i++) {
+        double a = 6.283185307179586476925286766559 * ((double)i + 0.5) / 512.0;
+        c[i] = (int)lround(250.0 * cos(a));
+        s[i] = (int)lround(250.0 * sin(a));
+    }
+    for (int k = 0; k < 4; k++) {
+        c[cos_fix[k]] = c[cos_fix[k]] > 0 ? 105 : -105;
+        s[sin_fix[k]] = s[sin_fix[k]] > 0 ? 105 : -105;
+    }
+    for (int i = 0; i < 512; i++) {
+        lut[i] = 2 * (c[i] + 65536 * s[i]);
+        int r = (-i) & 511;
+        lut[512 + i] = 2 * (c[r] + 65536 * s[r]);
+    }
+}
+
+/* src/gal-sig.cpp:9-233 without the BOC expansion: 2 bits per chip (E1-B, E1-C), set = level -1 */
+static void build_codes(uint32_t *codes)
+{
+    memset(codes, 0, E1_CODES_BYTES);
+    for (int p = 0; p < E1C_N_PRN; p++)
+        for (int c = 0; c < E1_CODE_LEN; c++) {
+            uint32_t b = (E1B_PRN_WORDS[p][c >> 5] >> (31 - (c & 31))) & 1u;
+            uint32_t q = (E1C_PRN_WORDS[p][c >> 5] >> (31 - (c & 31))) & 1u;
+            codes[p * E1_CODE_WORDS_PER_PRN + (c >> 4)] |= (b | (q << 1)) << ((c & 15) * 2);
+        }
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+typedef void (*synth_fn)(const e1_synth_args);
+static synth_fn synth_for(int groups)
+{
+    switch (groups) {
+    case 1: return e1_synth_kernel<1>;
+    case 2: return e1_synth_kernel<2>;
+    case 4: return e1_synth_kernel<4>;
+    default: return nullptr;
+    }
+}
+
+extern "C" {
+
+const char *e1b200_version(void) { return E1B200_VERSION; }
+
+const char *e1b200_last_error(e1b200_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
+{
+    if (!cfg || !out)
+        return E1B200_EINVAL;
+    *out = nullptr;
+    if (!(cfg->fs_hz > 0.0) || cfg->samples_per_epoch < 1 || cfg->max_chan < 1 || cfg->max_chan > E1B200_MAX_CHAN)
+        return E1B200_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device || cfg->device < 0)
+        return E1B200_ENODEV;
+    e1b200_ctx *ctx = new (std::nothrow) e1b200_ctx();
+    if (!ctx)
+        return E1B200_ENOMEM;
+    ctx->cfg = *cfg;
+    if (ctx->cfg.dt_epoch == 0.0)
+        ctx->cfg.dt_epoch = 0.10000002314200000; /* src/galileo-sdr.cpp:347 */
+    ctx->delt = 1.0 / cfg->fs_hz;
+    /* one code period must not fit twice in a tile: tile * (1.023e6+margin)/fs < 4092 */
+    int groups = 4;
+    while (groups > 1 && (double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
+        groups >>= 1;
+    if ((double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0) {
+        delete ctx;
+        return E1B200_EINVAL; /* fs below ~0.27 MS/s */
+    }
+    groups = env_int("E1B200_GROUPS", groups);
+    if (!synth_for(groups)) {
+        delete ctx;
+        return E1B200_EINVAL;
+    }
+    ctx->groups = groups;
+    ctx->tile = groups * E1_GROUP;
+    ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
+    ctx->use_bulk = env_int("E1B200_NO_TMA", 0) ? 0 : 1;
+    ctx->amb_scale = env_int("E1B200_AMB_SCALE", 1);
+    if (ctx->amb_scale < 1)
+        ctx->amb_scale = 1;
+    size_t epoch_bytes = (size_t)cfg->samples_per_epoch * 4;
+    size_t target = (size_t)env_int("E1B200_BATCH_MB", 128) << 20;
+    long be = (long)(target / epoch_bytes);
+    ctx->batch_epochs = be < 1 ? 1 : (be > 512 ? 512 : (int)be);
+
+    if (cudaSetDevice(cfg->device) != cudaSuccess) {
+        delete ctx;
+        return E1B200_ENODEV;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+        delete ctx;
+        return E1B200_ENODEV;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + cfg->max_chan * (int)sizeof(e1_chan_par);
+    *out = ctx; /* from here on errors leave a context the caller can query and destroy */
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_buf[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+    }
+    synth_fn fn = synth_for(groups);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, E1_SYNTH_THREADS, ctx->smem_bytes));
+    if (occ < 1)
+        return fail(ctx, E1B200_ECUDA, "synthesis kernel does not fit on this device", cudaSuccess);
+    ctx->ctas_per_sm = env_int("E1B200_CTAS_PER_SM", occ);
+
+    uint32_t *h_codes = (uint32_t *)malloc(E1_CODES_BYTES);
+    int32_t h_lut[E1_LUT_ENTRIES];
+    if (!h_codes)
+        return fail(ctx, E1B200_ENOMEM, "host alloc", cudaSuccess);
+    build_codes(h_codes);
+    build_lut(h_lut);
+    CK(cudaMalloc(&ctx->d_codes, E1_CODES_BYTES));
+    CK(cudaMalloc(&ctx->d_lut, E1_LUT_BYTES));
+    CK(cudaMalloc(&ctx->d_phase, sizeof(double) * E1B200_MAX_CHAN));
+    CK(cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMemcpy(ctx->d_codes, h_codes, E1_CODES_BYTES, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_lut, h_lut, E1_LUT_BYTES, cudaMemcpyHostToDevice));
+    free(h_codes);
+    CK(cudaMemset(ctx->d_phase, 0, sizeof(double) * E1B200_MAX_CHAN));
+    CK(cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * (size_t)ctx->batch_epochs * ctx->tiles_per_epoch * cfg->max_chan));
+    return E1B200_OK;
+}
+
+int e1b200_destroy(e1b200_ctx *ctx)
+{
+    if (!ctx)
+        return E1B200_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream)
+        cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->d_codes);
+    cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_phase);
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_ck);
+    cudaFree(ctx->d_recs);
+    cudaFree(ctx->d_ranges);
+    cudaFree(ctx->d_out[0]);
+    cudaFree(ctx->d_out[1]);
+    for (cudaEvent_t ev : ctx->ev_pass)
+        cudaEventDestroy(ev);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_buf[i]) cudaEventDestroy(ctx->ev_buf[i]);
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return E1B200_OK;
+}
+
+/* allocateChannel() effects (src/channel.cpp:69-99): the slot's carrier phase is (re)initialised.
+ * The PRN itself travels in every epoch record, as chan[i].prn does in the reference. */
+int e1b200_set_channel(e1b200_ctx *ctx, int slot, int prn, double carr_phase0)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.max_chan || prn < 1 || prn > E1_N_PRN_CODES)
+        return E1B200_EINVAL;
+    return e1b200_set_carrier_phase(ctx, slot, carr_phase0);
+}
+
+/* src/channel.cpp:112-119: the slot goes idle; its phase is dead state. */
+int e1b200_clear_channel(e1b200_ctx *ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.max_chan)
+        return E1B200_EINVAL;
+    return e1b200_set_carrier_phase(ctx, slot, 0.0);
+}
+
+int e1b200_set_carrier_phase(e1b200_ctx *ctx, int slot, double phase)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.max_chan || !(fabs(phase) < 1.0))
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaMemcpyAsync(ctx->d_phase + slot, &phase, sizeof phase, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); /* &phase is a stack address */
+    return E1B200_OK;
+}
+
+int e1b200_get_carrier_phase(e1b200_ctx *ctx, int slot, double *out)
+{
+    if (!ctx || !out || slot < 0 || slot >= ctx->cfg.max_chan)
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaMemcpyAsync(out, ctx->d_phase + slot, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return E1B200_OK;
+}
+
+/* enqueue planner + synthesis for n (<= batch_epochs) epochs whose records are on the device */
+static int enqueue_pass(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int16_t *d_out)
+{
+    const e1b200_config *cfg = &ctx->cfg;
+    const int pi = ctx->n_pass++;
+    while ((int)ctx->ev_pass.size() < 3 * (pi + 1)) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        ctx->ev_pass.push_back(ev);
+    }
+    CK(cudaEventRecord(ctx->ev_pass[3 * pi], ctx->stream));
+    int nthr = n * cfg->max_chan;
+    e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
+                                                                     ctx->tile, ctx->tiles_per_epoch, ctx->delt);
+    e1_plan_carr_kernel<<<(cfg->max_chan + 31) / 32, 32, 0, ctx->stream>>>(d_recs, ctx->d_ck, ctx->d_phase, n, cfg->max_chan,
+                                                                         cfg->samples_per_epoch, ctx->tile,
+                                                                         ctx->tiles_per_epoch, ctx->delt);
+    CK(cudaEventRecord(ctx->ev_pass[3 * pi + 1], ctx->stream));
+    e1_synth_args A;
+    A.recs = d_recs;
+    A.ck = ctx->d_ck;
+    A.codes = ctx->d_codes;
+    A.lut = ctx->d_lut;
+    A.out = d_out;
+    A.counters = ctx->d_counters;
+    A.delt = ctx->delt;
+    A.n_epochs = n;
+    A.n_samp = cfg->samples_per_epoch;
+    A.max_chan = cfg->max_chan;
+    A.tile = ctx->tile;
+    A.tiles_per_epoch = ctx->tiles_per_epoch;
+    A.thr_carr = e1_thr_carr(ctx->tile, ctx->amb_scale);
+    A.thr_code = e1_thr_code(ctx->tile, ctx->amb_scale);
+    A.vec_ok = (cfg->samples_per_epoch % 4 == 0) && (((uintptr_t)d_out & 15u) == 0);
+    A.use_bulk = ctx->use_bulk;
+    long total_tiles = (long)n * ctx->tiles_per_epoch;
+    long grid = (long)ctx->sm_count * ctx->ctas_per_sm;
+    if (grid > total_tiles)
+        grid = total_tiles;
+    synth_for(ctx->groups)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
+    CK(cudaEventRecord(ctx->ev_pass[3 * pi + 2], ctx->stream));
+    CK(cudaGetLastError());
+    ctx->timing.kernel_launches += 3;
+    ctx->timing.synth_launches += 1;
+    return E1B200_OK;
+}
+
+static int finish_timing(e1b200_ctx *ctx)
+{
+    float plan = 0, synth = 0, total = 0;
+    for (int pi = 0; pi < ctx->n_pass; pi++) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, ctx->ev_pass[3 * pi], ctx->ev_pass[3 * pi + 1]));
+        CK(cudaEventElapsedTime(&b, ctx->ev_pass[3 * pi + 1], ctx->ev_pass[3 * pi + 2]));
+        plan += a;
+        synth += b;
+    }
+    if (ctx->n_pass)
+        CK(cudaEventElapsedTime(&total, ctx->ev_pass[0], ctx->ev_pass[3 * ctx->n_pass - 1]));
+    ctx->timing.plan_ms = plan;
+    ctx->timing.synth_ms = synth;
+    ctx->timing.total_ms = total;
+    CK(cudaMemcpy(ctx->counters, ctx->d_counters, sizeof ctx->counters, cudaMemcpyDeviceToHost));
+    if (ctx->counters[1]) {
+        CK(cudaMemset(ctx->d_counters, 0, sizeof ctx->counters));
+        return fail(ctx, E1B200_EINVAL, "planner rejected a record (code phase / f_code / ibit out of range, or fs too low for the tile)",
+                    cudaSuccess);
+    }
+    return E1B200_OK;
+}
+
+int e1b200_synth_epochs_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *d_recs, int16_t *d_out)
+{
+    if (!ctx || n_epochs < 0 || (n_epochs && (!d_recs || !d_out)))
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->n_pass = 0;
+    const size_t epoch_i16 = (size_t)ctx->cfg.samples_per_epoch * 2;
+    for (int e0 = 0; e0 < n_epochs; e0 += ctx->batch_epochs) {
+        int n = n_epochs - e0 < ctx->batch_epochs ? n_epochs - e0 : ctx->batch_epochs;
+        int rc = enqueue_pass(ctx, n, d_recs + (size_t)e0 * ctx->cfg.max_chan, d_out + (size_t)e0 * epoch_i16);
+        if (rc)
+            return rc;
+    }
+    return E1B200_OK;
+}
+
+int e1b200_sync(e1b200_ctx *ctx)
+{
+    if (!ctx)
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->timing.kernel_launches)
+        return finish_timing(ctx);
+    return E1B200_OK;
+}
+
+static int ensure_staging(e1b200_ctx *ctx, int want_ranges)
+{
+    const e1b200_config *cfg = &ctx->cfg;
+    size_t nrec = (size_t)ctx->batch_epochs * cfg->max_chan;
+    if (!ctx->d_recs)
+        CK(cudaMalloc(&ctx->d_recs, 2 * nrec * sizeof(e1_epoch_rec)));
+    if (want_ranges && !ctx->d_ranges)
+        CK(cudaMalloc(&ctx->d_ranges, 2 * nrec * sizeof(e1_range_rec)));
+    if (!ctx->d_out[0]) {
+        ctx->out_cap = (size_t)ctx->batch_epochs * cfg->samples_per_epoch * 4;
+        CK(cudaMalloc(&ctx->d_out[0], ctx->out_cap));
+        CK(cudaMalloc(&ctx->d_out[1], ctx->out_cap));
+    }
+    return E1B200_OK;
+}
+
+/* Host-buffer pipeline: records H2D, planner + synthesis on `stream`, D2H on `copy_stream`;
+ * two staging buffers so the copy of pass i overlaps the kernels of pass i+1. */
+static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, const e1_range_rec *ranges, int16_t *out)
+{
+    if (!ctx || n_epochs < 0 || (n_epochs && ((!recs && !ranges) || !out)))
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_staging(ctx, ranges != nullptr);
+    if (rc)
+        return rc;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->n_pass = 0;
+    const e1b200_config *cfg = &ctx->cfg;
+    const size_t epoch_i16 = (size_t)cfg->samples_per_epoch * 2;
+    const size_t nrec_buf = (size_t)ctx->batch_epochs * cfg->max_chan;
+    int pass = 0;
+    for (int e0 = 0; e0 < n_epochs; e0 += ctx->batch_epochs, pass++) {
+        int n = n_epochs - e0 < ctx->batch_epochs ? n_epochs - e0 : ctx->batch_epochs;
+        int b = pass & 1;
+        size_t nrec = (size_t)n * cfg->max_chan;
+        e1_epoch_rec *d_recs = ctx->d_recs + b * nrec_buf;
+        if (pass >= 2) /* staging buffer b is free once its previous D2H finished */
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+        if (ranges) {
+            e1_range_rec *d_rr = ctx->d_ranges + b * nrec_buf;
+            CK(cudaMemcpyAsync(d_rr, ranges + (size_t)e0 * cfg->max_chan, nrec * sizeof(e1_range_rec), cudaMemcpyHostToDevice,
+                               ctx->stream));
+            e1_restate_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, ctx->stream>>>(d_rr, d_recs, (int)nrec, cfg->dt_epoch);
+            ctx->timing.kernel_launches += 1;
+        } else {
+            CK(cudaMemcpyAsync(d_recs, recs + (size_t)e0 * cfg->max_chan, nrec * sizeof(e1_epoch_rec), cudaMemcpyHostToDevice,
+                               ctx->stream));
+        }
+        rc = enqueue_pass(ctx, n, d_recs, ctx->d_out[b]);
+        if (rc)
+            return rc;
+        CK(cudaEventRecord(ctx->ev_buf[b], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_buf[b], 0));
+        CK(cudaMemcpyAsync(out + (size_t)e0 * epoch_i16, ctx->d_out[b], (size_t)n * epoch_i16 * 2, cudaMemcpyDeviceToHost,
+                           ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+    }
+    return e1b200_sync(ctx);
+}
+
+int e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, int16_t *out)
+{
+    return synth_host(ctx, n_epochs, recs, nullptr, out);
+}
+
+int e1b200_synth_ranges(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *recs, int16_t *out)
+{
+    return synth_host(ctx, n_epochs, nullptr, recs, out);
+}
+
+int e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *d_rr, int16_t *d_out)
+{
+    if (!ctx || n_epochs < 0 || (n_epochs && (!d_rr || !d_out)))
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_staging(ctx, 0);
+    if (rc)
+        return rc;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->n_pass = 0;
+    const e1b200_config *cfg = &ctx->cfg;
+    const size_t epoch_i16 = (size_t)cfg->samples_per_epoch * 2;
+    for (int e0 = 0; e0 < n_epochs; e0 += ctx->batch_epochs) {
+        int n = n_epochs - e0 < ctx->batch_epochs ? n_epochs - e0 : ctx->batch_epochs;
+        size_t nrec = (size_t)n * cfg->max_chan;
+        /* single staging slot: stream order keeps pass i+1's restate behind pass i's synthesis */
+        e1_restate_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, ctx->stream>>>(d_rr + (size_t)e0 * cfg->max_chan, ctx->d_recs,
+                                                                                    (int)nrec, cfg->dt_epoch);
+        ctx->timing.kernel_launches += 1;
+        rc = enqueue_pass(ctx, n, ctx->d_recs, d_out + (size_t)e0 * epoch_i16);
+        if (rc)
+            return rc;
+    }
+    return E1B200_OK;
+}
+
+/* computeCodePhase (src/gal-sig.cpp:308-347) for callers that keep the restate on the CPU.
+ * Plain IEEE double operations in the reference's order; this file is compiled with
+ * -fmad=false / -ffp-contract=off so nothing is fused. */
+int e1b200_restate(double rho_prev, double rho_cur, double dt, double grx_sec, double *f_carr, double *f_code,
+                   double *code_phase0, int32_t *ibit0, int32_t *ipage_out)
+{
+    if (!f_carr || !f_code || !code_phase0 || !ibit0 || !(dt > 0.0))
+        return E1B200_EINVAL;
+    const double lambda_e1 = 0.1902936727983649, carr_to_code = 0.0006493506493506494, c_light = 2.99792458e8;
+    volatile double rhorate = (rho_cur - rho_prev) / dt;
+    volatile double fc = -rhorate / lambda_e1;
+    volatile double prod = fc * carr_to_code;
+    *f_carr = fc;
+    *f_code = 1.023e6 + prod;
+    volatile double tof = rho_cur / c_light;
+    volatile double diff = grx_sec - tof;
+    volatile double ms = diff * 1000.0;
+    int ipage = (int)(ms / 2000.0);
+    ms = ms - (double)(ipage * 2000);
+    int ibit = (int)((unsigned int)ms / 4u);
+    ms = ms - (double)(ibit * 4);
+    volatile double q = ms / 4.0;
+    *code_phase0 = q * (double)E1_CODE_LEN;
+    *ibit0 = (ibit + E1_SYM_PER_PAGE / 2) % E1_SYM_PER_PAGE;
+    if (ipage_out)
+        *ipage_out = ipage % 360;
+    return E1B200_OK;
+}
+
+int e1b200_get_timing(e1b200_ctx *ctx, e1b200_timing *out)
+{
+    if (!ctx || !out)
+        return E1B200_EINVAL;
+    *out = ctx->timing;
+    return E1B200_OK;
+}
+
+int e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out)
+{
+    if (!ctx || !out)
+        return E1B200_EINVAL;
+    out->exact_samples = ctx->counters[0];
+    out->planner_errors = ctx->counters[1];
+    out->tile = ctx->tile;
+    out->tiles_per_epoch = ctx->tiles_per_epoch;
+    out->batch_epochs = ctx->batch_epochs;
+    out->sm_count = ctx->sm_count;
+    out->ctas_per_sm = ctx->ctas_per_sm;
+    out->smem_bytes = ctx->smem_bytes;
+    return E1B200_OK;
+}
+
+void *e1b200_stream(e1b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int e1b200_host_alloc(void **p, size_t bytes)
+{
+    if (!p)
+        return E1B200_EINVAL;
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? E1B200_OK : E1B200_ENOMEM;
+}
+
+int e1b200_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? E1B200_OK : E1B200_ECUDA; }
+
+} /* extern "C" */

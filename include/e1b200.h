@@ -131,6 +131,18 @@ int  e1b200_restate(double rho_prev, double rho_cur, double dt, double grx_sec,
                     double *f_carr, double *f_code, double *code_phase0, int32_t *ibit0, int32_t *ipage);
 
 int  e1b200_get_timing(e1b200_ctx *ctx, e1b200_timing *out);
+
+/* Exactness bookkeeping and launch geometry (for tests, bench and profiles).                */
+typedef struct e1b200_stats {
+    uint64_t exact_samples;    /* channel-samples the closed form flagged as ambiguous and the
+                                  exact walk resolved, cumulative since create                    */
+    uint64_t planner_errors;   /* records the planner rejected, cumulative                        */
+    int32_t tile;              /* samples per planner checkpoint / synthesis tile                 */
+    int32_t tiles_per_epoch;
+    int32_t batch_epochs;      /* epochs per internal pass                                        */
+    int32_t sm_count, ctas_per_sm, smem_bytes;
+} e1b200_stats;
+int  e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out);
 void *e1b200_stream(e1b200_ctx *ctx);          /* cudaStream_t the context launches on           */
 const char *e1b200_last_error(e1b200_ctx *ctx);
 const char *e1b200_version(void);

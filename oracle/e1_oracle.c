@@ -158,50 +158,73 @@ void e1o_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs,
 }
 
 /* ---- multi-threaded variant: the reference is single-threaded; this spreads channels over
- * host threads so the CPU baseline can use every core the box has.                         */
+ * host threads so the CPU baseline can use every core the box has.  Per epoch: every thread
+ * synthesises its channels into a private int32 block, barrier, every thread sums a slice of
+ * samples over all private blocks and casts to int16 (integer addition is associative, so the
+ * bytes equal the serial version's), barrier.                                                */
 typedef struct {
     double delt;
-    int n_samp, max_chan, n_epochs, c0, c1;
+    int n_samp, max_chan, n_epochs, n_threads, tid, c0, c1;
     const e1_epoch_rec *recs;
     double *carr_phase;
-    int *acc; /* [n_epochs][2*n_samp] private */
+    int **acc; /* [n_threads] -> private [2*n_samp] */
+    int16_t *out;
+    pthread_barrier_t *bar;
 } mt_job;
 
 static void *mt_worker(void *arg)
 {
     mt_job *j = (mt_job *)arg;
-    for (int e = 0; e < j->n_epochs; e++)
-        synth_epoch_channels(j->delt, j->n_samp, j->recs + (size_t)e * j->max_chan, j->c0, j->c1,
-                             j->carr_phase, j->acc + (size_t)e * 2 * j->n_samp);
+    const size_t len = 2 * (size_t)j->n_samp;
+    const size_t k0 = len * (size_t)j->tid / (size_t)j->n_threads, k1 = len * (size_t)(j->tid + 1) / (size_t)j->n_threads;
+    int *mine = j->acc[j->tid];
+    for (int e = 0; e < j->n_epochs; e++) {
+        memset(mine, 0, sizeof(int) * len);
+        synth_epoch_channels(j->delt, j->n_samp, j->recs + (size_t)e * j->max_chan, j->c0, j->c1, j->carr_phase, mine);
+        pthread_barrier_wait(j->bar);
+        int16_t *o = j->out + (size_t)e * len;
+        for (size_t k = k0; k < k1; k++) {
+            int s = 0;
+            for (int t = 0; t < j->n_threads; t++)
+                s += j->acc[t][k];
+            o[k] = (short)s;
+        }
+        pthread_barrier_wait(j->bar);
+    }
     return NULL;
 }
 
 void e1o_synth_epochs_mt(double fs_hz, int n_samp, int max_chan, int n_epochs,
                          const e1_epoch_rec *recs, double *carr_phase, int16_t *out, int n_threads)
 {
-    if (n_threads < 1) n_threads = 1;
+    if (max_chan < 1 || n_samp < 1)
+        return;
     if (n_threads > max_chan) n_threads = max_chan;
-    size_t per = (size_t)n_epochs * 2 * n_samp;
+    if (n_threads < 1) n_threads = 1;
+    for (int c = 0; c < max_chan; c++) /* build the shared tables before the threads start */
+        for (int e = 0; e < n_epochs; e++)
+            if (recs[(size_t)e * max_chan + c].prn > 0)
+                codes_for(recs[(size_t)e * max_chan + c].prn);
     mt_job *jobs = (mt_job *)calloc((size_t)n_threads, sizeof *jobs);
     pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof *th);
+    int **acc = (int **)calloc((size_t)n_threads, sizeof *acc);
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, NULL, (unsigned)n_threads);
+    for (int t = 0; t < n_threads; t++)
+        acc[t] = (int *)malloc(sizeof(int) * 2 * (size_t)n_samp);
     for (int t = 0; t < n_threads; t++) {
         mt_job *j = &jobs[t];
         j->delt = 1.0 / fs_hz; j->n_samp = n_samp; j->max_chan = max_chan; j->n_epochs = n_epochs;
+        j->n_threads = n_threads; j->tid = t;
         j->c0 = (int)((long)max_chan * t / n_threads);
         j->c1 = (int)((long)max_chan * (t + 1) / n_threads);
-        j->recs = recs; j->carr_phase = carr_phase;
-        j->acc = (int *)calloc(per, sizeof(int));
+        j->recs = recs; j->carr_phase = carr_phase; j->acc = acc; j->out = out; j->bar = &bar;
         pthread_create(&th[t], NULL, mt_worker, j);
     }
     for (int t = 0; t < n_threads; t++)
         pthread_join(th[t], NULL);
-    for (size_t k = 0; k < per; k++) {
-        int s = 0;
-        for (int t = 0; t < n_threads; t++)
-            s += jobs[t].acc[k];
-        out[k] = (short)s;
-    }
+    pthread_barrier_destroy(&bar);
     for (int t = 0; t < n_threads; t++)
-        free(jobs[t].acc);
-    free(jobs); free(th);
+        free(acc[t]);
+    free(acc); free(jobs); free(th);
 }

@@ -98,6 +98,67 @@ def oracle_restate(rho_prev, rho_cur, dt, grx_sec):
     return f[0].value, f[1].value, f[2].value, ib.value, ip.value
 
 
+# ----------------------------------------------------------------------------- hostsim loader
+_hostsim = None
+HOSTSIM_DIR = Path(__file__).resolve().parent / "hostsim"
+
+
+def hostsim():
+    """tests/hostsim/libe1hostsim.so: the product's exact-arithmetic header (csrc/e1_core.h) compiled
+    for the host and driven like the kernels drive it.  Test scaffolding for GPU-less boxes."""
+    global _hostsim
+    if _hostsim is None:
+        so, src = HOSTSIM_DIR / "libe1hostsim.so", HOSTSIM_DIR / "hostsim.cpp"
+        deps = [src, PKG / "csrc" / "e1_core.h", ROOT / "include" / "e1b200.h"]
+        if not so.exists() or any(so.stat().st_mtime < d.stat().st_mtime for d in deps):
+            subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra",
+                                   "-o", str(so), str(src)])
+        hs = C.CDLL(str(so))
+        hs.hs_carr_advance.restype = C.c_double
+        hs.hs_carr_advance.argtypes = [C.c_double, C.c_double, C.c_long, C.c_long]
+        hs.hs_carr_literal.restype = C.c_double
+        hs.hs_carr_literal.argtypes = [C.c_double, C.c_double, C.c_long]
+        hs.hs_code_advance.restype = C.c_double
+        hs.hs_code_advance.argtypes = [C.c_double, C.c_double, C.c_long, C.POINTER(C.c_long)]
+        hs.hs_code_literal.restype = C.c_double
+        hs.hs_code_literal.argtypes = [C.c_double, C.c_double, C.c_long, C.POINTER(C.c_long)]
+        hs.hs_to_fixed.restype = C.c_ulonglong
+        hs.hs_to_fixed.argtypes = [C.c_double, C.c_int]
+        hs.hs_build_codes.argtypes = [C.c_void_p]
+        hs.hs_synth_epochs.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _hostsim = hs
+    return _hostsim
+
+
+def product_lut():
+    """int32[1024] carrier table in the product's layout, built from the ORACLE's tables."""
+    c, s = (C.c_int * 512)(), (C.c_int * 512)()
+    oracle().e1o_carrier_lut(c, s)
+    c, s = np.array(c), np.array(s)
+    lut = np.zeros(1024, np.int32)
+    i = np.arange(512)
+    lut[:512] = 2 * (c + 65536 * s)
+    r = (-i) & 511
+    lut[512:] = 2 * (c[r] + 65536 * s[r])
+    return lut
+
+
+def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1):
+    """Same contract as oracle_synth, through the product's core header on the host.
+    Returns (int16 [n_epochs*n_samp, 2], final phases, stats[3])."""
+    recs = np.ascontiguousarray(recs)
+    n_epochs, max_chan = recs.shape
+    ph = np.zeros(max_chan) if carr_phase is None else np.array(carr_phase, dtype=np.float64)
+    out = np.zeros((n_epochs * n_samp, 2), np.int16)
+    st = np.zeros(3, np.uint64)
+    lut = product_lut()
+    rc = hostsim().hs_synth_epochs(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, out.ctypes.data,
+                                   groups, amb_scale, lut.ctypes.data, st.ctypes.data)
+    assert rc == 0, f"hostsim planner errors: {st}"
+    return out, ph, st
+
+
 # ------------------------------------------------------------------- reference trace -> recs
 def trace_to_recs(trace, max_chan):
     """Channel-state trace of the reference (oracle/ref_hooks) -> e1_epoch_rec[n_epochs][max_chan].
@@ -165,4 +226,77 @@ def synthetic_recs(n_epochs, n_chan, fs_hz, seed=0, max_chan=None, f_max=4000.0)
                 r["carr_phase_init"] = ph0[c]
             if ib + 25 >= 500:  # the page turns inside (or at the end of) this epoch
                 cur[c], nxt[c] = nxt[c], page()
+    return recs
+
+
+def synthetic_ranges(n_epochs, n_chan, seed=0, max_chan=None, dt=REF_DT, grx0=43200.0):
+    """Pseudorange-level synthetic inputs for the device-side restate (BASELINE config 4): per channel a
+    range of ~2.3e7 m with a range rate of +-800 m/s and a small acceleration; pages as in synthetic_recs.
+    Returns (RANGE_DTYPE [n_epochs, max_chan], REC_DTYPE [n_epochs, max_chan] restated by the ORACLE)."""
+    rng = np.random.default_rng(seed)
+    max_chan = max_chan or n_chan
+    rr = np.zeros((n_epochs, max_chan), RANGE_DTYPE)
+    recs = np.zeros((n_epochs, max_chan), REC_DTYPE)
+    sync = np.array([0, 1, 0, 1, 1, 0, 0, 0, 0, 0], np.uint8)
+    rho0 = rng.uniform(2.2e7, 2.6e7, n_chan)
+    v = rng.uniform(-800, 800, n_chan)
+    a = rng.uniform(-0.5, 0.5, n_chan)
+    ph0 = rng.uniform(0, 1, n_chan)
+
+    def page():
+        return pack_page(np.concatenate([sync, rng.integers(0, 2, 240), sync, rng.integers(0, 2, 240)]).astype(np.uint8))
+
+    cur = [page() for _ in range(n_chan)]
+    nxt = [page() for _ in range(n_chan)]
+    for e in range(n_epochs):
+        t0, t1 = e * dt, (e + 1) * dt
+        for c in range(n_chan):
+            r = rr[e, c]
+            r["prn"] = (c % 50) + 1
+            r["rho_prev"] = rho0[c] + v[c] * t0 + 0.5 * a[c] * t0 * t0
+            r["rho_cur"] = rho0[c] + v[c] * t1 + 0.5 * a[c] * t1 * t1
+            r["grx_sec"] = grx0 + t1
+            fc, fcode, cp, ib, _ = oracle_restate(float(r["rho_prev"]), float(r["rho_cur"]), dt, float(r["grx_sec"]))
+            o = recs[e, c]
+            o["prn"], o["ibit0"], o["code_phase0"], o["f_code"], o["f_carr"] = r["prn"], ib, cp, fcode, fc
+            if e == 0:
+                r["flags"] = o["flags"] = E1_REC_SET_PHASE
+                r["carr_phase_init"] = o["carr_phase_init"] = ph0[c]
+            r["page_cur"], r["page_next"] = cur[c], nxt[c]
+            o["page_cur"], o["page_next"] = cur[c], nxt[c]
+            if ib + 26 >= 500:
+                cur[c], nxt[c] = nxt[c], page()
+    return rr, recs
+
+
+def synthetic_recs_fast(n_epochs, n_chan, fs_hz, seed=0, max_chan=None, f_max=4000.0):
+    """Vectorised generator with the SURVEY.md section 8(d) distribution, for bench-size inputs
+    (thousands of epochs).  Not sample-identical to synthetic_recs(); same statistics."""
+    rng = np.random.default_rng(seed)
+    max_chan = max_chan or n_chan
+    recs = np.zeros((n_epochs, max_chan), REC_DTYPE)
+    e = np.arange(n_epochs)[:, None]
+    f0 = rng.uniform(-f_max, f_max, n_chan)[None, :]
+    f = f0 + rng.uniform(-0.1, 0.1, (n_epochs, n_chan)) * (e + 1)
+    ib0 = rng.integers(0, 500, n_chan)[None, :]
+    ib = (ib0 + 25 * e) % 500
+    v = recs[:, :n_chan]
+    v["prn"] = (np.arange(n_chan) % 50 + 1)[None, :]
+    v["ibit0"] = ib
+    v["code_phase0"] = (rng.uniform(0, 4092, n_chan)[None, :] + 0.024 * e) % 4092
+    v["f_carr"] = f
+    v["f_code"] = 1.023e6 + f * 0.0006493506493506494
+    v["flags"][0, :] = E1_REC_SET_PHASE
+    v["carr_phase_init"][0, :] = rng.uniform(0, 1, n_chan)
+    sync = np.array([0, 1, 0, 1, 1, 0, 0, 0, 0, 0], np.uint8)
+    # a page lasts 20 epochs; page k of a channel is in force while floor((ib0 + 25 e) / 500) == k
+    pidx = (ib0 + 25 * e) // 500
+    n_pages = int(pidx.max()) + 2
+    sym = rng.integers(0, 2, (n_chan, n_pages, 500), dtype=np.uint8)
+    sym[:, :, 0:10] = sync
+    sym[:, :, 250:260] = sync
+    packed = np.packbits(np.concatenate([sym, np.zeros((n_chan, n_pages, 12), np.uint8)], axis=2), axis=2, bitorder="little")
+    c = np.arange(n_chan)[None, :]
+    v["page_cur"] = packed[c, pidx]
+    v["page_next"] = packed[c, pidx + 1]
     return recs

@@ -1,0 +1,82 @@
+"""The C-ABI shared library: it loads, exports every entry point include/e1b200.h declares, its
+structs have the documented sizes, and its host-side restate equals the oracle's.  No kernel is
+launched here (this file runs on boxes without a GPU)."""
+import ctypes as C
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import e1util as U
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "galileo-sdr-sim_b200"))
+import build as B  # noqa: E402
+import e1b200 as E  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build_lib()
+    return E.load()
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "e1b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(e1b200_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(E.SYMBOLS)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(E.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (e1b200_\w+)", out))
+    assert exported == set(names)
+
+
+def test_library_contains_sm100a_kernels_and_no_oracle(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", str(E.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    syms = subprocess.run(["nm", "-D", str(E.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "e1o_" not in syms          # the CPU oracle is not linked into the product
+    assert "libe1oracle" not in subprocess.run(["ldd", str(E.LIB_PATH)], capture_output=True, text=True).stdout
+
+
+def test_struct_layouts_match_header():
+    assert E.REC_DTYPE.itemsize == 176 and E.RANGE_DTYPE.itemsize == 168
+    assert E.REC_DTYPE == U.REC_DTYPE and E.RANGE_DTYPE == U.RANGE_DTYPE
+    assert C.sizeof(E.Config) == 32 and C.sizeof(E.Timing) == 20 and C.sizeof(E.Stats) == 40
+
+
+def test_host_restate_equals_oracle(lib):
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        rho0 = rng.uniform(2.0e7, 2.8e7)
+        rho1 = rho0 + rng.uniform(-90, 90)
+        grx = rng.uniform(0, 604800)
+        assert E.restate(rho0, rho1, U.REF_DT, grx) == U.oracle_restate(rho0, rho1, U.REF_DT, grx)
+
+
+def test_version_and_argument_checks(lib):
+    assert b"sm_100a" in lib.e1b200_version()
+    h = C.c_void_p()
+    bad = E.Config(2.6e6, 260000, 0, 0, 0, 0.0)
+    assert lib.e1b200_create(C.byref(bad), C.byref(h)) == -1 and not h.value      # E1B200_EINVAL
+    bad = E.Config(2.6e6, 260000, 65, 0, 0, 0.0)
+    assert lib.e1b200_create(C.byref(bad), C.byref(h)) == -1
+    assert lib.e1b200_destroy(None) == -1
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(E.E1B200Error):
+        E.Synth(2.6e6, 260000, 16)

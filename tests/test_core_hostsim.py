@@ -1,0 +1,154 @@
+"""Host-side checks of the product's exact arithmetic (galileo-sdr-sim_b200/csrc/e1_core.h): the
+binade-jump walkers against the literal reference recurrences, and the whole
+planner -> closed form -> ambiguity fallback chain against the CPU oracle and the reference's
+golden blocks.  Runs without a GPU (the header is compiled for the host by tests/hostsim)."""
+import ctypes as C
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import e1util as U
+
+GOLD = Path(__file__).parent / "golden"
+FS26 = U.fs_as_reference(2.6e6)
+FS25 = U.fs_as_reference(25e6)
+
+
+def test_carrier_walker_equals_literal_loop():
+    hs = U.hostsim()
+    rng = np.random.default_rng(11)
+    for fs in (FS26, FS25):
+        delt = 1.0 / fs
+        for i in range(150):
+            f = rng.uniform(-5000, 5000) if i % 3 else rng.uniform(-20, 20)
+            if i % 50 == 0:
+                f = 0.0
+            sp = f * delt
+            phi = rng.uniform(-1, 1) if i % 2 else rng.uniform(0, 1) * (1 if f >= 0 else -1)
+            n = int(rng.integers(1, 400000))
+            assert hs.hs_carr_advance(phi, sp, 0, n) == hs.hs_carr_literal(phi, sp, n), (fs, f, phi, n)
+
+
+def test_carrier_walker_ties_and_sign_changes():
+    """Steps with many trailing zero bits make exact half-ulp ties in several binades; opposite signs of
+    phase and Doppler walk the magnitude down through zero."""
+    hs = U.hostsim()
+    for sp in (2.0 ** -10, 2.0 ** -10 + 2.0 ** -53, 3 * 2.0 ** -12, 2.0 ** -9 + 2.0 ** -54, 1e-3, 0.25, 0.499, 2.0 ** -60, 1e-300):
+        for phi in (0.0, 0.3, 0.999999, 2.0 ** -30, 0.5 + 2.0 ** -53, 1 - 2.0 ** -53):
+            for s in (1, -1):
+                for ps in (1, -1):
+                    n = 50003
+                    assert hs.hs_carr_advance(ps * phi, s * sp, 0, n) == hs.hs_carr_literal(ps * phi, s * sp, n), (sp, phi, s, ps)
+
+
+def test_code_walker_equals_literal_loop():
+    hs = U.hostsim()
+    rng = np.random.default_rng(12)
+    for fs in (FS26, FS25, 4.0e6):
+        delt = 1.0 / fs
+        for i in range(150):
+            f = rng.uniform(-5000, 5000)
+            sc = (1.023e6 + f * 0.0006493506493506494) * delt
+            cp = rng.uniform(0, 4092) if i % 5 else rng.uniform(0, 1e-6)
+            n = int(rng.integers(1, 400000))
+            w1, w2 = C.c_long(), C.c_long()
+            a = hs.hs_code_advance(cp, sc, n, w1)
+            b = hs.hs_code_literal(cp, sc, n, w2)
+            assert a == b and w1.value == w2.value, (fs, f, cp, n)
+
+
+def test_fixed_point_conversion():
+    hs = U.hostsim()
+    assert hs.hs_to_fixed(0.5, 64) == 1 << 63
+    assert hs.hs_to_fixed(-0.25, 64) == 1 << 62
+    assert hs.hs_to_fixed(4091.5, 52) == int(4091.5 * 2 ** 52)
+    assert hs.hs_to_fixed(1e-30, 64) == 0
+    assert hs.hs_to_fixed(2.0 ** -64, 64) == 1
+    x = 0.123456789012345678
+    assert hs.hs_to_fixed(x, 64) == int(x * 2 ** 64)
+
+
+def test_code_table_matches_oracle_halfchips():
+    """2-bit chip table (product layout) -> the oracle's 8184-entry BOC(1,1) tables, all 50 PRNs."""
+    hs = U.hostsim()
+    codes = np.zeros(50 * 256, np.uint32)
+    hs.hs_build_codes(codes.ctypes.data)
+    lib = U.oracle()
+    t = (C.c_short * 8184)()
+    c = np.arange(4092)
+    for prn in range(1, 51):
+        w = codes[(prn - 1) * 256 + (c >> 4)] >> ((c & 15) * 2)
+        for is_c in (0, 1):
+            lib.e1o_halfchip_table(prn, is_c, t)
+            chip = 1 - 2 * ((w >> is_c) & 1).astype(np.int64)
+            ref = np.array(t)
+            assert np.array_equal(ref[1::2], chip) and np.array_equal(ref[0::2], -chip), (prn, is_c)
+
+
+@pytest.mark.parametrize("name,epochs", [("cfg1", (0, 1, 2, 28, 29, 30, 98)), ("paris45", (0, 1, 190, 191, 300, 301, 448))])
+def test_pipeline_matches_reference_blocks(name, epochs):
+    """Planner + closed form + fallback reproduce the reference's own 0.1 s blocks (SHA-256 fixtures
+    generated from oracle/_ref), starting each probe from the reference's traced carrier phase."""
+    z = np.load(GOLD / f"{name}_recs.npz")
+    recs, phase = z["recs"], z["phase"]
+    sha = (GOLD / f"{name}_sha256.txt").read_text().splitlines()[1:]
+    N = 260000
+    for e in epochs:
+        ph = np.where(np.isnan(phase[e]), 0.0, phase[e])
+        out, _, st = U.hostsim_synth(FS26, N, recs[e:e + 1], ph)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == sha[e], (name, e, st)
+
+
+def test_pipeline_carries_phase_like_the_oracle():
+    z = np.load(GOLD / "cfg1_recs.npz")
+    recs = z["recs"][:5]
+    a, pa = U.oracle_synth(FS26, 260000, recs)
+    b, pb, st = U.hostsim_synth(FS26, 260000, recs)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
+    # reference's own traced phase at the top of epoch 4
+    act = recs[4]["prn"] > 0
+    _, p4, _ = U.hostsim_synth(FS26, 260000, recs[:4])
+    assert np.array_equal(p4[act], z["phase"][4][act])
+
+
+@pytest.mark.parametrize("fs,n_samp,n_chan,groups", [(FS26, 26000, 9, 4), (FS25, 250000, 12, 4), (FS25, 100001, 5, 2),
+                                                       (4.0e6, 40000, 3, 1)])
+def test_pipeline_matches_oracle_synthetic(fs, n_samp, n_chan, groups):
+    recs = U.synthetic_recs(4, n_chan, fs, seed=n_chan, max_chan=n_chan + 2)
+    a, pa = U.oracle_synth(fs, n_samp, recs)
+    b, pb, st = U.hostsim_synth(fs, n_samp, recs, groups=groups)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb), st
+
+
+def test_result_independent_of_ambiguity_threshold():
+    """Inflating the ambiguity bound only sends more samples through the exact walk: the output
+    must not change.  This is the check that the closed form and the walk agree where it matters."""
+    recs = U.synthetic_recs(2, 10, FS26, seed=21)
+    a, _ = U.oracle_synth(FS26, 52000, recs)
+    counts = []
+    for scale in (1, 1000, 100000, 10000000):
+        b, _, st = U.hostsim_synth(FS26, 52000, recs, amb_scale=scale)
+        assert np.array_equal(a, b), scale
+        counts.append(int(st[0]))
+    assert counts == sorted(counts) and counts[-1] > counts[0]
+
+
+def test_doppler_sign_flip_and_phase_reset_mid_run():
+    """f_carr changes sign across epochs (phase and Doppler of opposite sign -> magnitude walks down
+    through zero), a channel is re-initialised mid-run, another goes idle and comes back."""
+    fs, N = FS26, 30000
+    recs = U.synthetic_recs(8, 4, fs, seed=33, max_chan=5)
+    for e in range(8):
+        recs[e, 0]["f_carr"] = (3.5 - e) * 700.0          # crosses zero between epochs 3 and 4
+        recs[e, 0]["f_code"] = 1.023e6 + recs[e, 0]["f_carr"] * 0.0006493506493506494
+        recs[e, 1]["f_carr"] = -(3.5 - e) * 0.4           # tiny Doppler, sign flip
+        recs[e, 1]["f_code"] = 1.023e6 + recs[e, 1]["f_carr"] * 0.0006493506493506494
+    recs[5, 2]["flags"] = U.E1_REC_SET_PHASE
+    recs[5, 2]["carr_phase_init"] = 0.987654321
+    recs[2:4, 3]["prn"] = 0                               # idle for two epochs
+    recs[6, 3]["f_carr"] = 0.0
+    a, pa = U.oracle_synth(fs, N, recs)
+    b, pb, st = U.hostsim_synth(fs, N, recs)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb), st
