@@ -402,10 +402,393 @@ E1_HD double e1_plan_carr_epoch(const e1_epoch_rec *r, e1_tile_ck *o, int stride
     return phi;
 }
 
-/* Tile checkpoint + epoch record -> the per-channel parameters the sample loop reads. */
-E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, int tile, e1_chan_par *p)
+/* ------------------------------------------------------------------ parallel carrier planner
+ *
+ * The carrier recurrence is serial over the whole run, but it is *translation invariant*: two
+ * trajectories whose starts differ by D, a multiple of 2^-52 cycle, stay exactly D apart for as
+ * long as every pair of corresponding values lies in the same binade -- every rounding grid
+ * below 1.0 divides 2^-52, so fl(x + D + s) = fl(x + s) + D -- with one exception: a step s that
+ * is a multiple of 2^-53 can make exact ties at the wrap step, whose round-half-even direction
+ * depends on the parity of D (such epochs are walked serially).  Values right after a wrap are multiples of 2^-52.  Hence:
+ *
+ *   drift pass   (parallel, per epoch)   walk each epoch from an *ideal* start phase; the
+ *                                        measured end-start gives that epoch's rounding drift
+ *   estimate     (serial, O(1)/epoch)    prefix of the drifts -> start phase of every epoch to
+ *                                        ~1e-15 cycle
+ *   span pass    (parallel, per epoch)   from a *guessed* post-wrap value at the last wrap of
+ *                                        the previous epoch ("anchor") walk exactly to the end
+ *                                        of the epoch, writing hat checkpoints and the interval
+ *                                        [lo,hi) of translations D for which the walk is valid
+ *   chain        (serial, O(1)/epoch)    D = true anchor value - guess; if lo <= D < hi the
+ *                                        epoch's checkpoints are hat + D, else (rare) the epoch
+ *                                        is walked serially from its true start
+ * Correctness never depends on the guesses, only speed does.                                   */
+#define E1_UNIT_NONE 0   /* slot idle this epoch                                                   */
+#define E1_UNIT_EXACT 1  /* walked from an exactly known start (batch start / E1_REC_SET_PHASE)    */
+#define E1_UNIT_HAT 2    /* walked from a guessed anchor: needs the chain's translation            */
+#define E1_UNIT_SERIAL 3 /* not eligible for a guess: the chain walks it                           */
+
+typedef struct e1_unit { /* one per (epoch, channel), 64 bytes */
+    double anchor_p;  /* HAT: guessed |phase| right after the anchor wrap (multiple of 2^-52)   */
+    double end_phi;   /* signed phase after the epoch's last sample (hat for HAT units)         */
+    double last_p;    /* |phase| right after the last wrap inside this epoch (hat for HAT)      */
+    double lo, hi;    /* HAT: valid translations, lo <= D < hi                                  */
+    int32_t anchor_k; /* HAT: sample index (1..N) of the anchor wrap inside the previous epoch  */
+    int32_t last_k;   /* sample index (1..N) of the last wrap inside this epoch, -1 if none     */
+    int32_t type;
+    int32_t neg;      /* sign of the walk (1: phase <= 0)                                       */
+    double reserved;
+} e1_unit;
+
+typedef struct e1_span_track {
+    double lo, hi;
+    int64_t last_k;
+    double last_p;
+} e1_span_track;
+
+E1_HD double e1_binade_floor(double x) { return e1_from_bits((e1_bits(x) >> 52) << 52); }
+E1_HD double e1_binade_top(double x) { return e1_from_bits(((e1_bits(x) >> 52) + 1) << 52); }
+
+/* x is a nonzero multiple of 2^-53: such a step can land exactly half way between two
+ * representable values at the wrap step (the tie case above) */
+E1_HD int e1_is_multiple_2m53(double x)
 {
-    p->phi = c->phi;
+    int64_t b = e1_bits(x) & 0x7fffffffffffffffLL;
+    int e = (int)(b >> 52);
+    uint64_t m = (uint64_t)(b & 0xfffffffffffffLL);
+    if (e == 0)
+        return 0;
+    m |= 1ULL << 52;
+    int tz = 0;
+    while (!(m & 1ULL)) {
+        m >>= 1;
+        tz++;
+    }
+    /* x = m_odd * 2^(e - 1075 + tz) */
+    return (e - 1075 + tz) >= -53;
+}
+
+/* Aligned-regime walk of the phase magnitude: a in [0,1) grows by t in (0,0.5) per sample and
+ * wraps at 1.0, from sample k to k_end.  Bit-identical to the literal loop (same binade jumps
+ * as e1_walk_up) and in addition
+ *   - writes sign*a to o[(kt/tile)*stride].phi for every tile start kt with k < kt < n_emit
+ *     (o == NULL: no checkpoints),
+ *   - narrows tr->[lo,hi) to the translations that keep every visited value in its binade,
+ *   - records the last wrap in tr->last_k / last_p.                                          */
+E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile, int64_t n_emit, e1_tile_ck *o,
+                          int stride, int neg, e1_span_track *tr)
+{
+    int64_t ti = k / tile + 1; /* next tile index to checkpoint */
+    int64_t kt = o ? ti * (int64_t)tile : (int64_t)0x7fffffffffffffffLL;
+    double lo = tr->lo, hi = tr->hi;
+#define E1_EMIT(val)                                                                                                   \
+    do {                                                                                                               \
+        if (kt < n_emit)                                                                                               \
+            o[(size_t)ti * stride].phi = neg ? -(val) : (val);                                                         \
+        kt += tile;                                                                                                    \
+        ti++;                                                                                                          \
+    } while (0)
+    while (k < k_end) {
+        double x1 = e1_add(a, t);
+        k++;
+        if (x1 >= 1.0) {
+            double m = e1_add(1.0, -x1);
+            if (m > lo)
+                lo = m;
+            a = e1_add(x1, -1.0);
+            tr->last_k = k;
+            tr->last_p = a;
+            if (k == kt)
+                E1_EMIT(a);
+            continue;
+        }
+        {
+            double up = e1_add(e1_binade_top(x1), -x1), dn = e1_add(e1_binade_floor(x1), -x1);
+            if (up < hi)
+                hi = up;
+            if (dn > lo)
+                lo = dn;
+        }
+        a = x1;
+        if (k == kt)
+            E1_EMIT(a);
+        if (k + 1 >= k_end)
+            continue;
+        double x2 = e1_add(x1, t), x3 = e1_add(x2, t);
+        int64_t b1 = e1_bits(x1), b2 = e1_bits(x2), b3 = e1_bits(x3);
+        if ((((b1 ^ b2) | (b1 ^ b3)) >> 52) != 0 || x3 >= 1.0)
+            continue;
+        int64_t d = b3 - b2;
+        int64_t end = ((b1 >> 52) + 1) << 52;
+        int64_t n;
+        k++; /* now at x2 */
+        a = x2;
+        if (k == kt)
+            E1_EMIT(a);
+        if (d == 0)
+            n = k_end - k; /* stuck for good */
+        else {
+            n = (end - 1 - b2) / d;
+            if (n > k_end - k)
+                n = k_end - k;
+        }
+        while (kt <= k + n && kt < n_emit) {
+            double v = e1_from_bits(b2 + (kt - k) * d);
+            E1_EMIT(v);
+        }
+        a = e1_from_bits(b2 + n * d);
+        k += n;
+        {
+            double up = e1_add(e1_from_bits(end), -a);
+            if (up < hi)
+                hi = up;
+        }
+    }
+#undef E1_EMIT
+    tr->lo = lo;
+    tr->hi = hi;
+    return a;
+}
+
+/* One whole epoch from an exactly known start phase (any sign combination): checkpoints are
+ * final.  Returns the phase after the last sample; last_k and last_p describe the last wrap when
+ * the whole epoch ran in the aligned regime (else *last_k = -1).                              */
+E1_HD double e1_carr_epoch_exact(double phi, double sp, int n_samp, int tile, int tiles_per_epoch, e1_tile_ck *o,
+                                 int stride, int32_t *last_k, double *last_p, int32_t *neg_out)
+{
+    const int neg = (phi < 0.0) || (phi == 0.0 && sp < 0.0);
+    const int aligned = (phi == 0.0) || (neg == (sp < 0.0));
+    *last_k = -1;
+    *last_p = 0.0;
+    *neg_out = neg;
+    if (sp == 0.0 || !aligned) {
+        for (int t = 0; t < tiles_per_epoch; t++) {
+            int64_t k0 = (int64_t)t * tile, k1 = k0 + tile;
+            if (k1 > n_samp)
+                k1 = n_samp;
+            o[(size_t)t * stride].phi = phi;
+            phi = e1_carr_advance(phi, sp, k0, k1);
+        }
+        return phi;
+    }
+    e1_span_track tr;
+    tr.lo = -2.0;
+    tr.hi = 2.0;
+    tr.last_k = -1;
+    tr.last_p = 0.0;
+    o[0].phi = phi;
+    double a = e1_span_walk(e1_fabs(phi), e1_fabs(sp), 0, n_samp, tile, n_samp, o, stride, neg, &tr);
+    *last_k = (int32_t)tr.last_k;
+    *last_p = tr.last_p;
+    return neg ? -a : a;
+}
+
+E1_HD int e1_rec_active(const e1_epoch_rec *r) { return r->prn >= 1 && r->prn <= E1C_N_PRN; }
+
+/* phase + whole-epoch advance, folded back into (-1,1) the way :532 does (sign kept) */
+E1_HD double e1_ideal_next(double g, double sp, int n_samp)
+{
+    double v = g + (double)n_samp * sp;
+    if (v >= 1.0)
+        v -= (double)(long long)v;
+    else if (v <= -1.0)
+        v -= (double)(long long)v;
+    return v;
+}
+
+/* K0: ideal (rounding-free, double precision) start phase of every epoch of one channel. */
+E1_HD void e1_v2_ideal_prefix(const e1_epoch_rec *recs, int stride, int n_epochs, double phi0, int n_samp, double delt,
+                              double *g_out)
+{
+    double g = phi0;
+    for (int e = 0; e < n_epochs; e++) {
+        const e1_epoch_rec *r = &recs[(size_t)e * stride];
+        if (e1_rec_active(r) && (r->flags & E1_REC_SET_PHASE))
+            g = r->carr_phase_init;
+        g_out[(size_t)e * stride] = g;
+        if (e1_rec_active(r))
+            g = e1_ideal_next(g, e1_mul(r->f_carr, delt), n_samp);
+    }
+}
+
+/* drift pass: exact walk of one epoch from its ideal start; returns the end phase */
+E1_HD double e1_v2_drift_unit(const e1_epoch_rec *r, double g, int n_samp, double delt)
+{
+    if (!e1_rec_active(r))
+        return g;
+    return e1_carr_advance(g, e1_mul(r->f_carr, delt), 0, n_samp);
+}
+
+/* K1: refined start-phase estimates of one channel.  The drift pass walked epoch e exactly from
+ * the ideal start g[e] to end[e]; the true start est[e] differs from g[e] by a tiny eta, and by
+ * translation the true end is end[e] + eta (to within an ulp or two).                          */
+E1_HD void e1_v2_estimate_prefix(const e1_epoch_rec *recs, int stride, int n_epochs, double phi0, const double *g,
+                                 const double *end, double *est)
+{
+    double cur = phi0;
+    for (int e = 0; e < n_epochs; e++) {
+        const e1_epoch_rec *r = &recs[(size_t)e * stride];
+        const size_t i = (size_t)e * stride;
+        if (e1_rec_active(r) && (r->flags & E1_REC_SET_PHASE))
+            cur = r->carr_phase_init;
+        est[i] = cur;
+        if (!e1_rec_active(r))
+            continue;
+        double eta = cur - g[i];
+        if (eta > 0.5)
+            eta -= 1.0;
+        else if (eta < -0.5)
+            eta += 1.0;
+        cur = end[i] + eta;
+        if (cur >= 1.0)
+            cur -= 1.0;
+        else if (cur <= -1.0)
+            cur += 1.0;
+    }
+}
+
+/* span pass for one (epoch, channel).  recs_ch/est_ch/unit/o point at this channel's epoch e. */
+E1_HD void e1_v2_span_unit(const e1_epoch_rec *r, const e1_epoch_rec *r_prev, int e, double phi_batch_start,
+                           double est_prev, int n_samp, int tile, int tiles_per_epoch, double delt, e1_tile_ck *o,
+                           int stride, e1_unit *u)
+{
+    u->type = E1_UNIT_NONE;
+    u->last_k = -1;
+    u->anchor_k = -1;
+    u->anchor_p = 0.0;
+    u->end_phi = 0.0;
+    u->last_p = 0.0;
+    u->lo = 0.0;
+    u->hi = 0.0;
+    u->neg = 0;
+    u->reserved = 0.0;
+    if (!e1_rec_active(r))
+        return;
+    const double sp = e1_mul(r->f_carr, delt);
+    if (e == 0 || (r->flags & E1_REC_SET_PHASE)) {
+        const double phi = (r->flags & E1_REC_SET_PHASE) ? r->carr_phase_init : phi_batch_start;
+        u->type = E1_UNIT_EXACT;
+        u->end_phi = e1_carr_epoch_exact(phi, sp, n_samp, tile, tiles_per_epoch, o, stride, &u->last_k, &u->last_p, &u->neg);
+        return;
+    }
+    u->type = E1_UNIT_SERIAL;
+    if (!e1_rec_active(r_prev))
+        return;
+    const double sp0 = e1_mul(r_prev->f_carr, delt);
+    if (sp == 0.0 || sp0 == 0.0 || (sp < 0.0) != (sp0 < 0.0))
+        return;
+    if (!(e1_fabs(sp) < 0.5) || !(e1_fabs(sp0) < 0.5))
+        return;
+    if (e1_is_multiple_2m53(sp) || e1_is_multiple_2m53(sp0))
+        return;
+    const int neg = sp < 0.0;
+    if (est_prev != 0.0 && (est_prev < 0.0) != neg)
+        return; /* previous epoch started in the mixed regime */
+    const double a0 = e1_fabs(est_prev), t0 = e1_fabs(sp0), t1 = e1_fabs(sp);
+    if (!(a0 < 1.0))
+        return;
+    /* last wrap of the previous epoch according to the estimate: unwrapped phase a0 + k*t0 */
+    const double total = a0 + (double)n_samp * t0;
+    const double W = (double)(long long)total;
+    if (W < 1.0)
+        return; /* no wrap to anchor on */
+    double kd = (W - a0) / t0;
+    int64_t kL = (int64_t)kd;
+    if ((double)kL < kd)
+        kL++;
+    double p = 0.0;
+    for (int tries = 0; tries < 3; tries++) { /* p = a0 + kL*t0 - W in double-double, want 0 <= p < t0 */
+#if defined(__CUDA_ARCH__)
+        const double hi_ = __dmul_rn((double)kL, t0), lo_ = __fma_rn((double)kL, t0, -hi_);
+#else
+        const double hi_ = (double)kL * t0, lo_ = __builtin_fma((double)kL, t0, -hi_);
+#endif
+        p = ((hi_ - W) + a0) + lo_;
+        if (p < 0.0)
+            kL++;
+        else if (p >= t0)
+            kL--;
+        else
+            break;
+    }
+    if (!(p >= 0.0) || !(p < t0) || kL < 1 || kL > n_samp)
+        return;
+    /* round the guess to the post-wrap grid */
+    const double two52 = 4503599627370496.0;
+    p = (double)(long long)(p * two52 + 0.5) / two52;
+    e1_span_track tr;
+    tr.lo = -p;
+    tr.hi = 2.0;
+    tr.last_k = -1;
+    tr.last_p = 0.0;
+    double a = e1_span_walk(p, t0, kL, n_samp, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
+    if (tr.last_k != -1)
+        return; /* the guessed anchor was not the last wrap after all */
+    o[0].phi = neg ? -a : a;
+    a = e1_span_walk(a, t1, 0, n_samp, tile, n_samp, o, stride, neg, &tr);
+    u->type = E1_UNIT_HAT;
+    u->neg = neg;
+    u->anchor_k = (int32_t)kL;
+    u->anchor_p = p;
+    u->end_phi = neg ? -a : a;
+    u->last_k = (int32_t)tr.last_k;
+    u->last_p = tr.last_p;
+    u->lo = tr.lo;
+    u->hi = tr.hi;
+}
+
+/* chain of one channel: validates HAT units, walks the others, writes the per-epoch translation
+ * delta[e] (signed; the epoch's checkpoints are ck.phi + delta) and returns the final phase.
+ * stats[0] += epochs walked serially, stats[1] += HAT units accepted.                          */
+E1_HD double e1_v2_chain(const e1_epoch_rec *recs, int stride, int n_epochs, double phi0, int n_samp, int tile,
+                         int tiles_per_epoch, double delt, e1_unit *units, e1_tile_ck *ck, size_t ck_epoch_stride,
+                         double *delta, unsigned long long *stats)
+{
+    double phi = phi0;
+    int prev_ok = 0, prev_neg = 0;
+    int32_t prev_k = -1;
+    double prev_p = 0.0;
+    for (int e = 0; e < n_epochs; e++) {
+        const e1_epoch_rec *r = &recs[(size_t)e * stride];
+        e1_unit *u = &units[(size_t)e * stride];
+        delta[(size_t)e * stride] = 0.0;
+        if (u->type == E1_UNIT_NONE) {
+            prev_ok = 0;
+            continue;
+        }
+        if (u->type == E1_UNIT_EXACT) {
+            phi = u->end_phi;
+        } else {
+            int ok = 0;
+            if (u->type == E1_UNIT_HAT && prev_ok && prev_neg == u->neg && prev_k == u->anchor_k) {
+                const double D = e1_add(prev_p, -u->anchor_p);
+                if (D >= u->lo && D < u->hi) {
+                    ok = 1;
+                    delta[(size_t)e * stride] = u->neg ? -D : D;
+                    phi = e1_add(u->end_phi, u->neg ? -D : D);
+                    u->last_p = e1_add(u->last_p, D);
+                    stats[1]++;
+                }
+            }
+            if (!ok) {
+                u->end_phi = e1_carr_epoch_exact(phi, e1_mul(r->f_carr, delt), n_samp, tile, tiles_per_epoch,
+                                                 ck + (size_t)e * ck_epoch_stride, stride, &u->last_k, &u->last_p, &u->neg);
+                phi = u->end_phi;
+                stats[0]++;
+            }
+        }
+        prev_ok = u->last_k >= 1;
+        prev_neg = u->neg;
+        prev_k = u->last_k;
+        prev_p = u->last_p;
+    }
+    return phi;
+}
+
+/* Tile checkpoint + epoch record -> the per-channel parameters the sample loop reads. */
+E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, int tile, double delta, e1_chan_par *p)
+{
+    p->phi = e1_add(c->phi, delta); /* planner translation of this epoch (exact, see e1_v2_chain) */
     p->cp = c->cp;
     p->sp = e1_mul(r->f_carr, delt);
     p->sc = e1_mul(r->f_code, delt);

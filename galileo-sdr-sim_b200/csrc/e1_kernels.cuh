@@ -36,6 +36,7 @@
 struct e1_synth_args {
     const e1_epoch_rec *recs;
     const e1_tile_ck *ck;
+    const double *delta; /* [n_epochs][max_chan] planner translation of each epoch's carrier checkpoints */
     const uint32_t *codes;
     const int32_t *lut;
     int16_t *out;
@@ -93,7 +94,7 @@ __global__ void e1_plan_code_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, in
                        tiles_per_epoch, delt);
 }
 
-/* one thread per channel, serial over the epochs of the call */
+/* serial reference planner (E1B200_CFG_SERIAL_PLANNER): one thread per channel, one exact walk */
 __global__ void e1_plan_carr_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, double *phase, int n_epochs,
                                     int max_chan, int n_samp, int tile, int tiles_per_epoch, double delt)
 {
@@ -105,6 +106,70 @@ __global__ void e1_plan_carr_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, do
         phi = e1_plan_carr_epoch(&recs[(size_t)e * max_chan + ch], ck + (size_t)e * tiles_per_epoch * max_chan + ch,
                                  max_chan, phi, n_samp, tile, tiles_per_epoch, delt);
     phase[ch] = phi;
+}
+
+/* parallel carrier planner (see e1_core.h): K0 ideal prefix, drift pass, K1 estimate prefix, span
+ * pass, chain.  Per-(epoch, channel) kernels map consecutive threads to consecutive epochs of one
+ * channel, so a warp walks similar Dopplers and stays converged.                                  */
+struct e1_plan_args {
+    const e1_epoch_rec *recs;
+    e1_tile_ck *ck;
+    double *phase;   /* [max_chan] carried carrier phase (in: batch start, out: batch end) */
+    double *g, *dend, *est, *delta; /* [n_epochs][max_chan] */
+    e1_unit *units;
+    unsigned long long *counters; /* [2] serial epochs, [3] HAT epochs */
+    double delt;
+    int n_epochs, n_samp, max_chan, tile, tiles_per_epoch;
+};
+
+__global__ void e1_v2_ideal_kernel(const e1_plan_args P)
+{
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < P.max_chan)
+        e1_v2_ideal_prefix(P.recs + ch, P.max_chan, P.n_epochs, P.phase[ch], P.n_samp, P.delt, P.g + ch);
+}
+
+__global__ void e1_v2_drift_kernel(const e1_plan_args P)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_epochs * P.max_chan)
+        return;
+    int ch = i / P.n_epochs, e = i - ch * P.n_epochs;
+    size_t j = (size_t)e * P.max_chan + ch;
+    P.dend[j] = e1_v2_drift_unit(&P.recs[j], P.g[j], P.n_samp, P.delt);
+}
+
+__global__ void e1_v2_estimate_kernel(const e1_plan_args P)
+{
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < P.max_chan)
+        e1_v2_estimate_prefix(P.recs + ch, P.max_chan, P.n_epochs, P.phase[ch], P.g + ch, P.dend + ch, P.est + ch);
+}
+
+__global__ void e1_v2_span_kernel(const e1_plan_args P)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_epochs * P.max_chan)
+        return;
+    int ch = i / P.n_epochs, e = i - ch * P.n_epochs;
+    size_t j = (size_t)e * P.max_chan + ch;
+    e1_v2_span_unit(&P.recs[j], e ? &P.recs[j - P.max_chan] : nullptr, e, P.phase[ch], e ? P.est[j - P.max_chan] : 0.0, P.n_samp,
+                    P.tile, P.tiles_per_epoch, P.delt, P.ck + (size_t)e * P.tiles_per_epoch * P.max_chan + ch, P.max_chan,
+                    &P.units[j]);
+}
+
+__global__ void e1_v2_chain_kernel(const e1_plan_args P)
+{
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= P.max_chan)
+        return;
+    unsigned long long st[2] = {0, 0};
+    P.phase[ch] = e1_v2_chain(P.recs + ch, P.max_chan, P.n_epochs, P.phase[ch], P.n_samp, P.tile, P.tiles_per_epoch, P.delt,
+                              P.units + ch, P.ck + ch, (size_t)P.tiles_per_epoch * P.max_chan, P.delta + ch, st);
+    if (st[0])
+        atomicAdd(&P.counters[2], st[0]);
+    if (st[1])
+        atomicAdd(&P.counters[3], st[1]);
 }
 
 /* ------------------------------------------------------------------ synthesis */
@@ -182,7 +247,7 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS) e1_synth_kernel(const e1_syn
             const e1_tile_ck c = A.ck[(size_t)tile_id * A.max_chan + tid];
             if (c.sym & E1_CK_ACTIVE) {
                 e1_chan_par p;
-                e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + tid], A.delt, A.tile, &p);
+                e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + tid], A.delt, A.tile, A.delta[(size_t)e * A.max_chan + tid], &p);
                 if (c.sym & E1_CK_ERROR)
                     atomicAdd(&s_cnt[1], 1ull);
                 s_par[atomicAdd(&s_nact, 1)] = p;

@@ -25,24 +25,26 @@ struct e1b200_ctx {
     int tile;           /* samples per planner checkpoint / synthesis tile              */
     int groups;         /* tile / 1024                                                  */
     int tiles_per_epoch;
-    int batch_epochs;   /* epochs per internal pass (bounds scratch)                    */
+    int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
+    int plan_epochs;    /* epochs per planner pass (bounds scratch)                     */
     int sm_count, ctas_per_sm, smem_bytes;
-    int use_bulk, amb_scale;
+    int use_bulk, amb_scale, serial_planner;
     cudaStream_t stream, copy_stream;
     cudaEvent_t ev_buf[2], ev_copy[2];
-    std::vector<cudaEvent_t> ev_pass; /* 3 per pass of the current call: plan start, plan end, synth end */
-    int n_pass;
+    std::vector<cudaEvent_t> ev;   /* pairs (start, end) of the current call */
+    std::vector<int> ev_kind;      /* 0 = planner pass, 1 = synthesis launch */
     uint32_t *d_codes;
     int32_t *d_lut;
     double *d_phase;
-    unsigned long long *d_counters;
+    unsigned long long *d_counters; /* [0] exact-fallback samples [1] planner errors [2] serial epochs [3] HAT epochs */
     e1_tile_ck *d_ck;
+    double *d_g, *d_dend, *d_est, *d_delta;
+    e1_unit *d_units;
     e1_epoch_rec *d_recs;     /* staging for the host entry points / restate output */
     e1_range_rec *d_ranges;
     int16_t *d_out[2];        /* staging for the host entry points */
-    size_t out_cap;           /* bytes per staging buffer */
     e1b200_timing timing;
-    unsigned long long counters[2];
+    unsigned long long counters[4];
     char err[256];
 };
 
@@ -127,8 +129,20 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     *out = nullptr;
     if (!(cfg->fs_hz > 0.0) || cfg->samples_per_epoch < 1 || cfg->max_chan < 1 || cfg->max_chan > E1B200_MAX_CHAN)
         return E1B200_EINVAL;
+    /* one code period must not fit twice in a tile: tile * (1.023e6+margin)/fs < 4092 */
+    int groups = 4;
+    while (groups > 1 && (double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
+        groups >>= 1;
+    if ((double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
+        return E1B200_EINVAL; /* fs below ~0.27 MS/s */
+    groups = env_int("E1B200_GROUPS", groups);
+    if (!synth_for(groups))
+        return E1B200_EINVAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device || cfg->device < 0)
+        return E1B200_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(cfg->device) != cudaSuccess || cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
         return E1B200_ENODEV;
     e1b200_ctx *ctx = new (std::nothrow) e1b200_ctx();
     if (!ctx)
@@ -137,19 +151,6 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     if (ctx->cfg.dt_epoch == 0.0)
         ctx->cfg.dt_epoch = 0.10000002314200000; /* src/galileo-sdr.cpp:347 */
     ctx->delt = 1.0 / cfg->fs_hz;
-    /* one code period must not fit twice in a tile: tile * (1.023e6+margin)/fs < 4092 */
-    int groups = 4;
-    while (groups > 1 && (double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
-        groups >>= 1;
-    if ((double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0) {
-        delete ctx;
-        return E1B200_EINVAL; /* fs below ~0.27 MS/s */
-    }
-    groups = env_int("E1B200_GROUPS", groups);
-    if (!synth_for(groups)) {
-        delete ctx;
-        return E1B200_EINVAL;
-    }
     ctx->groups = groups;
     ctx->tile = groups * E1_GROUP;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
@@ -157,20 +158,13 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->amb_scale = env_int("E1B200_AMB_SCALE", 1);
     if (ctx->amb_scale < 1)
         ctx->amb_scale = 1;
-    size_t epoch_bytes = (size_t)cfg->samples_per_epoch * 4;
-    size_t target = (size_t)env_int("E1B200_BATCH_MB", 128) << 20;
-    long be = (long)(target / epoch_bytes);
+    ctx->serial_planner = (cfg->flags & E1B200_CFG_SERIAL_PLANNER) || env_int("E1B200_SERIAL_PLANNER", 0);
+    const size_t epoch_bytes = (size_t)cfg->samples_per_epoch * 4;
+    long be = (long)(((size_t)env_int("E1B200_BATCH_MB", 128) << 20) / epoch_bytes);
     ctx->batch_epochs = be < 1 ? 1 : (be > 512 ? 512 : (int)be);
-
-    if (cudaSetDevice(cfg->device) != cudaSuccess) {
-        delete ctx;
-        return E1B200_ENODEV;
-    }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
-        delete ctx;
-        return E1B200_ENODEV;
-    }
+    const size_t ck_epoch_bytes = sizeof(e1_tile_ck) * (size_t)ctx->tiles_per_epoch * cfg->max_chan;
+    long pe = (long)(((size_t)env_int("E1B200_PLAN_MB", 2048) << 20) / ck_epoch_bytes);
+    ctx->plan_epochs = pe < 1 ? 1 : (pe > 4096 ? 4096 : (int)pe);
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + cfg->max_chan * (int)sizeof(e1_chan_par);
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
@@ -197,13 +191,12 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     CK(cudaMalloc(&ctx->d_codes, E1_CODES_BYTES));
     CK(cudaMalloc(&ctx->d_lut, E1_LUT_BYTES));
     CK(cudaMalloc(&ctx->d_phase, sizeof(double) * E1B200_MAX_CHAN));
-    CK(cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->d_counters, sizeof ctx->counters));
     CK(cudaMemcpy(ctx->d_codes, h_codes, E1_CODES_BYTES, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_lut, h_lut, E1_LUT_BYTES, cudaMemcpyHostToDevice));
     free(h_codes);
     CK(cudaMemset(ctx->d_phase, 0, sizeof(double) * E1B200_MAX_CHAN));
-    CK(cudaMemset(ctx->d_counters, 0, 2 * sizeof(unsigned long long)));
-    CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * (size_t)ctx->batch_epochs * ctx->tiles_per_epoch * cfg->max_chan));
+    CK(cudaMemset(ctx->d_counters, 0, sizeof ctx->counters));
     return E1B200_OK;
 }
 
@@ -221,11 +214,16 @@ int e1b200_destroy(e1b200_ctx *ctx)
     cudaFree(ctx->d_phase);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_ck);
+    cudaFree(ctx->d_g);
+    cudaFree(ctx->d_dend);
+    cudaFree(ctx->d_est);
+    cudaFree(ctx->d_delta);
+    cudaFree(ctx->d_units);
     cudaFree(ctx->d_recs);
     cudaFree(ctx->d_ranges);
     cudaFree(ctx->d_out[0]);
     cudaFree(ctx->d_out[1]);
-    for (cudaEvent_t ev : ctx->ev_pass)
+    for (cudaEvent_t ev : ctx->ev)
         cudaEventDestroy(ev);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_buf[i]) cudaEventDestroy(ctx->ev_buf[i]);
@@ -274,27 +272,95 @@ int e1b200_get_carrier_phase(e1b200_ctx *ctx, int slot, double *out)
     return E1B200_OK;
 }
 
-/* enqueue planner + synthesis for n (<= batch_epochs) epochs whose records are on the device */
-static int enqueue_pass(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int16_t *d_out)
+static int ensure_plan_scratch(e1b200_ctx *ctx)
+{
+    if (ctx->d_ck)
+        return E1B200_OK;
+    const size_t ne = (size_t)ctx->plan_epochs * ctx->cfg.max_chan;
+    CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * ne * ctx->tiles_per_epoch));
+    CK(cudaMalloc(&ctx->d_delta, sizeof(double) * ne));
+    CK(cudaMemset(ctx->d_delta, 0, sizeof(double) * ne));
+    if (!ctx->serial_planner) {
+        CK(cudaMalloc(&ctx->d_g, sizeof(double) * ne));
+        CK(cudaMalloc(&ctx->d_dend, sizeof(double) * ne));
+        CK(cudaMalloc(&ctx->d_est, sizeof(double) * ne));
+        CK(cudaMalloc(&ctx->d_units, sizeof(e1_unit) * ne));
+    }
+    return E1B200_OK;
+}
+
+static int mark(e1b200_ctx *ctx, int kind, int end)
+{
+    cudaEvent_t ev;
+    CK(cudaEventCreate(&ev));
+    ctx->ev.push_back(ev);
+    if (!end)
+        ctx->ev_kind.push_back(kind);
+    CK(cudaEventRecord(ev, ctx->stream));
+    return E1B200_OK;
+}
+
+static void reset_call(e1b200_ctx *ctx)
+{
+    for (cudaEvent_t ev : ctx->ev)
+        cudaEventDestroy(ev);
+    ctx->ev.clear();
+    ctx->ev_kind.clear();
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+}
+
+/* planner kernels for n (<= plan_epochs) epochs whose records are on the device */
+static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
 {
     const e1b200_config *cfg = &ctx->cfg;
-    const int pi = ctx->n_pass++;
-    while ((int)ctx->ev_pass.size() < 3 * (pi + 1)) {
-        cudaEvent_t ev;
-        CK(cudaEventCreate(&ev));
-        ctx->ev_pass.push_back(ev);
-    }
-    CK(cudaEventRecord(ctx->ev_pass[3 * pi], ctx->stream));
-    int nthr = n * cfg->max_chan;
+    int rc = mark(ctx, 0, 0);
+    if (rc)
+        return rc;
+    const int nthr = n * cfg->max_chan;
     e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
                                                                      ctx->tile, ctx->tiles_per_epoch, ctx->delt);
-    e1_plan_carr_kernel<<<(cfg->max_chan + 31) / 32, 32, 0, ctx->stream>>>(d_recs, ctx->d_ck, ctx->d_phase, n, cfg->max_chan,
-                                                                         cfg->samples_per_epoch, ctx->tile,
-                                                                         ctx->tiles_per_epoch, ctx->delt);
-    CK(cudaEventRecord(ctx->ev_pass[3 * pi + 1], ctx->stream));
+    if (ctx->serial_planner) {
+        e1_plan_carr_kernel<<<(cfg->max_chan + 31) / 32, 32, 0, ctx->stream>>>(d_recs, ctx->d_ck, ctx->d_phase, n, cfg->max_chan,
+                                                                             cfg->samples_per_epoch, ctx->tile,
+                                                                             ctx->tiles_per_epoch, ctx->delt);
+        ctx->timing.kernel_launches += 2;
+    } else {
+        e1_plan_args P;
+        P.recs = d_recs;
+        P.ck = ctx->d_ck;
+        P.phase = ctx->d_phase;
+        P.g = ctx->d_g;
+        P.dend = ctx->d_dend;
+        P.est = ctx->d_est;
+        P.delta = ctx->d_delta;
+        P.units = ctx->d_units;
+        P.counters = ctx->d_counters;
+        P.delt = ctx->delt;
+        P.n_epochs = n;
+        P.n_samp = cfg->samples_per_epoch;
+        P.max_chan = cfg->max_chan;
+        P.tile = ctx->tile;
+        P.tiles_per_epoch = ctx->tiles_per_epoch;
+        const int cb = (cfg->max_chan + 31) / 32;
+        e1_v2_ideal_kernel<<<cb, 32, 0, ctx->stream>>>(P);
+        e1_v2_drift_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
+        e1_v2_estimate_kernel<<<cb, 32, 0, ctx->stream>>>(P);
+        e1_v2_span_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
+        e1_v2_chain_kernel<<<cb, 32, 0, ctx->stream>>>(P);
+        ctx->timing.kernel_launches += 6;
+    }
+    CK(cudaGetLastError());
+    return mark(ctx, 0, 1);
+}
+
+/* synthesis of epochs [e_off, e_off+n) of the current plan into d_out */
+static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *d_recs_plan, int16_t *d_out)
+{
+    const e1b200_config *cfg = &ctx->cfg;
     e1_synth_args A;
-    A.recs = d_recs;
-    A.ck = ctx->d_ck;
+    A.recs = d_recs_plan + (size_t)e_off * cfg->max_chan;
+    A.ck = ctx->d_ck + (size_t)e_off * ctx->tiles_per_epoch * cfg->max_chan;
+    A.delta = ctx->d_delta + (size_t)e_off * cfg->max_chan;
     A.codes = ctx->d_codes;
     A.lut = ctx->d_lut;
     A.out = d_out;
@@ -313,35 +379,34 @@ static int enqueue_pass(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int1
     long grid = (long)ctx->sm_count * ctx->ctas_per_sm;
     if (grid > total_tiles)
         grid = total_tiles;
+    int rc = mark(ctx, 1, 0);
+    if (rc)
+        return rc;
     synth_for(ctx->groups)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
-    CK(cudaEventRecord(ctx->ev_pass[3 * pi + 2], ctx->stream));
     CK(cudaGetLastError());
-    ctx->timing.kernel_launches += 3;
+    ctx->timing.kernel_launches += 1;
     ctx->timing.synth_launches += 1;
-    return E1B200_OK;
+    return mark(ctx, 1, 1);
 }
 
 static int finish_timing(e1b200_ctx *ctx)
 {
     float plan = 0, synth = 0, total = 0;
-    for (int pi = 0; pi < ctx->n_pass; pi++) {
-        float a = 0, b = 0;
-        CK(cudaEventElapsedTime(&a, ctx->ev_pass[3 * pi], ctx->ev_pass[3 * pi + 1]));
-        CK(cudaEventElapsedTime(&b, ctx->ev_pass[3 * pi + 1], ctx->ev_pass[3 * pi + 2]));
-        plan += a;
-        synth += b;
+    for (size_t i = 0; i < ctx->ev_kind.size(); i++) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+        (ctx->ev_kind[i] ? synth : plan) += t;
     }
-    if (ctx->n_pass)
-        CK(cudaEventElapsedTime(&total, ctx->ev_pass[0], ctx->ev_pass[3 * ctx->n_pass - 1]));
+    if (!ctx->ev.empty())
+        CK(cudaEventElapsedTime(&total, ctx->ev.front(), ctx->ev.back()));
     ctx->timing.plan_ms = plan;
     ctx->timing.synth_ms = synth;
     ctx->timing.total_ms = total;
+    unsigned long long before = ctx->counters[1];
     CK(cudaMemcpy(ctx->counters, ctx->d_counters, sizeof ctx->counters, cudaMemcpyDeviceToHost));
-    if (ctx->counters[1]) {
-        CK(cudaMemset(ctx->d_counters, 0, sizeof ctx->counters));
+    if (ctx->counters[1] != before)
         return fail(ctx, E1B200_EINVAL, "planner rejected a record (code phase / f_code / ibit out of range, or fs too low for the tile)",
                     cudaSuccess);
-    }
     return E1B200_OK;
 }
 
@@ -350,13 +415,15 @@ int e1b200_synth_epochs_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec
     if (!ctx || n_epochs < 0 || (n_epochs && (!d_recs || !d_out)))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    memset(&ctx->timing, 0, sizeof ctx->timing);
-    ctx->n_pass = 0;
+    int rc = ensure_plan_scratch(ctx);
+    if (rc)
+        return rc;
+    reset_call(ctx);
     const size_t epoch_i16 = (size_t)ctx->cfg.samples_per_epoch * 2;
-    for (int e0 = 0; e0 < n_epochs; e0 += ctx->batch_epochs) {
-        int n = n_epochs - e0 < ctx->batch_epochs ? n_epochs - e0 : ctx->batch_epochs;
-        int rc = enqueue_pass(ctx, n, d_recs + (size_t)e0 * ctx->cfg.max_chan, d_out + (size_t)e0 * epoch_i16);
-        if (rc)
+    for (int e0 = 0; e0 < n_epochs; e0 += ctx->plan_epochs) {
+        int n = n_epochs - e0 < ctx->plan_epochs ? n_epochs - e0 : ctx->plan_epochs;
+        const e1_epoch_rec *r = d_recs + (size_t)e0 * ctx->cfg.max_chan;
+        if ((rc = enqueue_plan(ctx, n, r)) || (rc = enqueue_synth(ctx, 0, n, r, d_out + (size_t)e0 * epoch_i16)))
             return rc;
     }
     return E1B200_OK;
@@ -369,68 +436,72 @@ int e1b200_sync(e1b200_ctx *ctx)
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
-    if (ctx->timing.kernel_launches)
+    if (!ctx->ev.empty())
         return finish_timing(ctx);
     return E1B200_OK;
 }
 
-static int ensure_staging(e1b200_ctx *ctx, int want_ranges)
+static int ensure_staging(e1b200_ctx *ctx, int want_ranges, int want_out)
 {
     const e1b200_config *cfg = &ctx->cfg;
-    size_t nrec = (size_t)ctx->batch_epochs * cfg->max_chan;
+    size_t nrec = (size_t)ctx->plan_epochs * cfg->max_chan;
     if (!ctx->d_recs)
-        CK(cudaMalloc(&ctx->d_recs, 2 * nrec * sizeof(e1_epoch_rec)));
+        CK(cudaMalloc(&ctx->d_recs, nrec * sizeof(e1_epoch_rec)));
     if (want_ranges && !ctx->d_ranges)
-        CK(cudaMalloc(&ctx->d_ranges, 2 * nrec * sizeof(e1_range_rec)));
-    if (!ctx->d_out[0]) {
-        ctx->out_cap = (size_t)ctx->batch_epochs * cfg->samples_per_epoch * 4;
-        CK(cudaMalloc(&ctx->d_out[0], ctx->out_cap));
-        CK(cudaMalloc(&ctx->d_out[1], ctx->out_cap));
+        CK(cudaMalloc(&ctx->d_ranges, nrec * sizeof(e1_range_rec)));
+    if (want_out && !ctx->d_out[0]) {
+        size_t cap = (size_t)ctx->batch_epochs * cfg->samples_per_epoch * 4;
+        CK(cudaMalloc(&ctx->d_out[0], cap));
+        CK(cudaMalloc(&ctx->d_out[1], cap));
     }
     return E1B200_OK;
 }
 
-/* Host-buffer pipeline: records H2D, planner + synthesis on `stream`, D2H on `copy_stream`;
- * two staging buffers so the copy of pass i overlaps the kernels of pass i+1. */
+/* Host-buffer pipeline.  Per planner pass: records H2D, (restate,) planner kernels; then the
+ * synthesis runs in slices of batch_epochs into two staging buffers, each slice's D2H on
+ * `copy_stream` overlapping the next slice's kernel. */
 static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, const e1_range_rec *ranges, int16_t *out)
 {
     if (!ctx || n_epochs < 0 || (n_epochs && ((!recs && !ranges) || !out)))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_staging(ctx, ranges != nullptr);
+    int rc = ensure_plan_scratch(ctx);
+    if (!rc)
+        rc = ensure_staging(ctx, ranges != nullptr, 1);
     if (rc)
         return rc;
-    memset(&ctx->timing, 0, sizeof ctx->timing);
-    ctx->n_pass = 0;
+    reset_call(ctx);
     const e1b200_config *cfg = &ctx->cfg;
     const size_t epoch_i16 = (size_t)cfg->samples_per_epoch * 2;
-    const size_t nrec_buf = (size_t)ctx->batch_epochs * cfg->max_chan;
-    int pass = 0;
-    for (int e0 = 0; e0 < n_epochs; e0 += ctx->batch_epochs, pass++) {
-        int n = n_epochs - e0 < ctx->batch_epochs ? n_epochs - e0 : ctx->batch_epochs;
-        int b = pass & 1;
-        size_t nrec = (size_t)n * cfg->max_chan;
-        e1_epoch_rec *d_recs = ctx->d_recs + b * nrec_buf;
-        if (pass >= 2) /* staging buffer b is free once its previous D2H finished */
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+    int slice = 0;
+    for (int p0 = 0; p0 < n_epochs; p0 += ctx->plan_epochs) {
+        int np = n_epochs - p0 < ctx->plan_epochs ? n_epochs - p0 : ctx->plan_epochs;
+        size_t nrec = (size_t)np * cfg->max_chan;
         if (ranges) {
-            e1_range_rec *d_rr = ctx->d_ranges + b * nrec_buf;
-            CK(cudaMemcpyAsync(d_rr, ranges + (size_t)e0 * cfg->max_chan, nrec * sizeof(e1_range_rec), cudaMemcpyHostToDevice,
-                               ctx->stream));
-            e1_restate_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, ctx->stream>>>(d_rr, d_recs, (int)nrec, cfg->dt_epoch);
+            CK(cudaMemcpyAsync(ctx->d_ranges, ranges + (size_t)p0 * cfg->max_chan, nrec * sizeof(e1_range_rec),
+                               cudaMemcpyHostToDevice, ctx->stream));
+            e1_restate_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_ranges, ctx->d_recs, (int)nrec,
+                                                                                        cfg->dt_epoch);
             ctx->timing.kernel_launches += 1;
         } else {
-            CK(cudaMemcpyAsync(d_recs, recs + (size_t)e0 * cfg->max_chan, nrec * sizeof(e1_epoch_rec), cudaMemcpyHostToDevice,
-                               ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_recs, recs + (size_t)p0 * cfg->max_chan, nrec * sizeof(e1_epoch_rec),
+                               cudaMemcpyHostToDevice, ctx->stream));
         }
-        rc = enqueue_pass(ctx, n, d_recs, ctx->d_out[b]);
-        if (rc)
+        if ((rc = enqueue_plan(ctx, np, ctx->d_recs)))
             return rc;
-        CK(cudaEventRecord(ctx->ev_buf[b], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_buf[b], 0));
-        CK(cudaMemcpyAsync(out + (size_t)e0 * epoch_i16, ctx->d_out[b], (size_t)n * epoch_i16 * 2, cudaMemcpyDeviceToHost,
-                           ctx->copy_stream));
-        CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+        for (int e0 = 0; e0 < np; e0 += ctx->batch_epochs, slice++) {
+            int n = np - e0 < ctx->batch_epochs ? np - e0 : ctx->batch_epochs;
+            int b = slice & 1;
+            if (slice >= 2) /* staging buffer b is free once its previous D2H finished */
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+            if ((rc = enqueue_synth(ctx, e0, n, ctx->d_recs, ctx->d_out[b])))
+                return rc;
+            CK(cudaEventRecord(ctx->ev_buf[b], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_buf[b], 0));
+            CK(cudaMemcpyAsync(out + (size_t)(p0 + e0) * epoch_i16, ctx->d_out[b], (size_t)n * epoch_i16 * 2,
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+        }
     }
     return e1b200_sync(ctx);
 }
@@ -450,22 +521,22 @@ int e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec
     if (!ctx || n_epochs < 0 || (n_epochs && (!d_rr || !d_out)))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_staging(ctx, 0);
+    int rc = ensure_plan_scratch(ctx);
+    if (!rc)
+        rc = ensure_staging(ctx, 0, 0);
     if (rc)
         return rc;
-    memset(&ctx->timing, 0, sizeof ctx->timing);
-    ctx->n_pass = 0;
+    reset_call(ctx);
     const e1b200_config *cfg = &ctx->cfg;
     const size_t epoch_i16 = (size_t)cfg->samples_per_epoch * 2;
-    for (int e0 = 0; e0 < n_epochs; e0 += ctx->batch_epochs) {
-        int n = n_epochs - e0 < ctx->batch_epochs ? n_epochs - e0 : ctx->batch_epochs;
+    for (int e0 = 0; e0 < n_epochs; e0 += ctx->plan_epochs) {
+        int n = n_epochs - e0 < ctx->plan_epochs ? n_epochs - e0 : ctx->plan_epochs;
         size_t nrec = (size_t)n * cfg->max_chan;
         /* single staging slot: stream order keeps pass i+1's restate behind pass i's synthesis */
         e1_restate_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, ctx->stream>>>(d_rr + (size_t)e0 * cfg->max_chan, ctx->d_recs,
                                                                                     (int)nrec, cfg->dt_epoch);
         ctx->timing.kernel_launches += 1;
-        rc = enqueue_pass(ctx, n, ctx->d_recs, d_out + (size_t)e0 * epoch_i16);
-        if (rc)
+        if ((rc = enqueue_plan(ctx, n, ctx->d_recs)) || (rc = enqueue_synth(ctx, 0, n, ctx->d_recs, d_out + (size_t)e0 * epoch_i16)))
             return rc;
     }
     return E1B200_OK;
@@ -514,6 +585,9 @@ int e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out)
         return E1B200_EINVAL;
     out->exact_samples = ctx->counters[0];
     out->planner_errors = ctx->counters[1];
+    out->serial_epochs = ctx->counters[2];
+    out->hat_epochs = ctx->counters[3];
+    out->plan_epochs = ctx->plan_epochs;
     out->tile = ctx->tile;
     out->tiles_per_epoch = ctx->tiles_per_epoch;
     out->batch_epochs = ctx->batch_epochs;

@@ -40,8 +40,9 @@ class Timing(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("exact_samples", C.c_uint64), ("planner_errors", C.c_uint64), ("tile", C.c_int32),
-                ("tiles_per_epoch", C.c_int32), ("batch_epochs", C.c_int32), ("sm_count", C.c_int32),
+    _fields_ = [("exact_samples", C.c_uint64), ("planner_errors", C.c_uint64), ("serial_epochs", C.c_uint64),
+                ("hat_epochs", C.c_uint64), ("tile", C.c_int32), ("tiles_per_epoch", C.c_int32),
+                ("batch_epochs", C.c_int32), ("plan_epochs", C.c_int32), ("sm_count", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("smem_bytes", C.c_int32)]
 
 

@@ -137,9 +137,12 @@ typedef struct e1b200_stats {
     uint64_t exact_samples;    /* channel-samples the closed form flagged as ambiguous and the
                                   exact walk resolved, cumulative since create                    */
     uint64_t planner_errors;   /* records the planner rejected, cumulative                        */
+    uint64_t serial_epochs;    /* channel-epochs the carrier chain had to walk serially           */
+    uint64_t hat_epochs;       /* channel-epochs planned in parallel and accepted by the chain    */
     int32_t tile;              /* samples per planner checkpoint / synthesis tile                 */
     int32_t tiles_per_epoch;
-    int32_t batch_epochs;      /* epochs per internal pass                                        */
+    int32_t batch_epochs;      /* epochs per D2H staging slice (host entry points)                */
+    int32_t plan_epochs;       /* epochs per planner pass                                         */
     int32_t sm_count, ctas_per_sm, smem_bytes;
 } e1b200_stats;
 int  e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out);

@@ -127,6 +127,9 @@ def hostsim():
         hs.hs_build_codes.argtypes = [C.c_void_p]
         hs.hs_synth_epochs.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        hs.hs_synth_epochs_p.argtypes = hs.hs_synth_epochs.argtypes + [C.c_int]
+        hs.hs_plan_compare.restype = C.c_long
+        hs.hs_plan_compare.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _hostsim = hs
     return _hostsim
 
@@ -144,19 +147,31 @@ def product_lut():
     return lut
 
 
-def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1):
+def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1, planner=2):
     """Same contract as oracle_synth, through the product's core header on the host.
-    Returns (int16 [n_epochs*n_samp, 2], final phases, stats[3])."""
+    planner 1 = serial exact walk per channel, 2 = the parallel planner's passes (default, what the
+    kernels run).  Returns (int16 [n_epochs*n_samp, 2], final phases, stats[5]): stats = fallback
+    samples, planner errors, slow-path threads, epochs walked serially by the chain, HAT epochs."""
     recs = np.ascontiguousarray(recs)
     n_epochs, max_chan = recs.shape
     ph = np.zeros(max_chan) if carr_phase is None else np.array(carr_phase, dtype=np.float64)
     out = np.zeros((n_epochs * n_samp, 2), np.int16)
-    st = np.zeros(3, np.uint64)
+    st = np.zeros(5, np.uint64)
     lut = product_lut()
-    rc = hostsim().hs_synth_epochs(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, out.ctypes.data,
-                                   groups, amb_scale, lut.ctypes.data, st.ctypes.data)
+    rc = hostsim().hs_synth_epochs_p(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, out.ctypes.data,
+                                     groups, amb_scale, lut.ctypes.data, st.ctypes.data, planner)
     assert rc == 0, f"hostsim planner errors: {st}"
     return out, ph, st
+
+
+def hostsim_plan_compare(fs_hz, n_samp, recs, carr_phase=None, groups=4):
+    """Serial vs parallel carrier planner on the host: (mismatching checkpoints, [serial epochs, HAT epochs, active epochs])."""
+    recs = np.ascontiguousarray(recs)
+    n_epochs, max_chan = recs.shape
+    ph = np.zeros(max_chan) if carr_phase is None else np.array(carr_phase, dtype=np.float64)
+    st = np.zeros(3, np.uint64)
+    bad = hostsim().hs_plan_compare(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, groups, st.ctypes.data)
+    return int(bad), [int(x) for x in st]
 
 
 # ------------------------------------------------------------------- reference trace -> recs

@@ -64,8 +64,23 @@ void hs_build_codes(uint32_t *codes)
 // from the oracle's tables so this file holds no second copy of them).
 // stats[0] = samples resolved by the literal fallback, stats[1] = planner errors,
 // stats[2] = threads that took the slow path.
+// planner: 1 = serial reference planner (one exact walk per channel), 2 = parallel planner (drift
+// pass, estimate prefix, span pass, chain) in the order the kernels run it.
+// stats[3] = epochs the chain walked serially, stats[4] = HAT units accepted (planner 2 only).
+int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs, double *phase,
+                      int16_t *out, int groups, int amb_scale, const int32_t *lut, unsigned long long *stats, int planner);
+
 int hs_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs, double *phase,
                     int16_t *out, int groups, int amb_scale, const int32_t *lut, unsigned long long *stats)
+{
+    unsigned long long st[5];
+    int rc = hs_synth_epochs_p(fs_hz, n_samp, max_chan, n_epochs, recs, phase, out, groups, amb_scale, lut, st, 1);
+    stats[0] = st[0], stats[1] = st[1], stats[2] = st[2];
+    return rc;
+}
+
+int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs, double *phase,
+                      int16_t *out, int groups, int amb_scale, const int32_t *lut, unsigned long long *stats, int planner)
 {
     const double delt = 1.0 / fs_hz;
     const int threads = 256, tile = groups * threads * E1C_RUN;
@@ -78,12 +93,40 @@ int hs_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs, const 
         for (int ch = 0; ch < max_chan; ch++)
             e1_plan_code_epoch(&recs[(size_t)e * max_chan + ch], &ck[(size_t)e * tpe * max_chan + ch], max_chan, n_samp, tile,
                                tpe, delt);
-    for (int ch = 0; ch < max_chan; ch++) {
-        double phi = phase[ch];
+    std::vector<double> delta((size_t)n_epochs * max_chan, 0.0);
+    stats[3] = stats[4] = 0;
+    if (planner == 1) {
+        for (int ch = 0; ch < max_chan; ch++) {
+            double phi = phase[ch];
+            for (int e = 0; e < n_epochs; e++)
+                phi = e1_plan_carr_epoch(&recs[(size_t)e * max_chan + ch], &ck[(size_t)e * tpe * max_chan + ch], max_chan, phi,
+                                         n_samp, tile, tpe, delt);
+            phase[ch] = phi;
+        }
+    } else if (n_epochs > 0) {
+        const size_t ne = (size_t)n_epochs * max_chan;
+        std::vector<double> g(ne), dend(ne), est(ne);
+        std::vector<e1_unit> units(ne);
+        for (int ch = 0; ch < max_chan; ch++)
+            e1_v2_ideal_prefix(recs + ch, max_chan, n_epochs, phase[ch], n_samp, delt, &g[ch]);
         for (int e = 0; e < n_epochs; e++)
-            phi = e1_plan_carr_epoch(&recs[(size_t)e * max_chan + ch], &ck[(size_t)e * tpe * max_chan + ch], max_chan, phi,
-                                     n_samp, tile, tpe, delt);
-        phase[ch] = phi;
+            for (int ch = 0; ch < max_chan; ch++)
+                dend[(size_t)e * max_chan + ch] = e1_v2_drift_unit(&recs[(size_t)e * max_chan + ch], g[(size_t)e * max_chan + ch], n_samp, delt);
+        for (int ch = 0; ch < max_chan; ch++)
+            e1_v2_estimate_prefix(recs + ch, max_chan, n_epochs, phase[ch], &g[ch], &dend[ch], &est[ch]);
+        for (int e = 0; e < n_epochs; e++)
+            for (int ch = 0; ch < max_chan; ch++) {
+                const size_t i = (size_t)e * max_chan + ch;
+                e1_v2_span_unit(&recs[i], e ? &recs[i - max_chan] : nullptr, e, phase[ch], e ? est[i - max_chan] : 0.0, n_samp, tile,
+                                tpe, delt, &ck[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
+            }
+        for (int ch = 0; ch < max_chan; ch++) {
+            unsigned long long st2[2] = {0, 0};
+            phase[ch] = e1_v2_chain(recs + ch, max_chan, n_epochs, phase[ch], n_samp, tile, tpe, delt, &units[ch], &ck[ch],
+                                    (size_t)tpe * max_chan, &delta[ch], st2);
+            stats[3] += st2[0];
+            stats[4] += st2[1];
+        }
     }
     const uint32_t thr_carr = e1_thr_carr(tile, amb_scale), thr_code = e1_thr_code(tile, amb_scale);
     std::vector<e1_chan_par> par(max_chan);
@@ -97,7 +140,7 @@ int hs_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs, const 
                     continue;
                 if (c->sym & E1_CK_ERROR)
                     stats[1]++;
-                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, &par[nact++]);
+                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, delta[(size_t)e * max_chan + ch], &par[nact++]);
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
             int16_t *o = out + ((size_t)e * n_samp + (size_t)t * tile) * 2;
@@ -125,5 +168,62 @@ int hs_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs, const 
                 }
         }
     return stats[1] ? -1 : 0;
+}
+
+// Carrier planners only: serial walk (planner 1) against the parallel passes (planner 2), every
+// tile checkpoint and the final phase compared bit for bit.  Returns the number of mismatches;
+// stats[0] = epochs the chain walked serially, stats[1] = HAT epochs accepted, stats[2] = active epochs.
+long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs, const double *phase0,
+                     int groups, unsigned long long *stats)
+{
+    const double delt = 1.0 / fs_hz;
+    const int tile = groups * 256 * E1C_RUN;
+    const int tpe = (n_samp + tile - 1) / tile;
+    const size_t ne = (size_t)n_epochs * max_chan;
+    std::vector<e1_tile_ck> ck1(ne * tpe), ck2(ne * tpe);
+    memset(ck1.data(), 0, ck1.size() * sizeof(e1_tile_ck));
+    memset(ck2.data(), 0, ck2.size() * sizeof(e1_tile_ck));
+    std::vector<double> g(ne), dend(ne), est(ne), delta(ne, 0.0), p1(max_chan), p2(max_chan);
+    std::vector<e1_unit> units(ne);
+    stats[0] = stats[1] = stats[2] = 0;
+    for (int ch = 0; ch < max_chan; ch++) {
+        double phi = phase0[ch];
+        for (int e = 0; e < n_epochs; e++)
+            phi = e1_plan_carr_epoch(&recs[(size_t)e * max_chan + ch], &ck1[(size_t)e * tpe * max_chan + ch], max_chan, phi, n_samp,
+                                     tile, tpe, delt);
+        p1[ch] = phi;
+    }
+    for (int ch = 0; ch < max_chan; ch++)
+        e1_v2_ideal_prefix(recs + ch, max_chan, n_epochs, phase0[ch], n_samp, delt, &g[ch]);
+    for (size_t i = 0; i < ne; i++)
+        dend[i] = e1_v2_drift_unit(&recs[i], g[i], n_samp, delt);
+    for (int ch = 0; ch < max_chan; ch++)
+        e1_v2_estimate_prefix(recs + ch, max_chan, n_epochs, phase0[ch], &g[ch], &dend[ch], &est[ch]);
+    for (int e = 0; e < n_epochs; e++)
+        for (int ch = 0; ch < max_chan; ch++) {
+            const size_t i = (size_t)e * max_chan + ch;
+            e1_v2_span_unit(&recs[i], e ? &recs[i - max_chan] : nullptr, e, phase0[ch], e ? est[i - max_chan] : 0.0, n_samp, tile, tpe,
+                            delt, &ck2[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
+        }
+    for (int ch = 0; ch < max_chan; ch++)
+        p2[ch] = e1_v2_chain(recs + ch, max_chan, n_epochs, phase0[ch], n_samp, tile, tpe, delt, &units[ch], &ck2[ch],
+                             (size_t)tpe * max_chan, &delta[ch], stats);
+    long bad = 0;
+    for (int e = 0; e < n_epochs; e++)
+        for (int ch = 0; ch < max_chan; ch++) {
+            const size_t i = (size_t)e * max_chan + ch;
+            if (!e1_rec_active(&recs[i]))
+                continue;
+            stats[2]++;
+            for (int t = 0; t < tpe; t++) {
+                const size_t j = ((size_t)e * tpe + t) * max_chan + ch;
+                if (e1_bits(ck1[j].phi) != e1_bits(e1_add(ck2[j].phi, delta[i])) && !(ck1[j].phi == 0.0 && e1_add(ck2[j].phi, delta[i]) == 0.0))
+                    bad++;
+            }
+        }
+    for (int ch = 0; ch < max_chan; ch++)
+        if (p1[ch] != p2[ch])
+            bad++;
+    return bad;
 }
 }

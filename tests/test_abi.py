@@ -52,7 +52,7 @@ def test_library_contains_sm100a_kernels_and_no_oracle(lib):
 def test_struct_layouts_match_header():
     assert E.REC_DTYPE.itemsize == 176 and E.RANGE_DTYPE.itemsize == 168
     assert E.REC_DTYPE == U.REC_DTYPE and E.RANGE_DTYPE == U.RANGE_DTYPE
-    assert C.sizeof(E.Config) == 32 and C.sizeof(E.Timing) == 20 and C.sizeof(E.Stats) == 40
+    assert C.sizeof(E.Config) == 32 and C.sizeof(E.Timing) == 20 and C.sizeof(E.Stats) == 64
 
 
 def test_host_restate_equals_oracle(lib):

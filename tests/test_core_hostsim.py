@@ -152,3 +152,63 @@ def test_doppler_sign_flip_and_phase_reset_mid_run():
     a, pa = U.oracle_synth(fs, N, recs)
     b, pb, st = U.hostsim_synth(fs, N, recs)
     assert np.array_equal(a, b) and np.array_equal(pa, pb), st
+
+
+# ------------------------------------------------------------------ parallel carrier planner
+@pytest.mark.parametrize("fs,n_samp,n_chan,n_epochs,seed", [(FS26, 260000, 36, 150, 1), (FS25, 2500000, 36, 40, 2),
+                                                             (4.0e6, 400000, 8, 60, 3)])
+def test_parallel_planner_equals_serial_walk(fs, n_samp, n_chan, n_epochs, seed):
+    """Every tile checkpoint (hat + translation) and the carried phase of the parallel planner equal
+    the serial exact walk bit for bit; nearly all epochs are accepted without a serial walk."""
+    recs = U.synthetic_recs_fast(n_epochs, n_chan, fs, seed=seed)
+    bad, (serial, hat, active) = U.hostsim_plan_compare(fs, n_samp, recs)
+    assert bad == 0
+    assert active == n_chan * n_epochs and hat > 0.95 * n_chan * (n_epochs - 1) and serial < 0.05 * active
+
+
+def test_parallel_planner_on_reference_trace():
+    z = np.load(GOLD / "paris45_recs.npz")
+    bad, (serial, hat, active) = U.hostsim_plan_compare(FS26, 260000, z["recs"])
+    assert bad == 0 and hat > 0.98 * active - 20
+
+
+def _step_multiple_of_2m53(fs, f_target):
+    """A Doppler whose per-sample phase step fl(f*delt) is an exact multiple of 2^-53 (round-half-even
+    ties at the wrap step: the planner must walk such epochs serially)."""
+    delt = 1.0 / fs
+    k0 = round(f_target * delt * 2.0 ** 53)
+    for k in range(k0, k0 + 4000):        # not every product is reachable: try neighbouring multiples
+        sp = k * 2.0 ** -53
+        f = sp / delt
+        for _ in range(8):
+            got = f * delt
+            if got == sp:
+                return f
+            f = np.nextafter(f, np.inf if got < sp else -np.inf)
+    raise AssertionError("no Doppler found")
+
+
+def test_parallel_planner_ties_idle_gaps_resets_and_low_doppler():
+    fs, n_samp, n_ep = FS26, 260000, 24
+    recs = U.synthetic_recs_fast(n_ep, 8, fs, seed=9, max_chan=9)
+    code = lambda f: 1.023e6 + f * 0.0006493506493506494
+    for e in range(n_ep):
+        f = _step_multiple_of_2m53(fs, 2500.0 + e)                 # ch 0: every epoch is a tie epoch
+        recs[e, 0]["f_carr"], recs[e, 0]["f_code"] = f, code(f)
+        f = 3.0 - 0.4 * e                                          # ch 1: |f| < 10 Hz (no wrap), sign flip
+        recs[e, 1]["f_carr"], recs[e, 1]["f_code"] = f, code(f)
+        f = (e - 11.5) * 300.0                                     # ch 2: fast sweep through zero
+        recs[e, 2]["f_carr"], recs[e, 2]["f_code"] = f, code(f)
+    recs[6:9, 3]["prn"] = 0                                        # ch 3: idle gap, comes back without a reset
+    recs[12, 4]["flags"] = U.E1_REC_SET_PHASE                      # ch 4: re-allocated mid-run
+    recs[12, 4]["carr_phase_init"] = 0.4321
+    recs[5, 5]["f_carr"] = 0.0                                     # ch 5: one epoch with zero Doppler
+    recs[:, 6]["f_carr"] = -np.abs(recs[:, 6]["f_carr"]) - 50.0    # ch 6: negative Doppler throughout
+    recs[:, 6]["f_code"] = code(recs[:, 6]["f_carr"])
+    bad, (serial, hat, active) = U.hostsim_plan_compare(fs, n_samp, recs, carr_phase=np.linspace(-0.9, 0.9, 9))
+    assert bad == 0
+    assert serial >= n_ep - 1          # at least the tie channel went through the serial path
+    # and the synthesised bytes agree with the oracle on a short prefix
+    a, pa = U.oracle_synth(fs, 26000, recs[:14], np.linspace(-0.9, 0.9, 9))
+    b, pb, st = U.hostsim_synth(fs, 26000, recs[:14], np.linspace(-0.9, 0.9, 9))
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)

@@ -97,7 +97,7 @@ def test_device_entry_and_call_splitting():
     s.sync()
     assert np.array_equal(d_out.cpu().numpy().reshape(-1, 2), ref)
     t = s.timing()
-    assert t.synth_ms > 0 and t.kernel_launches == 3 and t.synth_launches == 1
+    assert t.synth_ms > 0 and t.plan_ms > 0 and t.kernel_launches == 7 and t.synth_launches == 1
     s2 = E.Synth(fs, n_samp, nch)
     a = s2.synth_epochs(recs[:2])
     b = s2.synth_epochs(recs[2:])
@@ -120,6 +120,26 @@ def test_internal_batching_and_no_tma_path(monkeypatch):
     s = E.Synth(fs, n_samp, nch)
     assert np.array_equal(s.synth_epochs(recs), ref)
     s.close()
+
+
+def test_parallel_planner_equals_serial_planner(monkeypatch):
+    """The parallel carrier planner (drift pass, span pass, chain) must give the same bytes and the
+    same carried phase as the one-thread-per-channel exact walk, and accept nearly every epoch."""
+    fs, n_samp, nch, n_ep = FS26, 130000, 16, 60
+    recs = U.synthetic_recs_fast(n_ep, nch, fs, seed=77)
+    s = E.Synth(fs, n_samp, nch)
+    a = s.synth_epochs(recs)
+    pa, st = s.carrier_phases(), s.stats()
+    s.close()
+    monkeypatch.setenv("E1B200_SERIAL_PLANNER", "1")
+    s = E.Synth(fs, n_samp, nch)
+    b = s.synth_epochs(recs)
+    pb = s.carrier_phases()
+    s.close()
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
+    assert st.hat_epochs > 0.9 * nch * (n_ep - 1) and st.serial_epochs < 0.1 * nch * n_ep
+    ref, ph = U.oracle_synth(fs, n_samp, recs[:4], threads=8)
+    assert np.array_equal(a[:4 * n_samp], ref)
 
 
 def test_result_independent_of_ambiguity_threshold(monkeypatch):
