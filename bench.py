@@ -283,6 +283,8 @@ def main():
                          "note": "issue-bound by design: ~20 integer ops per channel-sample vs 4 B per sample"},
             "clocks": clocks, "gpu_launches": launches,
             "exact_fallback_samples": int(synth.stats().exact_samples),
+            "planner": {"hat_epochs": int(synth.stats().hat_epochs), "serial_epochs": int(synth.stats().serial_epochs),
+                        "note": "cumulative channel-epochs planned in parallel vs walked serially by the chain"},
         }
         if e2e:
             line["e2e"] = e2e

@@ -585,61 +585,77 @@ E1_HD double e1_carr_epoch_exact(double phi, double sp, int n_samp, int tile, in
 
 E1_HD int e1_rec_active(const e1_epoch_rec *r) { return r->prn >= 1 && r->prn <= E1C_N_PRN; }
 
+/* What the carrier planner needs from one epoch record, stored channel-major ([channel][epoch])
+ * so the serial per-channel passes read contiguous memory. */
+typedef struct e1_prep {
+    double sp;      /* fl(f_carr * delt): carrier phase step per sample (:531)                  */
+    double init;    /* carr_phase_init (valid with E1_PREP_SET_PHASE)                            */
+    uint32_t flags; /* E1_PREP_*                                                                 */
+    uint32_t pad;
+} e1_prep;
+#define E1_PREP_ACTIVE 1u
+#define E1_PREP_SET_PHASE 2u
+
+E1_HD void e1_v2_prep(const e1_epoch_rec *r, double delt, e1_prep *p)
+{
+    const int act = e1_rec_active(r);
+    p->sp = act ? e1_mul(r->f_carr, delt) : 0.0;
+    p->init = r->carr_phase_init;
+    p->flags = (act ? E1_PREP_ACTIVE : 0u) | ((act && (r->flags & E1_REC_SET_PHASE)) ? E1_PREP_SET_PHASE : 0u);
+    p->pad = 0;
+}
+
 /* phase + whole-epoch advance, folded back into (-1,1) the way :532 does (sign kept) */
 E1_HD double e1_ideal_next(double g, double sp, int n_samp)
 {
     double v = g + (double)n_samp * sp;
-    if (v >= 1.0)
-        v -= (double)(long long)v;
-    else if (v <= -1.0)
+    if (v >= 1.0 || v <= -1.0)
         v -= (double)(long long)v;
     return v;
 }
 
 /* K0: ideal (rounding-free, double precision) start phase of every epoch of one channel. */
-E1_HD void e1_v2_ideal_prefix(const e1_epoch_rec *recs, int stride, int n_epochs, double phi0, int n_samp, double delt,
-                              double *g_out)
+E1_HD void e1_v2_ideal_prefix(const e1_prep *pp, int n_epochs, double phi0, int n_samp, double *g_out)
 {
     double g = phi0;
     for (int e = 0; e < n_epochs; e++) {
-        const e1_epoch_rec *r = &recs[(size_t)e * stride];
-        if (e1_rec_active(r) && (r->flags & E1_REC_SET_PHASE))
-            g = r->carr_phase_init;
-        g_out[(size_t)e * stride] = g;
-        if (e1_rec_active(r))
-            g = e1_ideal_next(g, e1_mul(r->f_carr, delt), n_samp);
+        const uint32_t f = pp[e].flags;
+        if (f & E1_PREP_SET_PHASE)
+            g = pp[e].init;
+        g_out[e] = g;
+        if (f & E1_PREP_ACTIVE)
+            g = e1_ideal_next(g, pp[e].sp, n_samp);
     }
 }
 
 /* drift pass: exact walk of one epoch from its ideal start; returns the end phase */
-E1_HD double e1_v2_drift_unit(const e1_epoch_rec *r, double g, int n_samp, double delt)
+E1_HD double e1_v2_drift_unit(const e1_prep *p, double g, int n_samp)
 {
-    if (!e1_rec_active(r))
+    if (!(p->flags & E1_PREP_ACTIVE))
         return g;
-    return e1_carr_advance(g, e1_mul(r->f_carr, delt), 0, n_samp);
+    return e1_carr_advance(g, p->sp, 0, n_samp);
 }
 
 /* K1: refined start-phase estimates of one channel.  The drift pass walked epoch e exactly from
  * the ideal start g[e] to end[e]; the true start est[e] differs from g[e] by a tiny eta, and by
  * translation the true end is end[e] + eta (to within an ulp or two).                          */
-E1_HD void e1_v2_estimate_prefix(const e1_epoch_rec *recs, int stride, int n_epochs, double phi0, const double *g,
-                                 const double *end, double *est)
+E1_HD void e1_v2_estimate_prefix(const e1_prep *pp, int n_epochs, double phi0, const double *g, const double *end,
+                                 double *est)
 {
     double cur = phi0;
     for (int e = 0; e < n_epochs; e++) {
-        const e1_epoch_rec *r = &recs[(size_t)e * stride];
-        const size_t i = (size_t)e * stride;
-        if (e1_rec_active(r) && (r->flags & E1_REC_SET_PHASE))
-            cur = r->carr_phase_init;
-        est[i] = cur;
-        if (!e1_rec_active(r))
+        const uint32_t f = pp[e].flags;
+        if (f & E1_PREP_SET_PHASE)
+            cur = pp[e].init;
+        est[e] = cur;
+        if (!(f & E1_PREP_ACTIVE))
             continue;
-        double eta = cur - g[i];
+        double eta = cur - g[e];
         if (eta > 0.5)
             eta -= 1.0;
         else if (eta < -0.5)
             eta += 1.0;
-        cur = end[i] + eta;
+        cur = end[e] + eta;
         if (cur >= 1.0)
             cur -= 1.0;
         else if (cur <= -1.0)
@@ -647,10 +663,10 @@ E1_HD void e1_v2_estimate_prefix(const e1_epoch_rec *recs, int stride, int n_epo
     }
 }
 
-/* span pass for one (epoch, channel).  recs_ch/est_ch/unit/o point at this channel's epoch e. */
-E1_HD void e1_v2_span_unit(const e1_epoch_rec *r, const e1_epoch_rec *r_prev, int e, double phi_batch_start,
-                           double est_prev, int n_samp, int tile, int tiles_per_epoch, double delt, e1_tile_ck *o,
-                           int stride, e1_unit *u)
+/* span pass for one (epoch, channel): p / p_prev are this channel's prep records of epoch e and
+ * e-1, o its first tile checkpoint of epoch e (tile stride `stride`). */
+E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, double phi_batch_start, double est_prev,
+                           int n_samp, int tile, int tiles_per_epoch, e1_tile_ck *o, int stride, e1_unit *u)
 {
     u->type = E1_UNIT_NONE;
     u->last_k = -1;
@@ -662,19 +678,19 @@ E1_HD void e1_v2_span_unit(const e1_epoch_rec *r, const e1_epoch_rec *r_prev, in
     u->hi = 0.0;
     u->neg = 0;
     u->reserved = 0.0;
-    if (!e1_rec_active(r))
+    if (!(pr->flags & E1_PREP_ACTIVE))
         return;
-    const double sp = e1_mul(r->f_carr, delt);
-    if (e == 0 || (r->flags & E1_REC_SET_PHASE)) {
-        const double phi = (r->flags & E1_REC_SET_PHASE) ? r->carr_phase_init : phi_batch_start;
+    const double sp = pr->sp;
+    if (e == 0 || (pr->flags & E1_PREP_SET_PHASE)) {
+        const double phi = (pr->flags & E1_PREP_SET_PHASE) ? pr->init : phi_batch_start;
         u->type = E1_UNIT_EXACT;
         u->end_phi = e1_carr_epoch_exact(phi, sp, n_samp, tile, tiles_per_epoch, o, stride, &u->last_k, &u->last_p, &u->neg);
         return;
     }
     u->type = E1_UNIT_SERIAL;
-    if (!e1_rec_active(r_prev))
+    if (!(pr_prev->flags & E1_PREP_ACTIVE))
         return;
-    const double sp0 = e1_mul(r_prev->f_carr, delt);
+    const double sp0 = pr_prev->sp;
     if (sp == 0.0 || sp0 == 0.0 || (sp < 0.0) != (sp0 < 0.0))
         return;
     if (!(e1_fabs(sp) < 0.5) || !(e1_fabs(sp0) < 0.5))
@@ -739,48 +755,50 @@ E1_HD void e1_v2_span_unit(const e1_epoch_rec *r, const e1_epoch_rec *r_prev, in
 
 /* chain of one channel: validates HAT units, walks the others, writes the per-epoch translation
  * delta[e] (signed; the epoch's checkpoints are ck.phi + delta) and returns the final phase.
- * stats[0] += epochs walked serially, stats[1] += HAT units accepted.                          */
-E1_HD double e1_v2_chain(const e1_epoch_rec *recs, int stride, int n_epochs, double phi0, int n_samp, int tile,
-                         int tiles_per_epoch, double delt, e1_unit *units, e1_tile_ck *ck, size_t ck_epoch_stride,
-                         double *delta, unsigned long long *stats)
+ * ck points at this channel's first checkpoint; consecutive tiles are `stride` apart, consecutive
+ * epochs `ck_epoch_stride`.  stats[0] += epochs walked serially, stats[1] += HAT units accepted. */
+E1_HD double e1_v2_chain(const e1_prep *pp, int n_epochs, double phi0, int n_samp, int tile, int tiles_per_epoch,
+                         e1_unit *units, e1_tile_ck *ck, int stride, size_t ck_epoch_stride, double *delta,
+                         unsigned long long *stats)
 {
     double phi = phi0;
     int prev_ok = 0, prev_neg = 0;
     int32_t prev_k = -1;
     double prev_p = 0.0;
     for (int e = 0; e < n_epochs; e++) {
-        const e1_epoch_rec *r = &recs[(size_t)e * stride];
-        e1_unit *u = &units[(size_t)e * stride];
-        delta[(size_t)e * stride] = 0.0;
-        if (u->type == E1_UNIT_NONE) {
+        e1_unit *u = &units[e];
+        const int type = u->type;
+        delta[e] = 0.0;
+        if (type == E1_UNIT_NONE) {
             prev_ok = 0;
             continue;
         }
-        if (u->type == E1_UNIT_EXACT) {
+        int32_t last_k = u->last_k, neg = u->neg;
+        double last_p = u->last_p;
+        if (type == E1_UNIT_EXACT) {
             phi = u->end_phi;
         } else {
             int ok = 0;
-            if (u->type == E1_UNIT_HAT && prev_ok && prev_neg == u->neg && prev_k == u->anchor_k) {
+            if (type == E1_UNIT_HAT && prev_ok && prev_neg == neg && prev_k == u->anchor_k) {
                 const double D = e1_add(prev_p, -u->anchor_p);
                 if (D >= u->lo && D < u->hi) {
                     ok = 1;
-                    delta[(size_t)e * stride] = u->neg ? -D : D;
-                    phi = e1_add(u->end_phi, u->neg ? -D : D);
-                    u->last_p = e1_add(u->last_p, D);
+                    delta[e] = neg ? -D : D;
+                    phi = e1_add(u->end_phi, neg ? -D : D);
+                    last_p = e1_add(last_p, D);
                     stats[1]++;
                 }
             }
             if (!ok) {
-                u->end_phi = e1_carr_epoch_exact(phi, e1_mul(r->f_carr, delt), n_samp, tile, tiles_per_epoch,
-                                                 ck + (size_t)e * ck_epoch_stride, stride, &u->last_k, &u->last_p, &u->neg);
-                phi = u->end_phi;
+                phi = e1_carr_epoch_exact(phi, pp[e].sp, n_samp, tile, tiles_per_epoch, ck + (size_t)e * ck_epoch_stride, stride,
+                                          &last_k, &last_p, &neg);
                 stats[0]++;
             }
         }
-        prev_ok = u->last_k >= 1;
-        prev_neg = u->neg;
-        prev_k = u->last_k;
-        prev_p = u->last_p;
+        prev_ok = last_k >= 1;
+        prev_neg = neg;
+        prev_k = last_k;
+        prev_p = last_p;
     }
     return phi;
 }

@@ -36,7 +36,9 @@
 struct e1_synth_args {
     const e1_epoch_rec *recs;
     const e1_tile_ck *ck;
-    const double *delta; /* [n_epochs][max_chan] planner translation of each epoch's carrier checkpoints */
+    const double *delta; /* planner translation of each epoch's carrier checkpoints, channel-major:
+                            delta[ch * delta_stride + delta_off + e] for epoch e of this launch          */
+    int delta_stride, delta_off;
     const uint32_t *codes;
     const int32_t *lut;
     int16_t *out;
@@ -115,35 +117,45 @@ struct e1_plan_args {
     const e1_epoch_rec *recs;
     e1_tile_ck *ck;
     double *phase;   /* [max_chan] carried carrier phase (in: batch start, out: batch end) */
-    double *g, *dend, *est, *delta; /* [n_epochs][max_chan] */
+    e1_prep *prep;   /* channel-major [max_chan][n_epochs], like g, dend, est, delta and units */
+    double *g, *dend, *est, *delta;
     e1_unit *units;
     unsigned long long *counters; /* [2] serial epochs, [3] HAT epochs */
     double delt;
     int n_epochs, n_samp, max_chan, tile, tiles_per_epoch;
 };
 
+__global__ void e1_v2_prep_kernel(const e1_plan_args P)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x; /* record order: coalesced reads */
+    if (i >= P.n_epochs * P.max_chan)
+        return;
+    int e = i / P.max_chan, ch = i - e * P.max_chan;
+    e1_v2_prep(&P.recs[i], P.delt, &P.prep[(size_t)ch * P.n_epochs + e]);
+}
+
 __global__ void e1_v2_ideal_kernel(const e1_plan_args P)
 {
     int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch < P.max_chan)
-        e1_v2_ideal_prefix(P.recs + ch, P.max_chan, P.n_epochs, P.phase[ch], P.n_samp, P.delt, P.g + ch);
+        e1_v2_ideal_prefix(P.prep + (size_t)ch * P.n_epochs, P.n_epochs, P.phase[ch], P.n_samp, P.g + (size_t)ch * P.n_epochs);
 }
 
 __global__ void e1_v2_drift_kernel(const e1_plan_args P)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x; /* channel-major: a warp walks one channel's epochs */
     if (i >= P.n_epochs * P.max_chan)
         return;
-    int ch = i / P.n_epochs, e = i - ch * P.n_epochs;
-    size_t j = (size_t)e * P.max_chan + ch;
-    P.dend[j] = e1_v2_drift_unit(&P.recs[j], P.g[j], P.n_samp, P.delt);
+    P.dend[i] = e1_v2_drift_unit(&P.prep[i], P.g[i], P.n_samp);
 }
 
 __global__ void e1_v2_estimate_kernel(const e1_plan_args P)
 {
     int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch < P.max_chan)
-        e1_v2_estimate_prefix(P.recs + ch, P.max_chan, P.n_epochs, P.phase[ch], P.g + ch, P.dend + ch, P.est + ch);
+    if (ch >= P.max_chan)
+        return;
+    size_t o = (size_t)ch * P.n_epochs;
+    e1_v2_estimate_prefix(P.prep + o, P.n_epochs, P.phase[ch], P.g + o, P.dend + o, P.est + o);
 }
 
 __global__ void e1_v2_span_kernel(const e1_plan_args P)
@@ -152,10 +164,8 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
     if (i >= P.n_epochs * P.max_chan)
         return;
     int ch = i / P.n_epochs, e = i - ch * P.n_epochs;
-    size_t j = (size_t)e * P.max_chan + ch;
-    e1_v2_span_unit(&P.recs[j], e ? &P.recs[j - P.max_chan] : nullptr, e, P.phase[ch], e ? P.est[j - P.max_chan] : 0.0, P.n_samp,
-                    P.tile, P.tiles_per_epoch, P.delt, P.ck + (size_t)e * P.tiles_per_epoch * P.max_chan + ch, P.max_chan,
-                    &P.units[j]);
+    e1_v2_span_unit(&P.prep[i], e ? &P.prep[i - 1] : nullptr, e, P.phase[ch], e ? P.est[i - 1] : 0.0, P.n_samp, P.tile,
+                    P.tiles_per_epoch, P.ck + (size_t)e * P.tiles_per_epoch * P.max_chan + ch, P.max_chan, &P.units[i]);
 }
 
 __global__ void e1_v2_chain_kernel(const e1_plan_args P)
@@ -164,8 +174,9 @@ __global__ void e1_v2_chain_kernel(const e1_plan_args P)
     if (ch >= P.max_chan)
         return;
     unsigned long long st[2] = {0, 0};
-    P.phase[ch] = e1_v2_chain(P.recs + ch, P.max_chan, P.n_epochs, P.phase[ch], P.n_samp, P.tile, P.tiles_per_epoch, P.delt,
-                              P.units + ch, P.ck + ch, (size_t)P.tiles_per_epoch * P.max_chan, P.delta + ch, st);
+    size_t o = (size_t)ch * P.n_epochs;
+    P.phase[ch] = e1_v2_chain(P.prep + o, P.n_epochs, P.phase[ch], P.n_samp, P.tile, P.tiles_per_epoch, P.units + o, P.ck + ch,
+                              P.max_chan, (size_t)P.tiles_per_epoch * P.max_chan, P.delta + o, st);
     if (st[0])
         atomicAdd(&P.counters[2], st[0]);
     if (st[1])
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS) e1_synth_kernel(const e1_syn
             const e1_tile_ck c = A.ck[(size_t)tile_id * A.max_chan + tid];
             if (c.sym & E1_CK_ACTIVE) {
                 e1_chan_par p;
-                e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + tid], A.delt, A.tile, A.delta[(size_t)e * A.max_chan + tid], &p);
+                e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + tid], A.delt, A.tile, A.delta[(size_t)tid * A.delta_stride + A.delta_off + e], &p);
                 if (c.sym & E1_CK_ERROR)
                     atomicAdd(&s_cnt[1], 1ull);
                 s_par[atomicAdd(&s_nact, 1)] = p;

@@ -39,6 +39,8 @@ struct e1b200_ctx {
     unsigned long long *d_counters; /* [0] exact-fallback samples [1] planner errors [2] serial epochs [3] HAT epochs */
     e1_tile_ck *d_ck;
     double *d_g, *d_dend, *d_est, *d_delta;
+    e1_prep *d_prep;
+    int plan_n;               /* epochs in the current plan (stride of the channel-major arrays) */
     e1_unit *d_units;
     e1_epoch_rec *d_recs;     /* staging for the host entry points / restate output */
     e1_range_rec *d_ranges;
@@ -219,6 +221,7 @@ int e1b200_destroy(e1b200_ctx *ctx)
     cudaFree(ctx->d_est);
     cudaFree(ctx->d_delta);
     cudaFree(ctx->d_units);
+    cudaFree(ctx->d_prep);
     cudaFree(ctx->d_recs);
     cudaFree(ctx->d_ranges);
     cudaFree(ctx->d_out[0]);
@@ -285,6 +288,7 @@ static int ensure_plan_scratch(e1b200_ctx *ctx)
         CK(cudaMalloc(&ctx->d_dend, sizeof(double) * ne));
         CK(cudaMalloc(&ctx->d_est, sizeof(double) * ne));
         CK(cudaMalloc(&ctx->d_units, sizeof(e1_unit) * ne));
+        CK(cudaMalloc(&ctx->d_prep, sizeof(e1_prep) * ne));
     }
     return E1B200_OK;
 }
@@ -317,6 +321,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
     if (rc)
         return rc;
     const int nthr = n * cfg->max_chan;
+    ctx->plan_n = n;
     e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
                                                                      ctx->tile, ctx->tiles_per_epoch, ctx->delt);
     if (ctx->serial_planner) {
@@ -324,11 +329,14 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
                                                                              cfg->samples_per_epoch, ctx->tile,
                                                                              ctx->tiles_per_epoch, ctx->delt);
         ctx->timing.kernel_launches += 2;
+        /* the serial planner writes final checkpoints: translations are zero */
+        CK(cudaMemsetAsync(ctx->d_delta, 0, sizeof(double) * (size_t)nthr, ctx->stream));
     } else {
         e1_plan_args P;
         P.recs = d_recs;
         P.ck = ctx->d_ck;
         P.phase = ctx->d_phase;
+        P.prep = ctx->d_prep;
         P.g = ctx->d_g;
         P.dend = ctx->d_dend;
         P.est = ctx->d_est;
@@ -342,12 +350,13 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
         P.tile = ctx->tile;
         P.tiles_per_epoch = ctx->tiles_per_epoch;
         const int cb = (cfg->max_chan + 31) / 32;
+        e1_v2_prep_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(P);
         e1_v2_ideal_kernel<<<cb, 32, 0, ctx->stream>>>(P);
         e1_v2_drift_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
         e1_v2_estimate_kernel<<<cb, 32, 0, ctx->stream>>>(P);
         e1_v2_span_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
         e1_v2_chain_kernel<<<cb, 32, 0, ctx->stream>>>(P);
-        ctx->timing.kernel_launches += 6;
+        ctx->timing.kernel_launches += 7;
     }
     CK(cudaGetLastError());
     return mark(ctx, 0, 1);
@@ -360,7 +369,9 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     e1_synth_args A;
     A.recs = d_recs_plan + (size_t)e_off * cfg->max_chan;
     A.ck = ctx->d_ck + (size_t)e_off * ctx->tiles_per_epoch * cfg->max_chan;
-    A.delta = ctx->d_delta + (size_t)e_off * cfg->max_chan;
+    A.delta = ctx->d_delta;
+    A.delta_stride = ctx->plan_n;
+    A.delta_off = e_off;
     A.codes = ctx->d_codes;
     A.lut = ctx->d_lut;
     A.out = d_out;

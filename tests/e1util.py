@@ -292,7 +292,8 @@ def synthetic_recs_fast(n_epochs, n_chan, fs_hz, seed=0, max_chan=None, f_max=40
     recs = np.zeros((n_epochs, max_chan), REC_DTYPE)
     e = np.arange(n_epochs)[:, None]
     f0 = rng.uniform(-f_max, f_max, n_chan)[None, :]
-    f = f0 + rng.uniform(-0.1, 0.1, (n_epochs, n_chan)) * (e + 1)
+    # smooth Doppler: a constant rate of up to +-0.1 Hz per 0.1 s block (MEO passes stay below ~1 Hz/s)
+    f = f0 + rng.uniform(-0.1, 0.1, n_chan)[None, :] * e
     ib0 = rng.integers(0, 500, n_chan)[None, :]
     ib = (ib0 + 25 * e) % 500
     v = recs[:, :n_chan]

@@ -104,29 +104,39 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
             phase[ch] = phi;
         }
     } else if (n_epochs > 0) {
+        /* channel-major planner arrays, passes in kernel order */
         const size_t ne = (size_t)n_epochs * max_chan;
-        std::vector<double> g(ne), dend(ne), est(ne);
+        std::vector<double> g(ne), dend(ne), est(ne), dcm(ne, 0.0);
         std::vector<e1_unit> units(ne);
-        for (int ch = 0; ch < max_chan; ch++)
-            e1_v2_ideal_prefix(recs + ch, max_chan, n_epochs, phase[ch], n_samp, delt, &g[ch]);
+        std::vector<e1_prep> prep(ne);
         for (int e = 0; e < n_epochs; e++)
             for (int ch = 0; ch < max_chan; ch++)
-                dend[(size_t)e * max_chan + ch] = e1_v2_drift_unit(&recs[(size_t)e * max_chan + ch], g[(size_t)e * max_chan + ch], n_samp, delt);
+                e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, &prep[(size_t)ch * n_epochs + e]);
         for (int ch = 0; ch < max_chan; ch++)
-            e1_v2_estimate_prefix(recs + ch, max_chan, n_epochs, phase[ch], &g[ch], &dend[ch], &est[ch]);
-        for (int e = 0; e < n_epochs; e++)
-            for (int ch = 0; ch < max_chan; ch++) {
-                const size_t i = (size_t)e * max_chan + ch;
-                e1_v2_span_unit(&recs[i], e ? &recs[i - max_chan] : nullptr, e, phase[ch], e ? est[i - max_chan] : 0.0, n_samp, tile,
-                                tpe, delt, &ck[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
+            e1_v2_ideal_prefix(&prep[(size_t)ch * n_epochs], n_epochs, phase[ch], n_samp, &g[(size_t)ch * n_epochs]);
+        for (size_t i = 0; i < ne; i++)
+            dend[i] = e1_v2_drift_unit(&prep[i], g[i], n_samp);
+        for (int ch = 0; ch < max_chan; ch++) {
+            const size_t o = (size_t)ch * n_epochs;
+            e1_v2_estimate_prefix(&prep[o], n_epochs, phase[ch], &g[o], &dend[o], &est[o]);
+        }
+        for (int ch = 0; ch < max_chan; ch++)
+            for (int e = 0; e < n_epochs; e++) {
+                const size_t i = (size_t)ch * n_epochs + e;
+                e1_v2_span_unit(&prep[i], e ? &prep[i - 1] : nullptr, e, phase[ch], e ? est[i - 1] : 0.0, n_samp, tile, tpe,
+                                &ck[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
             }
         for (int ch = 0; ch < max_chan; ch++) {
             unsigned long long st2[2] = {0, 0};
-            phase[ch] = e1_v2_chain(recs + ch, max_chan, n_epochs, phase[ch], n_samp, tile, tpe, delt, &units[ch], &ck[ch],
-                                    (size_t)tpe * max_chan, &delta[ch], st2);
+            const size_t o = (size_t)ch * n_epochs;
+            phase[ch] = e1_v2_chain(&prep[o], n_epochs, phase[ch], n_samp, tile, tpe, &units[o], &ck[ch], max_chan,
+                                    (size_t)tpe * max_chan, &dcm[o], st2);
             stats[3] += st2[0];
             stats[4] += st2[1];
         }
+        for (int ch = 0; ch < max_chan; ch++)
+            for (int e = 0; e < n_epochs; e++)
+                delta[(size_t)e * max_chan + ch] = dcm[(size_t)ch * n_epochs + e];
     }
     const uint32_t thr_carr = e1_thr_carr(tile, amb_scale), thr_code = e1_thr_code(tile, amb_scale);
     std::vector<e1_chan_par> par(max_chan);
@@ -193,21 +203,33 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
                                      tile, tpe, delt);
         p1[ch] = phi;
     }
-    for (int ch = 0; ch < max_chan; ch++)
-        e1_v2_ideal_prefix(recs + ch, max_chan, n_epochs, phase0[ch], n_samp, delt, &g[ch]);
-    for (size_t i = 0; i < ne; i++)
-        dend[i] = e1_v2_drift_unit(&recs[i], g[i], n_samp, delt);
-    for (int ch = 0; ch < max_chan; ch++)
-        e1_v2_estimate_prefix(recs + ch, max_chan, n_epochs, phase0[ch], &g[ch], &dend[ch], &est[ch]);
+    std::vector<e1_prep> prep(ne);
+    std::vector<double> dcm(ne, 0.0);
     for (int e = 0; e < n_epochs; e++)
-        for (int ch = 0; ch < max_chan; ch++) {
-            const size_t i = (size_t)e * max_chan + ch;
-            e1_v2_span_unit(&recs[i], e ? &recs[i - max_chan] : nullptr, e, phase0[ch], e ? est[i - max_chan] : 0.0, n_samp, tile, tpe,
-                            delt, &ck2[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
-        }
+        for (int ch = 0; ch < max_chan; ch++)
+            e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, &prep[(size_t)ch * n_epochs + e]);
     for (int ch = 0; ch < max_chan; ch++)
-        p2[ch] = e1_v2_chain(recs + ch, max_chan, n_epochs, phase0[ch], n_samp, tile, tpe, delt, &units[ch], &ck2[ch],
-                             (size_t)tpe * max_chan, &delta[ch], stats);
+        e1_v2_ideal_prefix(&prep[(size_t)ch * n_epochs], n_epochs, phase0[ch], n_samp, &g[(size_t)ch * n_epochs]);
+    for (size_t i = 0; i < ne; i++)
+        dend[i] = e1_v2_drift_unit(&prep[i], g[i], n_samp);
+    for (int ch = 0; ch < max_chan; ch++) {
+        const size_t o = (size_t)ch * n_epochs;
+        e1_v2_estimate_prefix(&prep[o], n_epochs, phase0[ch], &g[o], &dend[o], &est[o]);
+    }
+    for (int ch = 0; ch < max_chan; ch++)
+        for (int e = 0; e < n_epochs; e++) {
+            const size_t i = (size_t)ch * n_epochs + e;
+            e1_v2_span_unit(&prep[i], e ? &prep[i - 1] : nullptr, e, phase0[ch], e ? est[i - 1] : 0.0, n_samp, tile, tpe,
+                            &ck2[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
+        }
+    for (int ch = 0; ch < max_chan; ch++) {
+        const size_t o = (size_t)ch * n_epochs;
+        p2[ch] = e1_v2_chain(&prep[o], n_epochs, phase0[ch], n_samp, tile, tpe, &units[o], &ck2[ch], max_chan,
+                             (size_t)tpe * max_chan, &dcm[o], stats);
+    }
+    for (int ch = 0; ch < max_chan; ch++)
+        for (int e = 0; e < n_epochs; e++)
+            delta[(size_t)e * max_chan + ch] = dcm[(size_t)ch * n_epochs + e];
     long bad = 0;
     for (int e = 0; e < n_epochs; e++)
         for (int ch = 0; ch < max_chan; ch++) {
