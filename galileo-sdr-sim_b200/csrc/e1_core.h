@@ -266,7 +266,16 @@ E1_HD uint32_t e1_thr_code(int T, int scale)
 
 /* ------------------------------------------------------------------ records shared by planner and synthesis */
 #define E1C_N_PRN 50
-#define E1C_CODE_WORDS_PER_PRN 256
+/* Code table: per PRN, one 2-bit field per BOC(1,1) half-chip hh = 0..8183 (chip c = hh/2):
+ *   bit 0 = E1-B chip bit XOR (hh & 1)      bit 1 = E1-B chip bit XOR E1-C chip bit
+ * 16 half-chips per 32-bit word, field of hh at bits 2*(hh&15) of word hh/16; 512 data words
+ * plus zero padding (the sample loop reads word i and i+1).                                   */
+#define E1C_CODE_WORDS_PER_PRN 516
+/* Carrier table: int32 [2][4][512], value for (regime r, field t, index i):
+ *   t = 0,1 -> 0;  t = 2 -> -2*(cos + 65536*sin);  t = 3 -> +2*(cos + 65536*sin)
+ *   of table index i (r = 0, phase >= 0) or (-i)&511 (r = 1, phase < 0), where
+ *   t = code field XOR (D | (D^S)<<1), D = nav symbol bit, S = secondary-code bit.             */
+#define E1C_LUT_ENTRIES 4096
 #define E1C_RUN 4 /* consecutive samples per thread per group -> one 128-bit store */
 /* GALILEO_E1_SECONDARY_CODE (include/constants.h:213), bit i = symbol i */
 #define E1C_SEC25_MASK 0x009B501Cu
@@ -284,14 +293,18 @@ typedef struct e1_tile_ck { /* 32 bytes, one per (epoch, tile, channel) */
 #define E1_CK_ERROR 32u
 
 typedef struct e1_chan_par { /* per active channel of the current tile (shared memory) */
-    uint64_t U0, dU;        /* |carrier phase| and its per-sample step, 2^-64 cycle   */
-    uint64_t H0, dH;        /* code phase and step, 2^-51 half-chip                   */
-    uint64_t Hw;            /* code phase at j_w                                      */
+    uint64_t U0, dU;        /* |carrier phase| and its per-sample step, 2^-64 cycle           */
+    uint64_t HA, dH;        /* code phase at sample 0 and step, 2^-51 half-chip, + E1C_H_BIAS */
+    uint64_t HB;            /* code phase extrapolated back from j_w to sample 0, + bias      */
     int32_t j_w;
-    uint32_t misc;          /* bits 0-3 = ck.sym symbols, bit 4 reflect LUT, bit 5 force
-                               exact, bits 8-15 prn-1                                 */
-    double phi, sp, cp, sc; /* exact checkpoint for the literal fallback              */
+    uint32_t misc;          /* bits 0-1 symbol field before the code wrap, bits 2-3 after it,
+                               bit 4 negative-phase regime, bit 5 force the exact path,
+                               bits 8-15 prn-1                                                */
+    double phi, sp, cp, sc; /* exact checkpoint for the exact fallback                        */
 } e1_chan_par;
+/* H carries one unit of its high word's 19-bit fraction as a bias so that "within 2^-19 of a
+ * half-chip boundary" reads as "fraction bits 1..18 are zero" (the coarse test of the fast path) */
+#define E1C_H_BIAS (1ull << 32)
 
 E1_HD uint32_t e1_umulhi(uint32_t a, uint32_t b)
 {
@@ -814,21 +827,23 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     const int aligned = (p->phi == 0.0) || (p->sp == 0.0) || (neg == (p->sp < 0.0));
     p->U0 = e1_to_fixed(p->phi, E1_CARR_FIX);
     uint64_t s = e1_to_fixed(p->sp, E1_CARR_FIX);
-    uint32_t misc = (c->sym & 15u) | (neg ? 16u : 0u) | ((uint32_t)(r->prn - 1) << 8);
-    if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < 0.5))
-        misc |= 32u; /* outside the closed form's domain: literal path */
+    /* symbol fields: D | (D^S)<<1 from the planner's (D, S) pairs */
+    const uint32_t sa = c->sym & 3u, sb = (c->sym >> 2) & 3u;
+    uint32_t misc = ((sa ^ (sa << 1)) & 3u) | (((sb ^ (sb << 1)) & 3u) << 2) | (neg ? 16u : 0u) | ((uint32_t)(r->prn - 1) << 8);
+    if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < 0.5) || !(p->sc < 2.0))
+        misc |= 32u; /* outside the closed form's domain: exact path */
     if (!aligned) {
         /* |phi| shrinks; if it can reach zero inside the tile the sign regime changes
-           mid-tile: leave that (rare) tile to the literal path */
+           mid-tile: leave that (rare) tile to the exact path */
         if (e1_fabs(p->phi) <= e1_mul(e1_fabs(p->sp), (double)(tile + 2)))
             misc |= 32u;
         s = 0ull - s;
     }
     p->dU = s;
-    p->H0 = e1_to_fixed(p->cp, E1_CODE_FIX);
     p->dH = e1_to_fixed(p->sc, E1_CODE_FIX);
-    p->Hw = e1_to_fixed(c->cp_w, E1_CODE_FIX);
+    p->HA = e1_to_fixed(p->cp, E1_CODE_FIX) + E1C_H_BIAS;
     p->j_w = c->j_w;
+    p->HB = (c->j_w == E1C_NO_WRAP) ? p->HA : e1_to_fixed(c->cp_w, E1_CODE_FIX) + E1C_H_BIAS - (uint64_t)(uint32_t)c->j_w * p->dH;
     p->misc = misc;
 }
 
@@ -856,19 +871,20 @@ static __device__ __noinline__ void e1_exact_indices(const e1_chan_par *p, int j
 #define e1_exact_indices e1_exact_indices_impl
 #endif
 
-/* One channel's contribution to the E1C_RUN consecutive samples starting at tile-relative j0
- * (src/galileo-sdr.cpp:509-525).  acc[i] accumulates I + 65536*Q.  `codes` is the 2-bit chip
- * table (all PRNs), `lut` the 1024-entry carrier table.  With exact == 0 the return value is
- * nonzero if any sample was ambiguous; with exact != 0 ambiguous samples are resolved by
- * e1_exact_indices and counted in *n_exact. */
-E1_HD uint32_t e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const int32_t *lut_base, int j0, int *acc,
+/* Reference form of one channel's contribution to the E1C_RUN consecutive samples starting at
+ * tile-relative j0 (src/galileo-sdr.cpp:509-525): full-precision closed form, full-precision
+ * ambiguity test, any position of the code wrap.  acc[i] accumulates I + 65536*Q.  With
+ * exact == 0 the return value is nonzero if any sample was ambiguous; with exact != 0 ambiguous
+ * samples are resolved by e1_exact_indices and counted in *n_exact.  The kernel uses it for the
+ * (rare) runs the fast form below hands back and for the exact re-evaluation. */
+E1_HD uint32_t e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const int32_t *lut4, int j0, int *acc,
                               uint32_t thr_carr, uint32_t thr_code, const int exact, unsigned long long *n_exact)
 {
-    const uint64_t U0 = p->U0, dU = p->dU, H0 = p->H0, dH = p->dH, Hw = p->Hw;
+    const uint64_t U0 = p->U0, dU = p->dU, HA = p->HA, dH = p->dH, HB = p->HB;
     const int jw = p->j_w;
     const uint32_t misc = p->misc;
     const uint32_t *code = codes + ((misc >> 8) & 0xffu) * E1C_CODE_WORDS_PER_PRN;
-    const int32_t *lut = lut_base + ((misc & 16u) ? 512 : 0);
+    const int32_t *lut = lut4 + ((misc & 16u) ? 2048 : 0);
     const uint32_t force = (misc >> 5) & 1u;
     uint32_t amb = 0;
     uint64_t U = U0 + (uint64_t)(uint32_t)j0 * dU;
@@ -878,7 +894,7 @@ E1_HD uint32_t e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const
     for (int i = 0; i < E1C_RUN; i++) {
         const int j = j0 + i;
         const int after = j >= jw;
-        const uint64_t H = (after ? Hw : H0) + (uint64_t)(uint32_t)(after ? j - jw : j) * dH;
+        const uint64_t H = (after ? HB : HA) + (uint64_t)(uint32_t)j * dH - E1C_H_BIAS;
         const uint32_t ds = after ? (misc >> 2) & 3u : misc & 3u;
         /* carrier: y = 511*|phi| in 9.32 fixed point */
         const uint32_t lo511 = e1_umulhi((uint32_t)U, 511u);
@@ -899,13 +915,70 @@ E1_HD uint32_t e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const
         } else {
             amb |= a;
         }
-        const uint32_t c = h >> 1;
-        const uint32_t v = code[c >> 4] >> ((c & 15u) * 2u);
-        /* sign bits of E1B*data and E1C*secondary; the BOC(1,1) sub-carrier negates even half-chips */
-        const uint32_t t = v ^ ds ^ ((h & 1u) ? 0u : 3u);
-        const int m = (int)((t >> 1) & 1u) - (int)(t & 1u);
-        acc[i] += m * lut[it];
+        const uint32_t t = ((code[h >> 4] >> ((h & 15u) * 2u)) ^ ds) & 3u;
+        acc[i] += lut[t * 512u + it];
         U += dU;
+    }
+    return amb;
+}
+
+E1_HD uint32_t e1_funnel_r(uint32_t lo, uint32_t hi, uint32_t n) /* low word of (hi:lo) >> (n & 31) */
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, n);
+#else
+    n &= 31u;
+    return n ? (lo >> n) | (hi << (32u - n)) : lo;
+#endif
+}
+
+/* Fast form of the same thing for the common run: the code wrap does not fall strictly inside
+ * it.  Differences from the reference form, all conservative:
+ *   - the carrier index comes from the high word of U only, stepped by the high word of dU: the
+ *     9.32 product is off by < 2048 units, so the ambiguity band is thr_carr + 2048 units wide;
+ *   - the code ambiguity test looks at the high word of H only (19 fraction bits, biased by one
+ *     unit): "fraction bits 1..18 zero" is a superset of the exact band;
+ *   - sign, zero and sub-carrier are folded into the table address: one LDS yields the term.
+ * Returns nonzero if any sample needs the reference form (the caller then redoes the thread's
+ * samples with exact != 0).  lutb is the carrier table as bytes (16 KiB, 8 KiB-aligned offset
+ * arithmetic inside), thr2 = 2*(thr_carr + 2048) + 1.                                          */
+E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lutb, int j0, int *acc,
+                           uint32_t thr_carr, uint32_t thr_code)
+{
+    const int jw = p->j_w;
+    const uint32_t misc = p->misc;
+    if ((j0 < jw && jw < j0 + E1C_RUN) || (misc & 32u))
+        return e1_channel_run(p, codes, (const int32_t *)lutb, j0, acc, thr_carr, thr_code, 0, (unsigned long long *)0);
+    const int after = j0 >= jw;
+    const uint64_t dH = p->dH;
+    uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * dH;
+    const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
+    uint32_t uh = (uint32_t)(U >> 32);
+    const uint32_t duh = (uint32_t)(p->dU >> 32);
+    const uint32_t tc = thr_carr + 2048u;
+    const uint64_t ybias = (uint64_t)tc;
+    const uint32_t ds = after ? (misc >> 2) & 3u : misc & 3u;
+    /* byte offset of lut4[regime][ds][0]: the code field is XORed into bits 11-12 below */
+    const uint32_t kbase = ((misc & 16u) << 9) | (ds << 11);
+    const uint32_t *code = codes + ((misc >> 8) & 0xffu) * E1C_CODE_WORDS_PER_PRN;
+    const uint32_t h0 = (uint32_t)(H >> 51);
+    const uint32_t win = e1_funnel_r(code[h0 >> 4], code[(h0 >> 4) + 1], (h0 & 15u) * 2u); /* half-chips h0..h0+15 */
+    const uint32_t rot0 = 21u - 2u * h0; /* rotate so that the field of half-chip h lands on bits 11-12 */
+    uint32_t amb = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < E1C_RUN; i++) {
+        const uint32_t hh = (uint32_t)(H >> 32);
+        amb |= (uint32_t)((hh & 0x7fffeu) == 0u);
+        const uint32_t h = hh >> 19;
+        const uint32_t vv = e1_funnel_r(win, win, 2u * h + rot0);
+        const uint64_t y = (uint64_t)uh * 511u + ybias;
+        amb |= (uint32_t)((uint32_t)y < 2u * tc + 1u);
+        const uint32_t off = (kbase + ((uint32_t)(y >> 32) << 2)) ^ (vv & 0x1800u);
+        acc[i] += *(const int32_t *)(lutb + off);
+        H += dH;
+        uh += duh;
     }
     return amb;
 }
@@ -915,6 +988,33 @@ E1_HD uint32_t e1_pack_iq(int acc)
 {
     const uint32_t x = (uint32_t)acc;
     return x + ((x & 0x8000u) << 1);
+}
+
+/* Host-side table builders (the product's C-ABI calls them at create(); tests/hostsim too).
+ * cos512/sin512: the reference's carrier tables (include/constants.h:216-284); b_words/c_words:
+ * the E1-B / E1-C primary codes of one PRN, chip j = bit 31-(j%32) of word j/32.              */
+E1_HD void e1_build_lut4(const int *cos512, const int *sin512, int32_t *lut4)
+{
+    for (int r = 0; r < 2; r++)
+        for (int i = 0; i < 512; i++) {
+            const int k = r ? ((-i) & 511) : i;
+            const int32_t w2 = 2 * (cos512[k] + 65536 * sin512[k]);
+            lut4[(r * 4 + 0) * 512 + i] = 0;
+            lut4[(r * 4 + 1) * 512 + i] = 0;
+            lut4[(r * 4 + 2) * 512 + i] = -w2;
+            lut4[(r * 4 + 3) * 512 + i] = w2;
+        }
+}
+E1_HD void e1_build_code_words(const uint32_t *b_words, const uint32_t *c_words, uint32_t *out)
+{
+    for (int i = 0; i < E1C_CODE_WORDS_PER_PRN; i++)
+        out[i] = 0;
+    for (int hh = 0; hh < 2 * E1C_CODE_LEN; hh++) {
+        const int c = hh >> 1;
+        const uint32_t b = (b_words[c >> 5] >> (31 - (c & 31))) & 1u, q = (c_words[c >> 5] >> (31 - (c & 31))) & 1u;
+        const uint32_t f = (b ^ (uint32_t)(hh & 1)) | ((b ^ q) << 1);
+        out[hh >> 4] |= f << ((hh & 15) * 2);
+    }
 }
 
 #endif /* E1_CORE_H */

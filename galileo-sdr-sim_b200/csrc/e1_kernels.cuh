@@ -10,10 +10,9 @@
  *   recs   e1_epoch_rec[n_epochs][max_chan]                         176 B each (caller / H2D)
  *   ck     e1_tile_ck[n_epochs][tiles_per_epoch][max_chan]           32 B each (scratch)
  *   out    int16 I,Q interleaved, sample (epoch*N + k) at byte 4*(epoch*N + k)
- *   codes  uint32[50][256]: chip c of PRN p -> bits 2*(c&15) (E1-B) and 2*(c&15)+1 (E1-C)
- *          of word p*256 + c/16; a set bit means chip level -1        51 200 B, smem-resident
- *   lut    int32[1024]: 2*(cos + 65536*sin) for index i (first 512) and for index (-i)&511
- *          (second 512, used while the carrier phase is negative)      4 096 B, smem-resident
+ *   codes  uint32[50][516]: one 2-bit field per BOC(1,1) half-chip (see e1_core.h)   103 200 B
+ *   lut    int32[2][4][512]: carrier term by (phase regime, code/symbol field, index) 16 384 B
+ *          both smem-resident, loaded once per persistent CTA with cp.async.bulk
  */
 #ifndef E1_KERNELS_CUH
 #define E1_KERNELS_CUH
@@ -27,9 +26,9 @@
 
 #define E1_CODE_WORDS_PER_PRN E1C_CODE_WORDS_PER_PRN
 #define E1_CODES_BYTES (E1C_N_PRN * E1_CODE_WORDS_PER_PRN * 4)
-#define E1_LUT_ENTRIES 1024
+#define E1_LUT_ENTRIES E1C_LUT_ENTRIES
 #define E1_LUT_BYTES (E1_LUT_ENTRIES * 4)
-#define E1_SYNTH_THREADS 256
+#define E1_SYNTH_THREADS 512
 #define E1_RUN E1C_RUN
 #define E1_GROUP (E1_SYNTH_THREADS * E1_RUN)
 
@@ -136,7 +135,9 @@ __global__ void e1_v2_prep_kernel(const e1_plan_args P)
 
 __global__ void e1_v2_ideal_kernel(const e1_plan_args P)
 {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = blockIdx.x; /* one channel per block: serial walks of different channels must not share a warp */
+    if (threadIdx.x != 0)
+        return;
     if (ch < P.max_chan)
         e1_v2_ideal_prefix(P.prep + (size_t)ch * P.n_epochs, P.n_epochs, P.phase[ch], P.n_samp, P.g + (size_t)ch * P.n_epochs);
 }
@@ -151,7 +152,9 @@ __global__ void e1_v2_drift_kernel(const e1_plan_args P)
 
 __global__ void e1_v2_estimate_kernel(const e1_plan_args P)
 {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = blockIdx.x; /* one channel per block: serial walks of different channels must not share a warp */
+    if (threadIdx.x != 0)
+        return;
     if (ch >= P.max_chan)
         return;
     size_t o = (size_t)ch * P.n_epochs;
@@ -170,7 +173,9 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
 
 __global__ void e1_v2_chain_kernel(const e1_plan_args P)
 {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = blockIdx.x; /* one channel per block: serial walks of different channels must not share a warp */
+    if (threadIdx.x != 0)
+        return;
     if (ch >= P.max_chan)
         return;
     unsigned long long st[2] = {0, 0};
@@ -215,7 +220,7 @@ __device__ __forceinline__ void e1_mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 template <int G>
-__global__ void __launch_bounds__(E1_SYNTH_THREADS) e1_synth_kernel(const e1_synth_args A)
+__global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_synth_args A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
@@ -274,27 +279,34 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS) e1_synth_kernel(const e1_syn
 #pragma unroll
             for (int i = 0; i < E1_RUN; i++)
                 acc[g][i] = 0;
-        uint32_t amb = 0;
+        uint32_t amb[G];
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            amb[g] = 0;
+        const unsigned char *lutb = reinterpret_cast<const unsigned char *>(s_lut);
         for (int a = 0; a < nact; a++) {
 #pragma unroll
             for (int g = 0; g < G; g++)
-                amb |= e1_channel_run(&s_par[a], s_codes, s_lut, g * E1_GROUP + tid * E1_RUN, acc[g], A.thr_carr,
-                                      A.thr_code, 0, nullptr);
+                amb[g] |= e1_run_fast(&s_par[a], s_codes, lutb, g * E1_GROUP + tid * E1_RUN, acc[g], A.thr_carr, A.thr_code);
         }
-        if (amb) { /* rare: redo this thread's samples, resolving ambiguous ones exactly */
-            unsigned long long n_exact = 0;
+        /* rare: some channel flagged a sample of run g.  Find the channel(s) by re-running the fast
+           form into a scratch accumulator, take their fast terms back out and add the exact ones. */
 #pragma unroll
-            for (int g = 0; g < G; g++)
+        for (int g = 0; g < G; g++) {
+            if (amb[g]) {
+                unsigned long long n_exact = 0;
+                const int j0 = g * E1_GROUP + tid * E1_RUN;
+                for (int a = 0; a < nact; a++) {
+                    int t4[E1_RUN] = {0, 0, 0, 0};
+                    if (e1_run_fast(&s_par[a], s_codes, lutb, j0, t4, A.thr_carr, A.thr_code)) {
 #pragma unroll
-                for (int i = 0; i < E1_RUN; i++)
-                    acc[g][i] = 0;
-            for (int a = 0; a < nact; a++) {
-#pragma unroll
-                for (int g = 0; g < G; g++)
-                    e1_channel_run(&s_par[a], s_codes, s_lut, g * E1_GROUP + tid * E1_RUN, acc[g], A.thr_carr,
-                                   A.thr_code, 1, &n_exact);
+                        for (int i = 0; i < E1_RUN; i++)
+                            acc[g][i] -= t4[i];
+                        e1_channel_run(&s_par[a], s_codes, s_lut, j0, acc[g], A.thr_carr, A.thr_code, 1, &n_exact);
+                    }
+                }
+                atomicAdd(&s_cnt[0], n_exact);
             }
-            atomicAdd(&s_cnt[0], n_exact);
         }
         /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
         int16_t *out_tile = A.out + ((size_t)e * A.n_samp + (size_t)t * A.tile) * 2;

@@ -69,7 +69,7 @@ static int fail(e1b200_ctx *c, int code, const char *what, cudaError_t ce)
 
 /* include/constants.h:216-284: round(250*cos(2*pi*(i+1/2)/512)), except the four entries per
  * table whose exact value is +-105.5, which the reference stores as +-105 */
-static void build_lut(int32_t *lut)
+static void build_lut(int32_t *lut4)
 {
     static const int cos_fix[4] = {92, 163, 348, 419}, sin_fix[4] = {35, 220, 291, 476};
     int c[512], s[512];
@@ -82,23 +82,14 @@ static void build_lut(int32_t *lut)
         c[cos_fix[k]] = c[cos_fix[k]] > 0 ? 105 : -105;
         s[sin_fix[k]] = s[sin_fix[k]] > 0 ? 105 : -105;
     }
-    for (int i = 0; i < 512; i++) {
-        lut[i] = 2 * (c[i] + 65536 * s[i]);
-        int r = (-i) & 511;
-        lut[512 + i] = 2 * (c[r] + 65536 * s[r]);
-    }
+    e1_build_lut4(c, s, lut4);
 }
 
-/* src/gal-sig.cpp:9-233 without the BOC expansion: 2 bits per chip (E1-B, E1-C), set = level -1 */
+/* src/gal-sig.cpp:9-233 (hex -> chips -> BOC(1,1) half-chips) in the packed layout of e1_core.h */
 static void build_codes(uint32_t *codes)
 {
-    memset(codes, 0, E1_CODES_BYTES);
     for (int p = 0; p < E1C_N_PRN; p++)
-        for (int c = 0; c < E1_CODE_LEN; c++) {
-            uint32_t b = (E1B_PRN_WORDS[p][c >> 5] >> (31 - (c & 31))) & 1u;
-            uint32_t q = (E1C_PRN_WORDS[p][c >> 5] >> (31 - (c & 31))) & 1u;
-            codes[p * E1_CODE_WORDS_PER_PRN + (c >> 4)] |= (b | (q << 1)) << ((c & 15) * 2);
-        }
+        e1_build_code_words(E1B_PRN_WORDS[p], E1C_PRN_WORDS[p], codes + (size_t)p * E1_CODE_WORDS_PER_PRN);
 }
 
 static int env_int(const char *name, int dflt)
@@ -132,11 +123,11 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     if (!(cfg->fs_hz > 0.0) || cfg->samples_per_epoch < 1 || cfg->max_chan < 1 || cfg->max_chan > E1B200_MAX_CHAN)
         return E1B200_EINVAL;
     /* one code period must not fit twice in a tile: tile * (1.023e6+margin)/fs < 4092 */
-    int groups = 4;
+    int groups = 4; /* tile = groups * 2048 samples */
     while (groups > 1 && (double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
         groups >>= 1;
     if ((double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
-        return E1B200_EINVAL; /* fs below ~0.27 MS/s */
+        return E1B200_EINVAL; /* fs below ~0.53 MS/s */
     groups = env_int("E1B200_GROUPS", groups);
     if (!synth_for(groups))
         return E1B200_EINVAL;
@@ -349,7 +340,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
         P.max_chan = cfg->max_chan;
         P.tile = ctx->tile;
         P.tiles_per_epoch = ctx->tiles_per_epoch;
-        const int cb = (cfg->max_chan + 31) / 32;
+        const int cb = cfg->max_chan; /* one channel per block */
         e1_v2_prep_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(P);
         e1_v2_ideal_kernel<<<cb, 32, 0, ctx->stream>>>(P);
         e1_v2_drift_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);

@@ -51,16 +51,15 @@ unsigned long long hs_to_fixed(double x, int sh) { return e1_to_fixed(x, sh); }
 
 void hs_build_codes(uint32_t *codes)
 {
-    memset(codes, 0, E1C_N_PRN * E1C_CODE_WORDS_PER_PRN * 4);
     for (int p = 0; p < E1C_N_PRN; p++)
-        for (int c = 0; c < 4092; c++) {
-            uint32_t b = (E1B_PRN_WORDS[p][c >> 5] >> (31 - (c & 31))) & 1u;
-            uint32_t q = (E1C_PRN_WORDS[p][c >> 5] >> (31 - (c & 31))) & 1u;
-            codes[p * E1C_CODE_WORDS_PER_PRN + (c >> 4)] |= (b | (q << 1)) << ((c & 15) * 2);
-        }
+        e1_build_code_words(E1B_PRN_WORDS[p], E1C_PRN_WORDS[p], codes + (size_t)p * E1C_CODE_WORDS_PER_PRN);
 }
 
-// Whole pipeline on the host.  lut: int32[1024] as the product builds it (passed in by the test
+void hs_build_lut4(const int *cos512, const int *sin512, int32_t *lut4) { e1_build_lut4(cos512, sin512, lut4); }
+
+int hs_code_words_per_prn(void) { return E1C_CODE_WORDS_PER_PRN; }
+
+// Whole pipeline on the host.  lut: int32[2][4][512] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
 // stats[0] = samples resolved by the literal fallback, stats[1] = planner errors,
 // stats[2] = threads that took the slow path.
@@ -83,7 +82,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                       int16_t *out, int groups, int amb_scale, const int32_t *lut, unsigned long long *stats, int planner)
 {
     const double delt = 1.0 / fs_hz;
-    const int threads = 256, tile = groups * threads * E1C_RUN;
+    const int threads = 512, tile = groups * threads * E1C_RUN;
     const int tpe = (n_samp + tile - 1) / tile;
     std::vector<uint32_t> codes(E1C_N_PRN * E1C_CODE_WORDS_PER_PRN);
     hs_build_codes(codes.data());
@@ -162,12 +161,17 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                     int acc[E1C_RUN] = {0, 0, 0, 0};
                     uint32_t amb = 0;
                     for (int a = 0; a < nact; a++)
-                        amb |= e1_channel_run(&par[a], codes.data(), lut, j0, acc, thr_carr, thr_code, 0, nullptr);
+                        amb |= e1_run_fast(&par[a], codes.data(), (const unsigned char *)lut, j0, acc, thr_carr, thr_code);
                     if (amb) {
                         stats[2]++;
-                        memset(acc, 0, sizeof acc);
-                        for (int a = 0; a < nact; a++)
-                            e1_channel_run(&par[a], codes.data(), lut, j0, acc, thr_carr, thr_code, 1, &stats[0]);
+                        for (int a = 0; a < nact; a++) {
+                            int t4[E1C_RUN] = {0, 0, 0, 0};
+                            if (e1_run_fast(&par[a], codes.data(), (const unsigned char *)lut, j0, t4, thr_carr, thr_code)) {
+                                for (int i = 0; i < E1C_RUN; i++)
+                                    acc[i] -= t4[i];
+                                e1_channel_run(&par[a], codes.data(), lut, j0, acc, thr_carr, thr_code, 1, &stats[0]);
+                            }
+                        }
                     }
                     for (int i = 0; i < E1C_RUN; i++)
                         if (j0 + i < n_valid) {
@@ -187,7 +191,7 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
                      int groups, unsigned long long *stats)
 {
     const double delt = 1.0 / fs_hz;
-    const int tile = groups * 256 * E1C_RUN;
+    const int tile = groups * 512 * E1C_RUN;
     const int tpe = (n_samp + tile - 1) / tile;
     const size_t ne = (size_t)n_epochs * max_chan;
     std::vector<e1_tile_ck> ck1(ne * tpe), ck2(ne * tpe);

@@ -71,20 +71,24 @@ def test_fixed_point_conversion():
 
 
 def test_code_table_matches_oracle_halfchips():
-    """2-bit chip table (product layout) -> the oracle's 8184-entry BOC(1,1) tables, all 50 PRNs."""
+    """Packed half-chip table (product layout: bit0 = E1-B bit ^ (hh&1), bit1 = E1-B ^ E1-C) -> the
+    oracle's 8184-entry BOC(1,1) tables, all 50 PRNs."""
     hs = U.hostsim()
-    codes = np.zeros(50 * 256, np.uint32)
+    W = hs.hs_code_words_per_prn()
+    codes = np.zeros(50 * W, np.uint32)
     hs.hs_build_codes(codes.ctypes.data)
     lib = U.oracle()
-    t = (C.c_short * 8184)()
-    c = np.arange(4092)
+    tb, tc = (C.c_short * 8184)(), (C.c_short * 8184)()
+    hh = np.arange(8184)
     for prn in range(1, 51):
-        w = codes[(prn - 1) * 256 + (c >> 4)] >> ((c & 15) * 2)
-        for is_c in (0, 1):
-            lib.e1o_halfchip_table(prn, is_c, t)
-            chip = 1 - 2 * ((w >> is_c) & 1).astype(np.int64)
-            ref = np.array(t)
-            assert np.array_equal(ref[1::2], chip) and np.array_equal(ref[0::2], -chip), (prn, is_c)
+        f = (codes[(prn - 1) * W + (hh >> 4)] >> ((hh & 15) * 2)) & 3
+        lib.e1o_halfchip_table(prn, 0, tb)
+        lib.e1o_halfchip_table(prn, 1, tc)
+        eb, ec = np.array(tb), np.array(tc)          # +-1 including the sub-carrier sign
+        # bit0 = B ^ (hh&1): the E1-B half-chip is -chip on even hh -> level +1 exactly when bit0 == 1 ... check both
+        assert np.array_equal(eb, np.where((f & 1) == 1, 1, -1) * 1), prn
+        assert np.array_equal(ec, np.where(((f & 1) ^ (f >> 1)) == 1, 1, -1)), prn
+        assert not codes[(prn - 1) * W + 512:(prn - 1) * W + W].any()
 
 
 @pytest.mark.parametrize("name,epochs", [("cfg1", (0, 1, 2, 28, 29, 30, 98)), ("paris45", (0, 1, 190, 191, 300, 301, 448))])
