@@ -266,17 +266,27 @@ E1_HD uint32_t e1_thr_code(int T, int scale)
 
 /* ------------------------------------------------------------------ records shared by planner and synthesis */
 #define E1C_N_PRN 50
-/* Code table: per PRN, one 2-bit field per BOC(1,1) half-chip hh = 0..8183 (chip c = hh/2):
- *   bit 0 = E1-B chip bit XOR (hh & 1)      bit 1 = E1-B chip bit XOR E1-C chip bit
- * 16 half-chips per 32-bit word, field of hh at bits 2*(hh&15) of word hh/16; 512 data words
- * plus zero padding (the sample loop reads word i and i+1).                                   */
+/* Code table: per PRN, one 2-bit field per BOC(1,1) half-chip hh = 0..8183 (chip c = hh/2), sixteen
+ * half-chips per 32-bit word, FIRST half-chip in the TOP bits: field of hh at bits 31-2k, 30-2k of
+ * word hh/16, k = hh & 15.  With bneg / cneg = 1 where the E1-B / E1-C half-chip value is -1
+ * (src/gal-sig.cpp:9-233: chip = 1 - 2*bit, sboc negates every even half-chip):
+ *   high bit = bneg          low bit = bneg XOR cneg
+ * XORing a word with the symbol pattern (D on the high bits, D^S on the low bits; D = nav symbol,
+ * S = secondary-code bit, src/galileo-sdr.cpp:517-518) turns the fields into (x, x^y) with
+ * x / y = 1 where B*d / C*s is -1, and `w & ((w << 1) | 0x55555555)` turns that into the 2-bit
+ * two's-complement value of  y - x = (B*d - C*s)/2  in {-1, 0, +1}  (:520-521).
+ * 512 data words plus zero padding (a window read touches word i and i+1).                       */
 #define E1C_CODE_WORDS_PER_PRN 516
-/* Carrier table: int32 [2][4][512], value for (regime r, field t, index i):
- *   t = 0,1 -> 0;  t = 2 -> -2*(cos + 65536*sin);  t = 3 -> +2*(cos + 65536*sin)
- *   of table index i (r = 0, phase >= 0) or (-i)&511 (r = 1, phase < 0), where
- *   t = code field XOR (D | (D^S)<<1), D = nav symbol bit, S = secondary-code bit.             */
-#define E1C_LUT_ENTRIES 4096
-#define E1C_RUN 4 /* consecutive samples per thread per group -> one 128-bit store */
+/* Carrier table: int32 [2][512][E1C_LUT_REP], value for (regime r, index i, copy l):
+ *   2*(cos + 65536*sin) of table index i (r = 0, phase >= 0) or (-i)&511 (r = 1, phase < 0)
+ * (include/constants.h:216-284, src/galileo-sdr.cpp:509-510).  Sixteen copies of every entry,
+ * one per (lane & 15), so a warp's 32 lookups fall into 16 distinct banks: at most a 2-way
+ * shared-memory conflict whatever the indices are.                                               */
+#define E1C_LUT_REP 16
+#define E1C_LUT_ENTRIES (2 * 512 * E1C_LUT_REP)
+#define E1C_LUT_REGIME_BYTES (512 * E1C_LUT_REP * 4)
+#define E1C_THREADS 512 /* synthesis CTA: thread t owns samples [t*R, (t+1)*R) of the tile */
+#define E1C_MAX_RUN 16
 /* GALILEO_E1_SECONDARY_CODE (include/constants.h:213), bit i = symbol i */
 #define E1C_SEC25_MASK 0x009B501Cu
 #define E1C_NO_WRAP 0x7fffffff
@@ -292,19 +302,26 @@ typedef struct e1_tile_ck { /* 32 bytes, one per (epoch, tile, channel) */
 #define E1_CK_ACTIVE 16u
 #define E1_CK_ERROR 32u
 
-typedef struct e1_chan_par { /* per active channel of the current tile (shared memory) */
-    uint64_t U0, dU;        /* |carrier phase| and its per-sample step, 2^-64 cycle           */
-    uint64_t HA, dH;        /* code phase at sample 0 and step, 2^-51 half-chip, + E1C_H_BIAS */
-    uint64_t HB;            /* code phase extrapolated back from j_w to sample 0, + bias      */
+typedef struct e1_chan_par { /* 96 bytes, one per active channel of a tile (HBM -> shared memory by bulk copy) */
+    uint64_t U0, dU;        /* |carrier phase| and its per-sample step, 2^-64 cycle                    */
+    uint64_t HA, HB;        /* code phase at sample 0 / extrapolated back from j_w to sample 0,
+                               2^-51 half-chip, plus the fast path's bias (e1_bias_h)                 */
+    uint64_t dH;            /* code phase step per sample, 2^-51 half-chip                            */
+    uint32_t dF;            /* dH >> 19: step of the fast path's 32-bit half-chip fraction            */
     int32_t j_w;
-    uint32_t misc;          /* bits 0-1 symbol field before the code wrap, bits 2-3 after it,
-                               bit 4 negative-phase regime, bit 5 force the exact path,
-                               bits 8-15 prn-1                                                */
-    double phi, sp, cp, sc; /* exact checkpoint for the exact fallback                        */
+    uint32_t pat_a, pat_b;  /* symbol XOR pattern for the code words before / after the code wrap     */
+    uint32_t code_off;      /* word offset of this PRN's code words                                   */
+    uint32_t misc;          /* bits 0-1 symbol field (D<<1 | D^S) before the wrap, bits 2-3 after it,
+                               bit 4 negative-phase regime, bit 5 force the generic path              */
+    double phi, sp, cp, sc; /* exact checkpoint for the exact fallback                                */
 } e1_chan_par;
-/* H carries one unit of its high word's 19-bit fraction as a bias so that "within 2^-19 of a
- * half-chip boundary" reads as "fraction bits 1..18 are zero" (the coarse test of the fast path) */
-#define E1C_H_BIAS (1ull << 32)
+#define E1_PAR_NEG 16u
+#define E1_PAR_FORCE 32u
+
+/* One tile's parameter block in HBM: header (16 bytes: n_active, 3 x pad) + max_chan e1_chan_par,
+ * active channels first. */
+#define E1C_BLK_HEADER 16
+E1_HD size_t e1_blk_bytes(int max_chan) { return E1C_BLK_HEADER + (size_t)max_chan * sizeof(e1_chan_par); }
 
 E1_HD uint32_t e1_umulhi(uint32_t a, uint32_t b)
 {
@@ -652,8 +669,8 @@ E1_HD double e1_v2_drift_unit(const e1_prep *p, double g, int n_samp)
 /* K1: refined start-phase estimates of one channel.  The drift pass walked epoch e exactly from
  * the ideal start g[e] to end[e]; the true start est[e] differs from g[e] by a tiny eta, and by
  * translation the true end is end[e] + eta (to within an ulp or two).                          */
-E1_HD void e1_v2_estimate_prefix(const e1_prep *pp, int n_epochs, double phi0, const double *g, const double *end,
-                                 double *est)
+E1_HD double e1_v2_estimate_prefix(const e1_prep *pp, int n_epochs, double phi0, const double *g, const double *end,
+                                   double *est)
 {
     double cur = phi0;
     for (int e = 0; e < n_epochs; e++) {
@@ -674,6 +691,7 @@ E1_HD void e1_v2_estimate_prefix(const e1_prep *pp, int n_epochs, double phi0, c
         else if (cur <= -1.0)
             cur += 1.0;
     }
+    return cur; /* estimate for the epoch after the last one: lets a caller continue chunk by chunk */
 }
 
 /* span pass for one (epoch, channel): p / p_prev are this channel's prep records of epoch e and
@@ -768,56 +786,94 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
 
 /* chain of one channel: validates HAT units, walks the others, writes the per-epoch translation
  * delta[e] (signed; the epoch's checkpoints are ck.phi + delta) and returns the final phase.
- * ck points at this channel's first checkpoint; consecutive tiles are `stride` apart, consecutive
- * epochs `ck_epoch_stride`.  stats[0] += epochs walked serially, stats[1] += HAT units accepted. */
+ * The state that runs along the chain is e1_chain_state; e1_v2_chain_step consumes one epoch, so
+ * the kernel can stage units / deltas through shared memory chunk by chunk.
+ * stats[0] += epochs walked serially, stats[1] += HAT units accepted. */
+typedef struct e1_chain_state {
+    double phi;    /* signed phase at the first sample of the next epoch                */
+    double prev_p; /* |phase| right after the last wrap of the previous epoch           */
+    int32_t prev_k;
+    int prev_ok, prev_neg;
+} e1_chain_state;
+
+E1_HD void e1_chain_init(e1_chain_state *s, double phi0)
+{
+    s->phi = phi0;
+    s->prev_p = 0.0;
+    s->prev_k = -1;
+    s->prev_ok = 0;
+    s->prev_neg = 0;
+}
+
+/* u: this epoch's unit; sp: its carrier step; ck_e: this channel's first checkpoint of this epoch
+ * (tiles `stride` apart), only touched when the epoch has to be walked serially. */
+E1_HD double e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, int n_samp, int tile, int tiles_per_epoch,
+                              e1_tile_ck *ck_e, int stride, unsigned long long *stats)
+{
+    const int type = u->type;
+    double delta = 0.0;
+    if (type == E1_UNIT_NONE) {
+        s->prev_ok = 0;
+        return delta;
+    }
+    int32_t last_k = u->last_k, neg = u->neg;
+    double last_p = u->last_p;
+    if (type == E1_UNIT_EXACT) {
+        s->phi = u->end_phi;
+    } else {
+        int ok = 0;
+        if (type == E1_UNIT_HAT && s->prev_ok && s->prev_neg == neg && s->prev_k == u->anchor_k) {
+            const double D = e1_add(s->prev_p, -u->anchor_p);
+            if (D >= u->lo && D < u->hi) {
+                ok = 1;
+                delta = neg ? -D : D;
+                s->phi = e1_add(u->end_phi, delta);
+                last_p = e1_add(last_p, D);
+                stats[1]++;
+            }
+        }
+        if (!ok) {
+            s->phi = e1_carr_epoch_exact(s->phi, sp, n_samp, tile, tiles_per_epoch, ck_e, stride, &last_k, &last_p, &neg);
+            stats[0]++;
+        }
+    }
+    s->prev_ok = last_k >= 1;
+    s->prev_neg = neg;
+    s->prev_k = last_k;
+    s->prev_p = last_p;
+    return delta;
+}
+
 E1_HD double e1_v2_chain(const e1_prep *pp, int n_epochs, double phi0, int n_samp, int tile, int tiles_per_epoch,
                          e1_unit *units, e1_tile_ck *ck, int stride, size_t ck_epoch_stride, double *delta,
                          unsigned long long *stats)
 {
-    double phi = phi0;
-    int prev_ok = 0, prev_neg = 0;
-    int32_t prev_k = -1;
-    double prev_p = 0.0;
-    for (int e = 0; e < n_epochs; e++) {
-        e1_unit *u = &units[e];
-        const int type = u->type;
-        delta[e] = 0.0;
-        if (type == E1_UNIT_NONE) {
-            prev_ok = 0;
-            continue;
-        }
-        int32_t last_k = u->last_k, neg = u->neg;
-        double last_p = u->last_p;
-        if (type == E1_UNIT_EXACT) {
-            phi = u->end_phi;
-        } else {
-            int ok = 0;
-            if (type == E1_UNIT_HAT && prev_ok && prev_neg == neg && prev_k == u->anchor_k) {
-                const double D = e1_add(prev_p, -u->anchor_p);
-                if (D >= u->lo && D < u->hi) {
-                    ok = 1;
-                    delta[e] = neg ? -D : D;
-                    phi = e1_add(u->end_phi, neg ? -D : D);
-                    last_p = e1_add(last_p, D);
-                    stats[1]++;
-                }
-            }
-            if (!ok) {
-                phi = e1_carr_epoch_exact(phi, pp[e].sp, n_samp, tile, tiles_per_epoch, ck + (size_t)e * ck_epoch_stride, stride,
-                                          &last_k, &last_p, &neg);
-                stats[0]++;
-            }
-        }
-        prev_ok = last_k >= 1;
-        prev_neg = neg;
-        prev_k = last_k;
-        prev_p = last_p;
-    }
-    return phi;
+    e1_chain_state s;
+    e1_chain_init(&s, phi0);
+    for (int e = 0; e < n_epochs; e++)
+        delta[e] = e1_v2_chain_step(&s, &units[e], pp[e].sp, n_samp, tile, tiles_per_epoch, ck + (size_t)e * ck_epoch_stride,
+                                    stride, stats);
+    return s.phi;
 }
 
+/* Ambiguity half-widths of the fast path for a run of R consecutive samples of a tile of T samples,
+ * in units of 2^-32 of the truncated quantity.  The fast path steps 32-bit truncations of the
+ * fixed-point phases, so sample i of the run is below the exact closed form by less than i+1 <= R
+ * units of 2^-32 cycle (carrier; times 511 in index units) / 2^-32 half-chip (code); the closed form
+ * itself is within e1_thr_carr / e1_thr_code of the serial value.  Adding the half-width as a bias
+ * makes "possibly on the other side of an integer" read as "fraction < 2*half-width + 1".        */
+E1_HD uint32_t e1_tc_carr(uint32_t thr_carr, int R) { return thr_carr + 511u * (uint32_t)R; }
+/* code: a run that contains the code wrap keeps stepping the pre-wrap closed form, which is within
+ * thr_code of the serial value at the wrap; the serial recurrence restarts there and drifts by at
+ * most thr_code more -> 2*thr_code on either side */
+E1_HD uint32_t e1_tc_code(uint32_t thr_code, int R) { return 2u * thr_code + (uint32_t)R + 1u; }
+E1_HD uint64_t e1_bias_h(uint32_t tc_code) { return (uint64_t)tc_code << 19; }
+E1_HD uint32_t e1_lim_carr(uint32_t tc_carr, uint32_t thr_carr) { return tc_carr + thr_carr + 1u; }
+E1_HD uint32_t e1_lim_code(uint32_t tc_code, uint32_t thr_code) { return tc_code + 2u * thr_code + 1u; }
+
 /* Tile checkpoint + epoch record -> the per-channel parameters the sample loop reads. */
-E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, int tile, double delta, e1_chan_par *p)
+E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, int tile, double delta, uint32_t tc_code,
+                       e1_chan_par *p)
 {
     p->phi = e1_add(c->phi, delta); /* planner translation of this epoch (exact, see e1_v2_chain) */
     p->cp = c->cp;
@@ -827,23 +883,31 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     const int aligned = (p->phi == 0.0) || (p->sp == 0.0) || (neg == (p->sp < 0.0));
     p->U0 = e1_to_fixed(p->phi, E1_CARR_FIX);
     uint64_t s = e1_to_fixed(p->sp, E1_CARR_FIX);
-    /* symbol fields: D | (D^S)<<1 from the planner's (D, S) pairs */
+    /* planner (D, S) pairs -> field order of the code words: D on the high bit, D^S on the low bit */
     const uint32_t sa = c->sym & 3u, sb = (c->sym >> 2) & 3u;
-    uint32_t misc = ((sa ^ (sa << 1)) & 3u) | (((sb ^ (sb << 1)) & 3u) << 2) | (neg ? 16u : 0u) | ((uint32_t)(r->prn - 1) << 8);
-    if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < 0.5) || !(p->sc < 2.0))
-        misc |= 32u; /* outside the closed form's domain: exact path */
+    const uint32_t da = ((sa & 1u) << 1) | ((sa ^ (sa >> 1)) & 1u), db = ((sb & 1u) << 1) | ((sb ^ (sb >> 1)) & 1u);
+    uint32_t misc = da | (db << 2) | (neg ? E1_PAR_NEG : 0u);
+    /* outside the fast path's domain (|phase| < 1, |step| < 1/2 cycle, at most one half-chip per
+       sample so the code window advances by carries): generic path */
+    if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < 0.5) || !(p->sc < 0.4999))
+        misc |= E1_PAR_FORCE;
     if (!aligned) {
         /* |phi| shrinks; if it can reach zero inside the tile the sign regime changes
            mid-tile: leave that (rare) tile to the exact path */
         if (e1_fabs(p->phi) <= e1_mul(e1_fabs(p->sp), (double)(tile + 2)))
-            misc |= 32u;
+            misc |= E1_PAR_FORCE;
         s = 0ull - s;
     }
     p->dU = s;
     p->dH = e1_to_fixed(p->sc, E1_CODE_FIX);
-    p->HA = e1_to_fixed(p->cp, E1_CODE_FIX) + E1C_H_BIAS;
+    p->dF = (uint32_t)(p->dH >> 19);
+    const uint64_t bias = e1_bias_h(tc_code);
+    p->HA = e1_to_fixed(p->cp, E1_CODE_FIX) + bias;
     p->j_w = c->j_w;
-    p->HB = (c->j_w == E1C_NO_WRAP) ? p->HA : e1_to_fixed(c->cp_w, E1_CODE_FIX) + E1C_H_BIAS - (uint64_t)(uint32_t)c->j_w * p->dH;
+    p->HB = (c->j_w == E1C_NO_WRAP) ? p->HA : e1_to_fixed(c->cp_w, E1_CODE_FIX) + bias - (uint64_t)(uint32_t)c->j_w * p->dH;
+    p->pat_a = ((da & 2u) ? 0xAAAAAAAAu : 0u) | ((da & 1u) ? 0x55555555u : 0u);
+    p->pat_b = ((db & 2u) ? 0xAAAAAAAAu : 0u) | ((db & 1u) ? 0x55555555u : 0u);
+    p->code_off = (uint32_t)(r->prn - 1) * E1C_CODE_WORDS_PER_PRN;
     p->misc = misc;
 }
 
@@ -871,30 +935,49 @@ static __device__ __noinline__ void e1_exact_indices(const e1_chan_par *p, int j
 #define e1_exact_indices e1_exact_indices_impl
 #endif
 
-/* Reference form of one channel's contribution to the E1C_RUN consecutive samples starting at
- * tile-relative j0 (src/galileo-sdr.cpp:509-525): full-precision closed form, full-precision
- * ambiguity test, any position of the code wrap.  acc[i] accumulates I + 65536*Q.  With
- * exact == 0 the return value is nonzero if any sample was ambiguous; with exact != 0 ambiguous
- * samples are resolved by e1_exact_indices and counted in *n_exact.  The kernel uses it for the
- * (rare) runs the fast form below hands back and for the exact re-evaluation. */
-E1_HD uint32_t e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const int32_t *lut4, int j0, int *acc,
-                              uint32_t thr_carr, uint32_t thr_code, const int exact, unsigned long long *n_exact)
+E1_HD uint32_t e1_funnel_l(uint32_t lo, uint32_t hi, uint32_t n) /* high word of (hi:lo) << (n & 31) */
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, n);
+#else
+    n &= 31u;
+    return n ? (hi << n) | (lo >> (32u - n)) : hi;
+#endif
+}
+
+/* a*b + c on 32 bits.  On the device this is spelled in PTX so the 64 * index + base address of the
+ * table lookup stays ONE multiply-add on the FMA pipe instead of being strength-reduced into a
+ * 64-bit shift, a mask and an add on the (busier) ALU pipe. */
+E1_HD uint32_t e1_mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return a * b + c;
+#endif
+}
+
+/* Generic form of one channel's contribution to the R consecutive samples starting at tile-relative
+ * j0 (src/galileo-sdr.cpp:509-525): full-precision closed form, full-precision ambiguity test, any
+ * position of the code wrap; ambiguous samples are resolved by e1_exact_indices and counted in
+ * *n_exact.  add[i] receives the term I + 65536*Q of sample j0+i.  lut_lane = carrier table + the
+ * caller's copy offset (4 * (lane & 15)).  Used for the rare runs the fast form hands back. */
+E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int R, int *add,
+                          uint32_t thr_carr, uint32_t thr_code, uint64_t bias_h, unsigned long long *n_exact)
 {
     const uint64_t U0 = p->U0, dU = p->dU, HA = p->HA, dH = p->dH, HB = p->HB;
     const int jw = p->j_w;
     const uint32_t misc = p->misc;
-    const uint32_t *code = codes + ((misc >> 8) & 0xffu) * E1C_CODE_WORDS_PER_PRN;
-    const int32_t *lut = lut4 + ((misc & 16u) ? 2048 : 0);
+    const uint32_t *code = codes + p->code_off;
+    const unsigned char *lut = lut_lane + ((misc & E1_PAR_NEG) ? E1C_LUT_REGIME_BYTES : 0);
     const uint32_t force = (misc >> 5) & 1u;
-    uint32_t amb = 0;
     uint64_t U = U0 + (uint64_t)(uint32_t)j0 * dU;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < E1C_RUN; i++) {
+    for (int i = 0; i < R; i++) {
         const int j = j0 + i;
         const int after = j >= jw;
-        const uint64_t H = (after ? HB : HA) + (uint64_t)(uint32_t)j * dH - E1C_H_BIAS;
+        const uint64_t H = (after ? HB : HA) + (uint64_t)(uint32_t)j * dH - bias_h;
         const uint32_t ds = after ? (misc >> 2) & 3u : misc & 3u;
         /* carrier: y = 511*|phi| in 9.32 fixed point */
         const uint32_t lo511 = e1_umulhi((uint32_t)U, 511u);
@@ -905,82 +988,80 @@ E1_HD uint32_t e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const
         uint32_t h = (uint32_t)(H >> 51);
         const uint32_t hf = (uint32_t)(H >> 19);
         const uint32_t a = (uint32_t)((yf + thr_carr) < 2u * thr_carr + 1u) | (uint32_t)((hf + thr_code) < 2u * thr_code + 1u) | force;
-        if (exact) {
-            if (a) {
-                uint32_t itx;
-                e1_exact_indices(p, j, &h, &itx);
-                it = (misc & 16u) ? ((0u - itx) & 511u) : itx; /* lut is already reflected */
-                (*n_exact)++;
-            }
-        } else {
-            amb |= a;
+        if (a) {
+            uint32_t itx;
+            e1_exact_indices(p, j, &h, &itx);
+            it = (misc & E1_PAR_NEG) ? ((0u - itx) & 511u) : itx; /* the table's regime half is already reflected */
+            (*n_exact)++;
         }
-        const uint32_t t = ((code[h >> 4] >> ((h & 15u) * 2u)) ^ ds) & 3u;
-        acc[i] += lut[t * 512u + it];
+        const uint32_t f = ((code[h >> 4] >> (30u - 2u * (h & 15u))) ^ ds) & 3u; /* (x, x^y) */
+        const int sgn = (f & 1u) ? ((f & 2u) ? -1 : 1) : 0;                      /* y - x */
+        add[i] = sgn * *(const int32_t *)(lut + it * (4u * E1C_LUT_REP));
         U += dU;
     }
-    return amb;
 }
 
-E1_HD uint32_t e1_funnel_r(uint32_t lo, uint32_t hi, uint32_t n) /* low word of (hi:lo) >> (n & 31) */
-{
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, n);
-#else
-    n &= 31u;
-    return n ? (lo >> n) | (hi << (32u - n)) : lo;
-#endif
-}
-
-/* Fast form of the same thing for the common run: the code wrap does not fall strictly inside
- * it.  Differences from the reference form, all conservative:
- *   - the carrier index comes from the high word of U only, stepped by the high word of dU: the
- *     9.32 product is off by < 2048 units, so the ambiguity band is thr_carr + 2048 units wide;
- *   - the code ambiguity test looks at the high word of H only (19 fraction bits, biased by one
- *     unit): "fraction bits 1..18 zero" is a superset of the exact band;
- *   - sign, zero and sub-carrier are folded into the table address: one LDS yields the term.
- * Returns nonzero if any sample needs the reference form (the caller then redoes the thread's
- * samples with exact != 0).  lutb is the carrier table as bytes (16 KiB, 8 KiB-aligned offset
- * arithmetic inside), thr2 = 2*(thr_carr + 2048) + 1.                                          */
-E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lutb, int j0, int *acc,
-                           uint32_t thr_carr, uint32_t thr_code)
+/* Fast form for the common run: the channel is inside the closed form's domain.  Per sample it costs one 32x32->64 multiply-add (carrier index and
+ * its fraction), one address multiply-add, one shared-memory load, one 32-bit add whose carry says
+ * "next half-chip" (the code window then moves up by one 2-bit field), one arithmetic shift (the
+ * signed chip value), one multiply-add into the accumulator, and half a 3-input minimum for each of
+ * the two ambiguity fractions.  Everything is conservative with respect to the generic form:
+ *   - carrier: only the high word of U is stepped, by the high word of dU; sample i is low by less
+ *     than i+1 units, the bias tc_carr = thr_carr + 511 R covers it;
+ *   - code: the fraction F (2^-32 half-chip) is stepped by dF = dH >> 19, same argument, bias in HA/HB;
+ *   - a run is ambiguous when the smallest biased fraction it saw is below lim = tc + thr + 1
+ *     (the serial value lies in [biased - tc - thr, biased)).
+ * A code wrap inside the run only changes how the 16-field window is assembled.
+ * Returns 0: terms added, final.  1: terms added but some sample is ambiguous (the caller takes them
+ * back out and uses the generic form).  2: nothing added, generic form needed.                      */
+template <int R>
+E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *acc,
+                           uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
 {
     const int jw = p->j_w;
     const uint32_t misc = p->misc;
-    if ((j0 < jw && jw < j0 + E1C_RUN) || (misc & 32u))
-        return e1_channel_run(p, codes, (const int32_t *)lutb, j0, acc, thr_carr, thr_code, 0, (unsigned long long *)0);
+    if (misc & E1_PAR_FORCE)
+        return 2u;
     const int after = j0 >= jw;
-    const uint64_t dH = p->dH;
-    uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * dH;
+    const uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * p->dH;
+    const uint32_t h0 = (uint32_t)(H >> 51);
+    uint32_t F = (uint32_t)(H >> 19);
+    const uint32_t dF = p->dF;
+    const uint32_t *code = codes + p->code_off;
+    uint32_t win = e1_funnel_l(code[(h0 >> 4) + 1], code[h0 >> 4], 2u * (h0 & 15u)); /* half-chips h0..h0+15, h0 on top */
+    win ^= after ? p->pat_b : p->pat_a;
+    if (j0 < jw && jw < j0 + R) {
+        /* the code wraps inside this run (:491-494): half-chip 8184 is half-chip 0 of the next code
+           period, under the next symbol.  The fraction keeps running from the pre-wrap checkpoint;
+           what that costs in accuracy is inside tc_code (see e1_tc_code). */
+        int k0 = 2 * E1C_CODE_LEN - (int)h0; /* window position of half-chip 0 */
+        k0 = k0 < 0 ? 0 : (k0 > 16 ? 16 : k0);
+        const uint32_t keep = k0 >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * k0));
+        const uint32_t wb = (k0 >= 16 ? 0u : (code[0] >> (2 * k0))) ^ p->pat_b;
+        win = (win & keep) | (wb & ~keep);
+    }
+    win &= (win << 1) | 0x55555555u; /* fields are now y - x in two's complement */
     const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
     uint32_t uh = (uint32_t)(U >> 32);
     const uint32_t duh = (uint32_t)(p->dU >> 32);
-    const uint32_t tc = thr_carr + 2048u;
-    const uint64_t ybias = (uint64_t)tc;
-    const uint32_t ds = after ? (misc >> 2) & 3u : misc & 3u;
-    /* byte offset of lut4[regime][ds][0]: the code field is XORed into bits 11-12 below */
-    const uint32_t kbase = ((misc & 16u) << 9) | (ds << 11);
-    const uint32_t *code = codes + ((misc >> 8) & 0xffu) * E1C_CODE_WORDS_PER_PRN;
-    const uint32_t h0 = (uint32_t)(H >> 51);
-    const uint32_t win = e1_funnel_r(code[h0 >> 4], code[(h0 >> 4) + 1], (h0 & 15u) * 2u); /* half-chips h0..h0+15 */
-    const uint32_t rot0 = 21u - 2u * h0; /* rotate so that the field of half-chip h lands on bits 11-12 */
-    uint32_t amb = 0;
+    const unsigned char *lut = lut_lane + ((misc & E1_PAR_NEG) ? E1C_LUT_REGIME_BYTES : 0);
+    uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < E1C_RUN; i++) {
-        const uint32_t hh = (uint32_t)(H >> 32);
-        amb |= (uint32_t)((hh & 0x7fffeu) == 0u);
-        const uint32_t h = hh >> 19;
-        const uint32_t vv = e1_funnel_r(win, win, 2u * h + rot0);
-        const uint64_t y = (uint64_t)uh * 511u + ybias;
-        amb |= (uint32_t)((uint32_t)y < 2u * tc + 1u);
-        const uint32_t off = (kbase + ((uint32_t)(y >> 32) << 2)) ^ (vv & 0x1800u);
-        acc[i] += *(const int32_t *)(lutb + off);
-        H += dH;
+    for (int i = 0; i < R; i++) {
+        const uint64_t y = (uint64_t)uh * 511u + tc_carr;
+        mY = (uint32_t)y < mY ? (uint32_t)y : mY;
+        mF = F < mF ? F : mF;
+        const int w = *(const int32_t *)(lut + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u));
+        acc[i] += w * ((int)win >> 30);
         uh += duh;
+        const uint32_t F2 = F + dF;
+        if (F2 < F)
+            win <<= 2;
+        F = F2;
     }
-    return amb;
+    return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
 }
 
 /* acc = I + 65536*Q  ->  the sink's little-endian (int16 I, int16 Q) pair (:536-537) */
@@ -993,16 +1074,14 @@ E1_HD uint32_t e1_pack_iq(int acc)
 /* Host-side table builders (the product's C-ABI calls them at create(); tests/hostsim too).
  * cos512/sin512: the reference's carrier tables (include/constants.h:216-284); b_words/c_words:
  * the E1-B / E1-C primary codes of one PRN, chip j = bit 31-(j%32) of word j/32.              */
-E1_HD void e1_build_lut4(const int *cos512, const int *sin512, int32_t *lut4)
+E1_HD void e1_build_lut(const int *cos512, const int *sin512, int32_t *lut)
 {
     for (int r = 0; r < 2; r++)
         for (int i = 0; i < 512; i++) {
             const int k = r ? ((-i) & 511) : i;
             const int32_t w2 = 2 * (cos512[k] + 65536 * sin512[k]);
-            lut4[(r * 4 + 0) * 512 + i] = 0;
-            lut4[(r * 4 + 1) * 512 + i] = 0;
-            lut4[(r * 4 + 2) * 512 + i] = -w2;
-            lut4[(r * 4 + 3) * 512 + i] = w2;
+            for (int l = 0; l < E1C_LUT_REP; l++)
+                lut[(r * 512 + i) * E1C_LUT_REP + l] = w2;
         }
 }
 E1_HD void e1_build_code_words(const uint32_t *b_words, const uint32_t *c_words, uint32_t *out)
@@ -1012,8 +1091,10 @@ E1_HD void e1_build_code_words(const uint32_t *b_words, const uint32_t *c_words,
     for (int hh = 0; hh < 2 * E1C_CODE_LEN; hh++) {
         const int c = hh >> 1;
         const uint32_t b = (b_words[c >> 5] >> (31 - (c & 31))) & 1u, q = (c_words[c >> 5] >> (31 - (c & 31))) & 1u;
-        const uint32_t f = (b ^ (uint32_t)(hh & 1)) | ((b ^ q) << 1);
-        out[hh >> 4] |= f << ((hh & 15) * 2);
+        /* value = -chip on even half-chips, +chip on odd ones; chip = -1 where the bit is 1 */
+        const uint32_t flip = (uint32_t)(hh & 1) ^ 1u, bneg = b ^ flip, cneg = q ^ flip;
+        const uint32_t f = (bneg << 1) | (bneg ^ cneg);
+        out[hh >> 4] |= f << (30 - (hh & 15) * 2);
     }
 }
 

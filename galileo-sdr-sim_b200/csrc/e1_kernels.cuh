@@ -28,24 +28,31 @@
 #define E1_CODES_BYTES (E1C_N_PRN * E1_CODE_WORDS_PER_PRN * 4)
 #define E1_LUT_ENTRIES E1C_LUT_ENTRIES
 #define E1_LUT_BYTES (E1_LUT_ENTRIES * 4)
-#define E1_SYNTH_THREADS 512
-#define E1_RUN E1C_RUN
-#define E1_GROUP (E1_SYNTH_THREADS * E1_RUN)
+#define E1_SYNTH_THREADS E1C_THREADS
 
 struct e1_synth_args {
-    const e1_epoch_rec *recs;
-    const e1_tile_ck *ck;
-    const double *delta; /* planner translation of each epoch's carrier checkpoints, channel-major:
-                            delta[ch * delta_stride + delta_off + e] for epoch e of this launch          */
-    int delta_stride, delta_off;
+    const unsigned char *blk; /* parameter blocks of this launch's tiles, e1_blk_bytes(max_chan) apart */
     const uint32_t *codes;
     const int32_t *lut;
     int16_t *out;
-    unsigned long long *counters; /* [0] ambiguous samples resolved exactly, [1] planner errors */
-    double delt;
+    unsigned long long *counters; /* [0] ambiguous samples resolved exactly */
     int n_epochs, n_samp, max_chan, tile, tiles_per_epoch;
-    uint32_t thr_carr, thr_code;
+    uint32_t thr_carr, thr_code; /* closed form vs serial recurrence (e1_thr_carr / e1_thr_code)  */
+    uint32_t tc_carr, tc_code;   /* + the fast path's truncation slack (e1_tc_carr / e1_tc_code) */
     int vec_ok, use_bulk;
+};
+
+struct e1_finalize_args {
+    const e1_epoch_rec *recs;
+    const e1_tile_ck *ck;
+    const double *delta; /* planner translation of each epoch's carrier checkpoints, channel-major:
+                            delta[ch * delta_stride + e]                                          */
+    int delta_stride;
+    unsigned char *blk;
+    unsigned long long *counters; /* [1] planner errors */
+    double delt;
+    int n_epochs, max_chan, tile, tiles_per_epoch;
+    uint32_t tc_code;
 };
 
 /* ------------------------------------------------------------------ restate (a8) */
@@ -133,13 +140,41 @@ __global__ void e1_v2_prep_kernel(const e1_plan_args P)
     e1_v2_prep(&P.recs[i], P.delt, &P.prep[(size_t)ch * P.n_epochs + e]);
 }
 
-__global__ void e1_v2_ideal_kernel(const e1_plan_args P)
+/* The three serial per-channel passes (ideal prefix, estimate prefix, chain) run one channel per
+ * block: the block stages a chunk of that channel's (channel-major, contiguous) records through
+ * shared memory with coalesced loads, thread 0 walks the chunk out of shared memory, the block
+ * writes the results back coalesced.  Walking straight out of global memory costs one DRAM round
+ * trip per epoch (measured: 7.9 us per epoch in the chain). */
+#define E1_SERIAL_THREADS 128
+#define E1_SERIAL_CHUNK 256
+
+__global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_ideal_kernel(const e1_plan_args P)
 {
-    int ch = blockIdx.x; /* one channel per block: serial walks of different channels must not share a warp */
-    if (threadIdx.x != 0)
+    __shared__ e1_prep s_prep[E1_SERIAL_CHUNK];
+    __shared__ double s_g[E1_SERIAL_CHUNK];
+    const int ch = blockIdx.x, tid = threadIdx.x;
+    if (ch >= P.max_chan)
         return;
-    if (ch < P.max_chan)
-        e1_v2_ideal_prefix(P.prep + (size_t)ch * P.n_epochs, P.n_epochs, P.phase[ch], P.n_samp, P.g + (size_t)ch * P.n_epochs);
+    const size_t o = (size_t)ch * P.n_epochs;
+    double g = P.phase[ch];
+    for (int e0 = 0; e0 < P.n_epochs; e0 += E1_SERIAL_CHUNK) {
+        const int n = min(E1_SERIAL_CHUNK, P.n_epochs - e0);
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
+            s_prep[i] = P.prep[o + e0 + i];
+        __syncthreads();
+        if (tid == 0)
+            for (int i = 0; i < n; i++) { /* e1_v2_ideal_prefix, one chunk */
+                const uint32_t f = s_prep[i].flags;
+                if (f & E1_PREP_SET_PHASE)
+                    g = s_prep[i].init;
+                s_g[i] = g;
+                if (f & E1_PREP_ACTIVE)
+                    g = e1_ideal_next(g, s_prep[i].sp, P.n_samp);
+            }
+        __syncthreads();
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
+            P.g[o + e0 + i] = s_g[i];
+    }
 }
 
 __global__ void e1_v2_drift_kernel(const e1_plan_args P)
@@ -150,15 +185,29 @@ __global__ void e1_v2_drift_kernel(const e1_plan_args P)
     P.dend[i] = e1_v2_drift_unit(&P.prep[i], P.g[i], P.n_samp);
 }
 
-__global__ void e1_v2_estimate_kernel(const e1_plan_args P)
+__global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_estimate_kernel(const e1_plan_args P)
 {
-    int ch = blockIdx.x; /* one channel per block: serial walks of different channels must not share a warp */
-    if (threadIdx.x != 0)
-        return;
+    __shared__ e1_prep s_prep[E1_SERIAL_CHUNK];
+    __shared__ double s_g[E1_SERIAL_CHUNK], s_end[E1_SERIAL_CHUNK], s_est[E1_SERIAL_CHUNK];
+    const int ch = blockIdx.x, tid = threadIdx.x;
     if (ch >= P.max_chan)
         return;
-    size_t o = (size_t)ch * P.n_epochs;
-    e1_v2_estimate_prefix(P.prep + o, P.n_epochs, P.phase[ch], P.g + o, P.dend + o, P.est + o);
+    const size_t o = (size_t)ch * P.n_epochs;
+    double cur = P.phase[ch];
+    for (int e0 = 0; e0 < P.n_epochs; e0 += E1_SERIAL_CHUNK) {
+        const int n = min(E1_SERIAL_CHUNK, P.n_epochs - e0);
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS) {
+            s_prep[i] = P.prep[o + e0 + i];
+            s_g[i] = P.g[o + e0 + i];
+            s_end[i] = P.dend[o + e0 + i];
+        }
+        __syncthreads();
+        if (tid == 0) /* e1_v2_estimate_prefix continues from `cur` */
+            cur = e1_v2_estimate_prefix(s_prep, n, cur, s_g, s_end, s_est);
+        __syncthreads();
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
+            P.est[o + e0 + i] = s_est[i];
+    }
 }
 
 __global__ void e1_v2_span_kernel(const e1_plan_args P)
@@ -171,21 +220,80 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
                     P.tiles_per_epoch, P.ck + (size_t)e * P.tiles_per_epoch * P.max_chan + ch, P.max_chan, &P.units[i]);
 }
 
-__global__ void e1_v2_chain_kernel(const e1_plan_args P)
+__global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1_plan_args P)
 {
-    int ch = blockIdx.x; /* one channel per block: serial walks of different channels must not share a warp */
-    if (threadIdx.x != 0)
-        return;
+    __shared__ __align__(16) e1_unit s_units[E1_SERIAL_CHUNK];
+    __shared__ double s_sp[E1_SERIAL_CHUNK], s_delta[E1_SERIAL_CHUNK];
+    const int ch = blockIdx.x, tid = threadIdx.x;
     if (ch >= P.max_chan)
         return;
+    const size_t o = (size_t)ch * P.n_epochs;
+    const size_t ck_epoch_stride = (size_t)P.tiles_per_epoch * P.max_chan;
     unsigned long long st[2] = {0, 0};
-    size_t o = (size_t)ch * P.n_epochs;
-    P.phase[ch] = e1_v2_chain(P.prep + o, P.n_epochs, P.phase[ch], P.n_samp, P.tile, P.tiles_per_epoch, P.units + o, P.ck + ch,
-                              P.max_chan, (size_t)P.tiles_per_epoch * P.max_chan, P.delta + o, st);
-    if (st[0])
-        atomicAdd(&P.counters[2], st[0]);
-    if (st[1])
-        atomicAdd(&P.counters[3], st[1]);
+    e1_chain_state cs;
+    e1_chain_init(&cs, P.phase[ch]);
+    for (int e0 = 0; e0 < P.n_epochs; e0 += E1_SERIAL_CHUNK) {
+        const int n = min(E1_SERIAL_CHUNK, P.n_epochs - e0);
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.units + o + e0);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_units);
+        for (int i = tid; i < n * (int)(sizeof(e1_unit) / 16); i += E1_SERIAL_THREADS)
+            dst[i] = src[i];
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
+            s_sp[i] = P.prep[o + e0 + i].sp;
+        __syncthreads();
+        if (tid == 0)
+            for (int i = 0; i < n; i++)
+                s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], s_sp[i], P.n_samp, P.tile, P.tiles_per_epoch,
+                                              P.ck + (size_t)(e0 + i) * ck_epoch_stride + ch, P.max_chan, st);
+        __syncthreads();
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
+            P.delta[o + e0 + i] = s_delta[i];
+    }
+    if (tid == 0) {
+        P.phase[ch] = cs.phi;
+        if (st[0])
+            atomicAdd(&P.counters[2], st[0]);
+        if (st[1])
+            atomicAdd(&P.counters[3], st[1]);
+    }
+}
+
+/* ------------------------------------------------------------------ finalize
+ * One warp per tile: tile checkpoints (+ the chain's translation) -> the tile's parameter block,
+ * active channels compacted to the front, so the synthesis CTAs only have to bulk-copy it. */
+__global__ void __launch_bounds__(128) e1_finalize_kernel(const e1_finalize_args A)
+{
+    const int lane = threadIdx.x & 31;
+    const long tile_id = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile_id >= (long)A.n_epochs * A.tiles_per_epoch)
+        return;
+    const int e = (int)(tile_id / A.tiles_per_epoch);
+    unsigned char *blk = A.blk + (size_t)tile_id * e1_blk_bytes(A.max_chan);
+    e1_chan_par *par = reinterpret_cast<e1_chan_par *>(blk + E1C_BLK_HEADER);
+    int base = 0;
+    unsigned long long errs = 0;
+    for (int c0 = 0; c0 < A.max_chan; c0 += 32) {
+        const int ch = c0 + lane;
+        e1_tile_ck c;
+        c.sym = 0;
+        if (ch < A.max_chan)
+            c = A.ck[(size_t)tile_id * A.max_chan + ch];
+        const bool active = (c.sym & E1_CK_ACTIVE) != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            e1_chan_par p;
+            e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + ch], A.delt, A.tile, A.delta[(size_t)ch * A.delta_stride + e],
+                        A.tc_code, &p);
+            if (c.sym & E1_CK_ERROR)
+                errs++;
+            par[base + __popc(m & ((1u << lane) - 1u))] = p;
+        }
+        base += __popc(m);
+    }
+    if (lane == 0)
+        *reinterpret_cast<uint4 *>(blk) = make_uint4((unsigned)base, 0u, 0u, 0u);
+    if (errs)
+        atomicAdd(&A.counters[1], errs);
 }
 
 /* ------------------------------------------------------------------ synthesis */
@@ -202,6 +310,9 @@ __device__ __forceinline__ void e1_bulk_g2s(void *dst, const void *src, uint32_t
 __device__ __forceinline__ void e1_mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" : : "r"(e1_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void e1_mbar_init_fence()
+{
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -219,121 +330,127 @@ __device__ __forceinline__ void e1_mbar_wait(uint64_t *bar, uint32_t parity)
                  : "memory");
 }
 
-template <int G>
+/* The rare path of one (thread, channel): the fast form flagged the run (rc 1: its terms are in the
+ * accumulators and come back out) or did not handle it (rc 2).  d[i] receives the correction. */
+template <int R>
+__device__ __noinline__ void e1_fix_run(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0,
+                                        int *d, uint32_t thr_carr, uint32_t thr_code, uint32_t tc_carr, uint32_t tc_code,
+                                        unsigned long long *n_exact)
+{
+    int t[R], g[R];
+#pragma unroll
+    for (int i = 0; i < R; i++)
+        t[i] = 0;
+    e1_run_fast<R>(p, codes, lut_lane, j0, t, tc_carr, e1_lim_carr(tc_carr, thr_carr), e1_lim_code(tc_code, thr_code));
+    e1_channel_run(p, codes, lut_lane, j0, R, g, thr_carr, thr_code, e1_bias_h(tc_code), n_exact);
+#pragma unroll
+    for (int i = 0; i < R; i++)
+        d[i] = g[i] - t[i];
+}
+
+/* Persistent CTA, one per SM.  Shared memory: code words of all PRNs (103 200 B) and the replicated
+ * carrier table (65 536 B), both loaded once by bulk copy; two parameter-block buffers, tile i+1's
+ * block in flight (bulk copy + mbarrier) while tile i is computed.  Thread t owns the R consecutive
+ * samples [t*R, (t+1)*R) of the tile and walks the active channels with the I/Q sums in registers. */
+template <int R>
 __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_synth_args A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
-    int32_t *s_lut = reinterpret_cast<int32_t *>(smem_raw + E1_CODES_BYTES);
-    e1_chan_par *s_par = reinterpret_cast<e1_chan_par *>(smem_raw + E1_CODES_BYTES + E1_LUT_BYTES);
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_nact;
-    __shared__ unsigned long long s_cnt[2];
+    unsigned char *s_lut = smem_raw + E1_CODES_BYTES;
+    const uint32_t blk_bytes = (uint32_t)e1_blk_bytes(A.max_chan);
+    unsigned char *s_blk0 = smem_raw + E1_CODES_BYTES + E1_LUT_BYTES;
+    __shared__ __align__(8) uint64_t s_bar[3]; /* [0] tables, [1],[2] parameter buffers */
+    __shared__ unsigned long long s_cnt;
 
     const int tid = threadIdx.x;
+    const long total_tiles = (long)A.n_epochs * A.tiles_per_epoch;
     if (tid == 0) {
-        s_cnt[0] = 0;
-        s_cnt[1] = 0;
-    }
-    /* tables: one bulk copy each through the TMA unit, once per (persistent) CTA */
-    if (A.use_bulk) {
-        if (tid == 0) {
-            e1_mbar_init(&s_bar, 1);
-            e1_mbar_expect(&s_bar, E1_CODES_BYTES + E1_LUT_BYTES);
-            e1_bulk_g2s(s_codes, A.codes, E1_CODES_BYTES, &s_bar);
-            e1_bulk_g2s(s_lut, A.lut, E1_LUT_BYTES, &s_bar);
+        s_cnt = 0;
+        e1_mbar_init(&s_bar[0], 1);
+        e1_mbar_init(&s_bar[1], 1);
+        e1_mbar_init(&s_bar[2], 1);
+        e1_mbar_init_fence();
+        if (A.use_bulk) {
+            e1_mbar_expect(&s_bar[0], E1_CODES_BYTES + E1_LUT_BYTES);
+            e1_bulk_g2s(s_codes, A.codes, E1_CODES_BYTES, &s_bar[0]);
+            e1_bulk_g2s(s_lut, A.lut, E1_LUT_BYTES, &s_bar[0]);
         }
-        __syncthreads();
-        e1_mbar_wait(&s_bar, 0);
+        if ((long)blockIdx.x < total_tiles) {
+            e1_mbar_expect(&s_bar[1], blk_bytes);
+            e1_bulk_g2s(s_blk0, A.blk + (size_t)blockIdx.x * blk_bytes, blk_bytes, &s_bar[1]);
+        }
+    }
+    __syncthreads();
+    if (A.use_bulk) {
+        e1_mbar_wait(&s_bar[0], 0);
     } else {
         for (int i = tid; i < E1_CODES_BYTES / 4; i += E1_SYNTH_THREADS)
             s_codes[i] = A.codes[i];
         for (int i = tid; i < E1_LUT_ENTRIES; i += E1_SYNTH_THREADS)
-            s_lut[i] = A.lut[i];
+            reinterpret_cast<int32_t *>(s_lut)[i] = A.lut[i];
+        __syncthreads();
     }
 
-    const int total_tiles = A.n_epochs * A.tiles_per_epoch;
-    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
-        const int e = tile_id / A.tiles_per_epoch, t = tile_id - e * A.tiles_per_epoch;
-        __syncthreads(); /* previous tile done with s_par */
-        if (tid == 0)
-            s_nact = 0;
-        __syncthreads();
-        if (tid < A.max_chan) {
-            const e1_tile_ck c = A.ck[(size_t)tile_id * A.max_chan + tid];
-            if (c.sym & E1_CK_ACTIVE) {
-                e1_chan_par p;
-                e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + tid], A.delt, A.tile, A.delta[(size_t)tid * A.delta_stride + A.delta_off + e], &p);
-                if (c.sym & E1_CK_ERROR)
-                    atomicAdd(&s_cnt[1], 1ull);
-                s_par[atomicAdd(&s_nact, 1)] = p;
-            }
+    const unsigned char *lut_lane = s_lut + 4 * (tid & (E1C_LUT_REP - 1));
+    const uint32_t lim_carr = e1_lim_carr(A.tc_carr, A.thr_carr), lim_code = e1_lim_code(A.tc_code, A.thr_code);
+    const int j0 = tid * R;
+    unsigned long long n_exact = 0;
+    int it = 0;
+    for (long tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, it++) {
+        const int b = it & 1;
+        /* every thread is past the previous tile (barrier at the end of the loop body), so the other
+           buffer is free: start the next tile's block now */
+        if (tid == 0 && tile_id + gridDim.x < total_tiles) {
+            e1_mbar_expect(&s_bar[2 - b], blk_bytes);
+            e1_bulk_g2s(s_blk0 + (size_t)(1 - b) * blk_bytes, A.blk + (size_t)(tile_id + gridDim.x) * blk_bytes, blk_bytes, &s_bar[2 - b]);
         }
-        __syncthreads();
-        const int nact = s_nact;
+        e1_mbar_wait(&s_bar[1 + b], (uint32_t)(it >> 1) & 1u);
+        const unsigned char *blk = s_blk0 + (size_t)b * blk_bytes;
+        const int nact = *reinterpret_cast<const int *>(blk);
+        const e1_chan_par *par = reinterpret_cast<const e1_chan_par *>(blk + E1C_BLK_HEADER);
+        const int e = (int)(tile_id / A.tiles_per_epoch), t = (int)(tile_id - (long)e * A.tiles_per_epoch);
         const int n_valid = min(A.tile, A.n_samp - t * A.tile);
 
-        int acc[G][E1_RUN];
+        if (j0 < n_valid) {
+            int acc[R];
 #pragma unroll
-        for (int g = 0; g < G; g++)
+            for (int i = 0; i < R; i++)
+                acc[i] = 0;
+            unsigned long long redo = 0;
+            for (int a = 0; a < nact; a++)
+                if (e1_run_fast<R>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code))
+                    redo |= 1ull << a;
+            while (redo) { /* rare: one (thread, channel) at a time through the generic form */
+                const int a = __ffsll((long long)redo) - 1;
+                redo &= redo - 1;
+                int d[R];
+                e1_fix_run<R>(&par[a], s_codes, lut_lane, j0, d, A.thr_carr, A.thr_code, A.tc_carr, A.tc_code, &n_exact);
 #pragma unroll
-            for (int i = 0; i < E1_RUN; i++)
-                acc[g][i] = 0;
-        uint32_t amb[G];
-#pragma unroll
-        for (int g = 0; g < G; g++)
-            amb[g] = 0;
-        const unsigned char *lutb = reinterpret_cast<const unsigned char *>(s_lut);
-        for (int a = 0; a < nact; a++) {
-#pragma unroll
-            for (int g = 0; g < G; g++)
-                amb[g] |= e1_run_fast(&s_par[a], s_codes, lutb, g * E1_GROUP + tid * E1_RUN, acc[g], A.thr_carr, A.thr_code);
-        }
-        /* rare: some channel flagged a sample of run g.  Find the channel(s) by re-running the fast
-           form into a scratch accumulator, take their fast terms back out and add the exact ones. */
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            if (amb[g]) {
-                unsigned long long n_exact = 0;
-                const int j0 = g * E1_GROUP + tid * E1_RUN;
-                for (int a = 0; a < nact; a++) {
-                    int t4[E1_RUN] = {0, 0, 0, 0};
-                    if (e1_run_fast(&s_par[a], s_codes, lutb, j0, t4, A.thr_carr, A.thr_code)) {
-#pragma unroll
-                        for (int i = 0; i < E1_RUN; i++)
-                            acc[g][i] -= t4[i];
-                        e1_channel_run(&s_par[a], s_codes, s_lut, j0, acc[g], A.thr_carr, A.thr_code, 1, &n_exact);
-                    }
-                }
-                atomicAdd(&s_cnt[0], n_exact);
+                for (int i = 0; i < R; i++)
+                    acc[i] += d[i];
             }
-        }
-        /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
-        int16_t *out_tile = A.out + ((size_t)e * A.n_samp + (size_t)t * A.tile) * 2;
+            /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
+            int16_t *dst = A.out + ((size_t)e * A.n_samp + (size_t)t * A.tile + j0) * 2;
+            if (A.vec_ok && j0 + R <= n_valid) {
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int j0 = g * E1_GROUP + tid * E1_RUN;
-            uint32_t w[E1_RUN];
-#pragma unroll
-            for (int i = 0; i < E1_RUN; i++)
-                w[i] = e1_pack_iq(acc[g][i]);
-            if (A.vec_ok && j0 + E1_RUN <= n_valid) {
-                *reinterpret_cast<uint4 *>(out_tile + (size_t)j0 * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int i = 0; i < R; i += 4)
+                    *reinterpret_cast<uint4 *>(dst + 2 * i) =
+                        make_uint4(e1_pack_iq(acc[i]), e1_pack_iq(acc[i + 1]), e1_pack_iq(acc[i + 2]), e1_pack_iq(acc[i + 3]));
             } else {
 #pragma unroll
-                for (int i = 0; i < E1_RUN; i++)
+                for (int i = 0; i < R; i++)
                     if (j0 + i < n_valid)
-                        *reinterpret_cast<uint32_t *>(out_tile + (size_t)(j0 + i) * 2) = w[i];
+                        *reinterpret_cast<uint32_t *>(dst + 2 * i) = e1_pack_iq(acc[i]);
             }
         }
+        __syncthreads(); /* all reads of this tile's block are done */
     }
+    if (n_exact)
+        atomicAdd(&s_cnt, n_exact);
     __syncthreads();
-    if (tid == 0 && A.counters) {
-        if (s_cnt[0])
-            atomicAdd(&A.counters[0], s_cnt[0]);
-        if (s_cnt[1])
-            atomicAdd(&A.counters[1], s_cnt[1]);
-    }
+    if (tid == 0 && A.counters && s_cnt)
+        atomicAdd(&A.counters[0], s_cnt);
 }
 
 #endif /* E1_KERNELS_CUH */

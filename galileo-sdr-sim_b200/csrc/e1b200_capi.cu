@@ -23,7 +23,7 @@ struct e1b200_ctx {
     e1b200_config cfg;
     double delt;        /* 1/fs, as the reference computes it (src/galileo-sdr.cpp:162) */
     int tile;           /* samples per planner checkpoint / synthesis tile              */
-    int groups;         /* tile / 1024                                                  */
+    int run;            /* consecutive samples per thread: tile = 512 * run             */
     int tiles_per_epoch;
     int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
     int plan_epochs;    /* epochs per planner pass (bounds scratch)                     */
@@ -38,6 +38,7 @@ struct e1b200_ctx {
     double *d_phase;
     unsigned long long *d_counters; /* [0] exact-fallback samples [1] planner errors [2] serial epochs [3] HAT epochs */
     e1_tile_ck *d_ck;
+    unsigned char *d_blk;     /* per-tile parameter blocks of the current plan */
     double *d_g, *d_dend, *d_est, *d_delta;
     e1_prep *d_prep;
     int plan_n;               /* epochs in the current plan (stride of the channel-major arrays) */
@@ -69,7 +70,7 @@ static int fail(e1b200_ctx *c, int code, const char *what, cudaError_t ce)
 
 /* include/constants.h:216-284: round(250*cos(2*pi*(i+1/2)/512)), except the four entries per
  * table whose exact value is +-105.5, which the reference stores as +-105 */
-static void build_lut(int32_t *lut4)
+static void build_lut(int32_t *lut)
 {
     static const int cos_fix[4] = {92, 163, 348, 419}, sin_fix[4] = {35, 220, 291, 476};
     int c[512], s[512];
@@ -82,7 +83,7 @@ static void build_lut(int32_t *lut4)
         c[cos_fix[k]] = c[cos_fix[k]] > 0 ? 105 : -105;
         s[sin_fix[k]] = s[sin_fix[k]] > 0 ? 105 : -105;
     }
-    e1_build_lut4(c, s, lut4);
+    e1_build_lut(c, s, lut);
 }
 
 /* src/gal-sig.cpp:9-233 (hex -> chips -> BOC(1,1) half-chips) in the packed layout of e1_core.h */
@@ -99,12 +100,12 @@ static int env_int(const char *name, int dflt)
 }
 
 typedef void (*synth_fn)(const e1_synth_args);
-static synth_fn synth_for(int groups)
+static synth_fn synth_for(int run)
 {
-    switch (groups) {
-    case 1: return e1_synth_kernel<1>;
-    case 2: return e1_synth_kernel<2>;
+    switch (run) {
     case 4: return e1_synth_kernel<4>;
+    case 8: return e1_synth_kernel<8>;
+    case 16: return e1_synth_kernel<16>;
     default: return nullptr;
     }
 }
@@ -122,14 +123,16 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     *out = nullptr;
     if (!(cfg->fs_hz > 0.0) || cfg->samples_per_epoch < 1 || cfg->max_chan < 1 || cfg->max_chan > E1B200_MAX_CHAN)
         return E1B200_EINVAL;
-    /* one code period must not fit twice in a tile: tile * (1.023e6+margin)/fs < 4092 */
-    int groups = 4; /* tile = groups * 2048 samples */
-    while (groups > 1 && (double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
-        groups >>= 1;
-    if ((double)(groups * E1_GROUP) * 1.03e6 / cfg->fs_hz >= 4000.0)
+    /* one code period must not fit twice in a tile: tile * (1.023e6+margin)/fs < 4092.  Below
+       ~2.1 MS/s a sample can span more than one half-chip and every channel takes the generic
+       (slow, still exact) form; the reference's only rate is 2.6 MS/s. */
+    int run = E1C_MAX_RUN; /* tile = 512 * run samples */
+    while (run > 4 && (double)(run * E1_SYNTH_THREADS) * 1.03e6 / cfg->fs_hz >= 4000.0)
+        run >>= 1;
+    if ((double)(run * E1_SYNTH_THREADS) * 1.03e6 / cfg->fs_hz >= 4000.0)
         return E1B200_EINVAL; /* fs below ~0.53 MS/s */
-    groups = env_int("E1B200_GROUPS", groups);
-    if (!synth_for(groups))
+    run = env_int("E1B200_RUN", run);
+    if (!synth_for(run))
         return E1B200_EINVAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device || cfg->device < 0)
@@ -144,8 +147,8 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     if (ctx->cfg.dt_epoch == 0.0)
         ctx->cfg.dt_epoch = 0.10000002314200000; /* src/galileo-sdr.cpp:347 */
     ctx->delt = 1.0 / cfg->fs_hz;
-    ctx->groups = groups;
-    ctx->tile = groups * E1_GROUP;
+    ctx->run = run;
+    ctx->tile = run * E1_SYNTH_THREADS;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
     ctx->use_bulk = env_int("E1B200_NO_TMA", 0) ? 0 : 1;
     ctx->amb_scale = env_int("E1B200_AMB_SCALE", 1);
@@ -155,11 +158,11 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     const size_t epoch_bytes = (size_t)cfg->samples_per_epoch * 4;
     long be = (long)(((size_t)env_int("E1B200_BATCH_MB", 128) << 20) / epoch_bytes);
     ctx->batch_epochs = be < 1 ? 1 : (be > 512 ? 512 : (int)be);
-    const size_t ck_epoch_bytes = sizeof(e1_tile_ck) * (size_t)ctx->tiles_per_epoch * cfg->max_chan;
+    const size_t ck_epoch_bytes = (sizeof(e1_tile_ck) * (size_t)cfg->max_chan + e1_blk_bytes(cfg->max_chan)) * (size_t)ctx->tiles_per_epoch;
     long pe = (long)(((size_t)env_int("E1B200_PLAN_MB", 2048) << 20) / ck_epoch_bytes);
     ctx->plan_epochs = pe < 1 ? 1 : (pe > 4096 ? 4096 : (int)pe);
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + cfg->max_chan * (int)sizeof(e1_chan_par);
+    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + 2 * (int)e1_blk_bytes(cfg->max_chan);
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -167,7 +170,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
         CK(cudaEventCreateWithFlags(&ctx->ev_buf[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
     }
-    synth_fn fn = synth_for(groups);
+    synth_fn fn = synth_for(run);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, E1_SYNTH_THREADS, ctx->smem_bytes));
@@ -176,8 +179,8 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->ctas_per_sm = env_int("E1B200_CTAS_PER_SM", occ);
 
     uint32_t *h_codes = (uint32_t *)malloc(E1_CODES_BYTES);
-    int32_t h_lut[E1_LUT_ENTRIES];
-    if (!h_codes)
+    int32_t *h_lut = (int32_t *)malloc(E1_LUT_BYTES);
+    if (!h_codes || !h_lut)
         return fail(ctx, E1B200_ENOMEM, "host alloc", cudaSuccess);
     build_codes(h_codes);
     build_lut(h_lut);
@@ -188,6 +191,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     CK(cudaMemcpy(ctx->d_codes, h_codes, E1_CODES_BYTES, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_lut, h_lut, E1_LUT_BYTES, cudaMemcpyHostToDevice));
     free(h_codes);
+    free(h_lut);
     CK(cudaMemset(ctx->d_phase, 0, sizeof(double) * E1B200_MAX_CHAN));
     CK(cudaMemset(ctx->d_counters, 0, sizeof ctx->counters));
     return E1B200_OK;
@@ -207,6 +211,7 @@ int e1b200_destroy(e1b200_ctx *ctx)
     cudaFree(ctx->d_phase);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_ck);
+    cudaFree(ctx->d_blk);
     cudaFree(ctx->d_g);
     cudaFree(ctx->d_dend);
     cudaFree(ctx->d_est);
@@ -272,6 +277,7 @@ static int ensure_plan_scratch(e1b200_ctx *ctx)
         return E1B200_OK;
     const size_t ne = (size_t)ctx->plan_epochs * ctx->cfg.max_chan;
     CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * ne * ctx->tiles_per_epoch));
+    CK(cudaMalloc(&ctx->d_blk, e1_blk_bytes(ctx->cfg.max_chan) * (size_t)ctx->plan_epochs * ctx->tiles_per_epoch));
     CK(cudaMalloc(&ctx->d_delta, sizeof(double) * ne));
     CK(cudaMemset(ctx->d_delta, 0, sizeof(double) * ne));
     if (!ctx->serial_planner) {
@@ -342,12 +348,30 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
         P.tiles_per_epoch = ctx->tiles_per_epoch;
         const int cb = cfg->max_chan; /* one channel per block */
         e1_v2_prep_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(P);
-        e1_v2_ideal_kernel<<<cb, 32, 0, ctx->stream>>>(P);
+        e1_v2_ideal_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         e1_v2_drift_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
-        e1_v2_estimate_kernel<<<cb, 32, 0, ctx->stream>>>(P);
+        e1_v2_estimate_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         e1_v2_span_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
-        e1_v2_chain_kernel<<<cb, 32, 0, ctx->stream>>>(P);
+        e1_v2_chain_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         ctx->timing.kernel_launches += 7;
+    }
+    {
+        e1_finalize_args F;
+        F.recs = d_recs;
+        F.ck = ctx->d_ck;
+        F.delta = ctx->d_delta;
+        F.delta_stride = n;
+        F.blk = ctx->d_blk;
+        F.counters = ctx->d_counters;
+        F.delt = ctx->delt;
+        F.n_epochs = n;
+        F.max_chan = cfg->max_chan;
+        F.tile = ctx->tile;
+        F.tiles_per_epoch = ctx->tiles_per_epoch;
+        F.tc_code = e1_tc_code(e1_thr_code(ctx->tile, ctx->amb_scale), ctx->run);
+        const long tiles = (long)n * ctx->tiles_per_epoch;
+        e1_finalize_kernel<<<(unsigned)((tiles + 3) / 4), 128, 0, ctx->stream>>>(F);
+        ctx->timing.kernel_launches += 1;
     }
     CK(cudaGetLastError());
     return mark(ctx, 0, 1);
@@ -358,16 +382,12 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
 {
     const e1b200_config *cfg = &ctx->cfg;
     e1_synth_args A;
-    A.recs = d_recs_plan + (size_t)e_off * cfg->max_chan;
-    A.ck = ctx->d_ck + (size_t)e_off * ctx->tiles_per_epoch * cfg->max_chan;
-    A.delta = ctx->d_delta;
-    A.delta_stride = ctx->plan_n;
-    A.delta_off = e_off;
+    (void)d_recs_plan;
+    A.blk = ctx->d_blk + e1_blk_bytes(cfg->max_chan) * (size_t)e_off * ctx->tiles_per_epoch;
     A.codes = ctx->d_codes;
     A.lut = ctx->d_lut;
     A.out = d_out;
     A.counters = ctx->d_counters;
-    A.delt = ctx->delt;
     A.n_epochs = n;
     A.n_samp = cfg->samples_per_epoch;
     A.max_chan = cfg->max_chan;
@@ -375,6 +395,8 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     A.tiles_per_epoch = ctx->tiles_per_epoch;
     A.thr_carr = e1_thr_carr(ctx->tile, ctx->amb_scale);
     A.thr_code = e1_thr_code(ctx->tile, ctx->amb_scale);
+    A.tc_carr = e1_tc_carr(A.thr_carr, ctx->run);
+    A.tc_code = e1_tc_code(A.thr_code, ctx->run);
     A.vec_ok = (cfg->samples_per_epoch % 4 == 0) && (((uintptr_t)d_out & 15u) == 0);
     A.use_bulk = ctx->use_bulk;
     long total_tiles = (long)n * ctx->tiles_per_epoch;
@@ -384,7 +406,7 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     int rc = mark(ctx, 1, 0);
     if (rc)
         return rc;
-    synth_for(ctx->groups)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
+    synth_for(ctx->run)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     ctx->timing.synth_launches += 1;

@@ -125,7 +125,7 @@ def hostsim():
         hs.hs_to_fixed.restype = C.c_ulonglong
         hs.hs_to_fixed.argtypes = [C.c_double, C.c_int]
         hs.hs_build_codes.argtypes = [C.c_void_p]
-        hs.hs_build_lut4.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+        hs.hs_build_lut.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
         hs.hs_synth_epochs.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         hs.hs_synth_epochs_p.argtypes = hs.hs_synth_epochs.argtypes + [C.c_int]
@@ -136,11 +136,11 @@ def hostsim():
 
 
 def product_lut():
-    """int32[2][4][512] carrier table in the product's layout, built from the ORACLE's tables."""
+    """int32[2][512][16] carrier table in the product's layout, built from the ORACLE's tables."""
     c, s = (C.c_int * 512)(), (C.c_int * 512)()
     oracle().e1o_carrier_lut(c, s)
-    lut = np.zeros(4096, np.int32)
-    hostsim().hs_build_lut4(c, s, lut.ctypes.data)
+    lut = np.zeros(hostsim().hs_lut_entries(), np.int32)
+    hostsim().hs_build_lut(c, s, lut.ctypes.data)
     return lut
 
 

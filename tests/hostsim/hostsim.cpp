@@ -55,11 +55,12 @@ void hs_build_codes(uint32_t *codes)
         e1_build_code_words(E1B_PRN_WORDS[p], E1C_PRN_WORDS[p], codes + (size_t)p * E1C_CODE_WORDS_PER_PRN);
 }
 
-void hs_build_lut4(const int *cos512, const int *sin512, int32_t *lut4) { e1_build_lut4(cos512, sin512, lut4); }
+void hs_build_lut(const int *cos512, const int *sin512, int32_t *lut) { e1_build_lut(cos512, sin512, lut); }
+int hs_lut_entries(void) { return E1C_LUT_ENTRIES; }
 
 int hs_code_words_per_prn(void) { return E1C_CODE_WORDS_PER_PRN; }
 
-// Whole pipeline on the host.  lut: int32[2][4][512] in the product layout (passed in by the test
+// Whole pipeline on the host.  lut: int32[2][512][16] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
 // stats[0] = samples resolved by the literal fallback, stats[1] = planner errors,
 // stats[2] = threads that took the slow path.
@@ -82,7 +83,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                       int16_t *out, int groups, int amb_scale, const int32_t *lut, unsigned long long *stats, int planner)
 {
     const double delt = 1.0 / fs_hz;
-    const int threads = 512, tile = groups * threads * E1C_RUN;
+    const int threads = E1C_THREADS, run = 4 * groups, tile = threads * run;
     const int tpe = (n_samp + tile - 1) / tile;
     std::vector<uint32_t> codes(E1C_N_PRN * E1C_CODE_WORDS_PER_PRN);
     hs_build_codes(codes.data());
@@ -138,48 +139,56 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                 delta[(size_t)e * max_chan + ch] = dcm[(size_t)ch * n_epochs + e];
     }
     const uint32_t thr_carr = e1_thr_carr(tile, amb_scale), thr_code = e1_thr_code(tile, amb_scale);
+    const uint32_t tc_carr = e1_tc_carr(thr_carr, run), tc_code = e1_tc_code(thr_code, run);
+    const uint32_t lim_carr = e1_lim_carr(tc_carr, thr_carr), lim_code = e1_lim_code(tc_code, thr_code);
     std::vector<e1_chan_par> par(max_chan);
     stats[0] = stats[1] = stats[2] = 0;
     for (int e = 0; e < n_epochs; e++)
         for (int t = 0; t < tpe; t++) {
-            int nact = 0;
+            int nact = 0; // e1_finalize_kernel
             for (int ch = 0; ch < max_chan; ch++) {
                 const e1_tile_ck *c = &ck[((size_t)e * tpe + t) * max_chan + ch];
                 if (!(c->sym & E1_CK_ACTIVE))
                     continue;
                 if (c->sym & E1_CK_ERROR)
                     stats[1]++;
-                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, delta[(size_t)e * max_chan + ch], &par[nact++]);
+                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, delta[(size_t)e * max_chan + ch], tc_code, &par[nact++]);
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
             int16_t *o = out + ((size_t)e * n_samp + (size_t)t * tile) * 2;
-            for (int g = 0; g < groups; g++)
-                for (int tid = 0; tid < threads; tid++) {
-                    const int j0 = (g * threads + tid) * E1C_RUN;
-                    if (j0 >= n_valid)
-                        continue;
-                    int acc[E1C_RUN] = {0, 0, 0, 0};
-                    uint32_t amb = 0;
-                    for (int a = 0; a < nact; a++)
-                        amb |= e1_run_fast(&par[a], codes.data(), (const unsigned char *)lut, j0, acc, thr_carr, thr_code);
-                    if (amb) {
-                        stats[2]++;
-                        for (int a = 0; a < nact; a++) {
-                            int t4[E1C_RUN] = {0, 0, 0, 0};
-                            if (e1_run_fast(&par[a], codes.data(), (const unsigned char *)lut, j0, t4, thr_carr, thr_code)) {
-                                for (int i = 0; i < E1C_RUN; i++)
-                                    acc[i] -= t4[i];
-                                e1_channel_run(&par[a], codes.data(), lut, j0, acc, thr_carr, thr_code, 1, &stats[0]);
-                            }
-                        }
+            for (int tid = 0; tid < threads; tid++) { // e1_synth_kernel, one thread
+                const int j0 = tid * run;
+                if (j0 >= n_valid)
+                    continue;
+                const unsigned char *lut_lane = (const unsigned char *)lut + 4 * (tid & (E1C_LUT_REP - 1));
+                int acc[E1C_MAX_RUN] = {0};
+                for (int a = 0; a < nact; a++) {
+                    uint32_t rc;
+                    switch (run) {
+                    case 4: rc = e1_run_fast<4>(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code); break;
+                    case 8: rc = e1_run_fast<8>(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code); break;
+                    default: rc = e1_run_fast<16>(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code); break;
                     }
-                    for (int i = 0; i < E1C_RUN; i++)
-                        if (j0 + i < n_valid) {
-                            uint32_t w = e1_pack_iq(acc[i]);
-                            o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
-                            o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
-                        }
+                    if (!rc)
+                        continue;
+                    stats[2]++; // e1_fix_run
+                    int tt[E1C_MAX_RUN] = {0}, g[E1C_MAX_RUN];
+                    switch (run) {
+                    case 4: e1_run_fast<4>(&par[a], codes.data(), lut_lane, j0, tt, tc_carr, lim_carr, lim_code); break;
+                    case 8: e1_run_fast<8>(&par[a], codes.data(), lut_lane, j0, tt, tc_carr, lim_carr, lim_code); break;
+                    default: e1_run_fast<16>(&par[a], codes.data(), lut_lane, j0, tt, tc_carr, lim_carr, lim_code); break;
+                    }
+                    e1_channel_run(&par[a], codes.data(), lut_lane, j0, run, g, thr_carr, thr_code, e1_bias_h(tc_code), &stats[0]);
+                    for (int i = 0; i < run; i++)
+                        acc[i] += g[i] - tt[i];
                 }
+                for (int i = 0; i < run; i++)
+                    if (j0 + i < n_valid) {
+                        uint32_t w = e1_pack_iq(acc[i]);
+                        o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
+                        o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
+                    }
+            }
         }
     return stats[1] ? -1 : 0;
 }
@@ -191,7 +200,7 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
                      int groups, unsigned long long *stats)
 {
     const double delt = 1.0 / fs_hz;
-    const int tile = groups * 512 * E1C_RUN;
+    const int tile = groups * 4 * E1C_THREADS;
     const int tpe = (n_samp + tile - 1) / tile;
     const size_t ne = (size_t)n_epochs * max_chan;
     std::vector<e1_tile_ck> ck1(ne * tpe), ck2(ne * tpe);

@@ -71,8 +71,9 @@ def test_fixed_point_conversion():
 
 
 def test_code_table_matches_oracle_halfchips():
-    """Packed half-chip table (product layout: bit0 = E1-B bit ^ (hh&1), bit1 = E1-B ^ E1-C) -> the
-    oracle's 8184-entry BOC(1,1) tables, all 50 PRNs."""
+    """Packed half-chip table (product layout: first half-chip in the top bits; high bit = 1 where the
+    E1-B half-chip is -1, low bit = high bit XOR (E1-C half-chip is -1)) -> the oracle's 8184-entry
+    BOC(1,1) tables, all 50 PRNs."""
     hs = U.hostsim()
     W = hs.hs_code_words_per_prn()
     codes = np.zeros(50 * W, np.uint32)
@@ -81,14 +82,27 @@ def test_code_table_matches_oracle_halfchips():
     tb, tc = (C.c_short * 8184)(), (C.c_short * 8184)()
     hh = np.arange(8184)
     for prn in range(1, 51):
-        f = (codes[(prn - 1) * W + (hh >> 4)] >> ((hh & 15) * 2)) & 3
+        f = (codes[(prn - 1) * W + (hh >> 4)] >> (30 - (hh & 15) * 2)) & 3
         lib.e1o_halfchip_table(prn, 0, tb)
         lib.e1o_halfchip_table(prn, 1, tc)
         eb, ec = np.array(tb), np.array(tc)          # +-1 including the sub-carrier sign
-        # bit0 = B ^ (hh&1): the E1-B half-chip is -chip on even hh -> level +1 exactly when bit0 == 1 ... check both
-        assert np.array_equal(eb, np.where((f & 1) == 1, 1, -1) * 1), prn
-        assert np.array_equal(ec, np.where(((f & 1) ^ (f >> 1)) == 1, 1, -1)), prn
+        bneg, cneg = f >> 1, (f >> 1) ^ (f & 1)
+        assert np.array_equal(eb, 1 - 2 * bneg.astype(np.int16)), prn
+        assert np.array_equal(ec, 1 - 2 * cneg.astype(np.int16)), prn
         assert not codes[(prn - 1) * W + 512:(prn - 1) * W + W].any()
+
+
+def test_carrier_table_layout():
+    """int32[2][512][16]: 2*(cos + 65536*sin) of the reference's tables, 16 copies per entry, second
+    half reflected for negative phase ((-i) & 511, src/galileo-sdr.cpp:509-510 with phi < 0)."""
+    c, s = (C.c_int * 512)(), (C.c_int * 512)()
+    U.oracle().e1o_carrier_lut(c, s)
+    c, s = np.array(c), np.array(s)
+    lut = U.product_lut().reshape(2, 512, 16)
+    w2 = 2 * (c + 65536 * s)
+    assert (lut == lut[:, :, :1]).all()
+    assert np.array_equal(lut[0, :, 0], w2)
+    assert np.array_equal(lut[1, :, 0], w2[(-np.arange(512)) & 511])
 
 
 @pytest.mark.parametrize("name,epochs", [("cfg1", (0, 1, 2, 28, 29, 30, 98)), ("paris45", (0, 1, 190, 191, 300, 301, 448))])
