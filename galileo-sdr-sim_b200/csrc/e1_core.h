@@ -312,11 +312,14 @@ typedef struct e1_chan_par { /* 96 bytes, one per active channel of a tile (HBM 
     uint32_t pat_a, pat_b;  /* symbol XOR pattern for the code words before / after the code wrap     */
     uint32_t code_off;      /* word offset of this PRN's code words                                   */
     uint32_t misc;          /* bits 0-1 symbol field (D<<1 | D^S) before the wrap, bits 2-3 after it,
-                               bit 4 negative-phase regime, bit 5 force the generic path              */
+                               bit 4 negative-phase regime, bit 5 force the generic path, bit 6: the
+                               phase runs through zero at tile sample j_z = bits 16-30 (from there on
+                               the magnitude is the two's complement of U and the regime flips)       */
     double phi, sp, cp, sc; /* exact checkpoint for the exact fallback                                */
 } e1_chan_par;
 #define E1_PAR_NEG 16u
 #define E1_PAR_FORCE 32u
+#define E1_PAR_HASZ 64u
 
 /* One tile's parameter block in HBM: header (16 bytes: n_active, 3 x pad) + max_chan e1_chan_par,
  * active channels first. */
@@ -438,8 +441,13 @@ E1_HD double e1_plan_carr_epoch(const e1_epoch_rec *r, e1_tile_ck *o, int stride
  * trajectories whose starts differ by D, a multiple of 2^-52 cycle, stay exactly D apart for as
  * long as every pair of corresponding values lies in the same binade -- every rounding grid
  * below 1.0 divides 2^-52, so fl(x + D + s) = fl(x + s) + D -- with one exception: a step s that
- * is a multiple of 2^-53 can make exact ties at the wrap step, whose round-half-even direction
- * depends on the parity of D (such epochs are walked serially).  Values right after a wrap are multiples of 2^-52.  Hence:
+ * is a multiple of 2^-53 can make exact ties at the wrap step (x + s an odd multiple of 2^-53 in
+ * [1,2), where the grid is 2^-52), whose round-half-even direction depends on the parity of
+ * d = D / 2^-52.  With d odd the translated walk lands one grid step to the other side, i.e. its
+ * translation becomes d + 1 (guess rounded down) or d - 1 (guess rounded up) -- even either way, so
+ * only the FIRST tie wrap of an epoch matters: the span pass records where it is and which way the
+ * guess went (e1_unit.tie_k / tie_dir) and the chain splits the epoch's translation there.
+ * Values right after a wrap are multiples of 2^-52.  Hence:
  *
  *   drift pass   (parallel, per epoch)   walk each epoch from an *ideal* start phase; the
  *                                        measured end-start gives that epoch's rounding drift
@@ -467,36 +475,27 @@ typedef struct e1_unit { /* one per (epoch, channel), 64 bytes */
     int32_t last_k;   /* sample index (1..N) of the last wrap inside this epoch, -1 if none     */
     int32_t type;
     int32_t neg;      /* sign of the walk (1: phase <= 0)                                       */
-    double reserved;
+    int32_t tie_k;    /* HAT: sample index (1..N) of the first tie wrap inside this epoch, -1 if none */
+    int32_t tie_dir;  /* HAT: +1 the guess rounded down there, -1 it rounded up                    */
 } e1_unit;
+
+/* Translation of one (channel, epoch): its carrier checkpoints are ck.phi + a for tile starts before
+ * sample k_split and ck.phi + b from there on (k_split = 0 and a = b unless a tie wrap split it). */
+typedef struct e1_trans {
+    double a, b;
+    int32_t k_split, pad;
+} e1_trans;
 
 typedef struct e1_span_track {
     double lo, hi;
     int64_t last_k;
     double last_p;
+    int64_t tie_k; /* first wrap whose sum was an exact tie (set by the caller to -1) */
+    int tie_dir;
 } e1_span_track;
 
 E1_HD double e1_binade_floor(double x) { return e1_from_bits((e1_bits(x) >> 52) << 52); }
 E1_HD double e1_binade_top(double x) { return e1_from_bits(((e1_bits(x) >> 52) + 1) << 52); }
-
-/* x is a nonzero multiple of 2^-53: such a step can land exactly half way between two
- * representable values at the wrap step (the tie case above) */
-E1_HD int e1_is_multiple_2m53(double x)
-{
-    int64_t b = e1_bits(x) & 0x7fffffffffffffffLL;
-    int e = (int)(b >> 52);
-    uint64_t m = (uint64_t)(b & 0xfffffffffffffLL);
-    if (e == 0)
-        return 0;
-    m |= 1ULL << 52;
-    int tz = 0;
-    while (!(m & 1ULL)) {
-        m >>= 1;
-        tz++;
-    }
-    /* x = m_odd * 2^(e - 1075 + tz) */
-    return (e - 1075 + tz) >= -53;
-}
 
 /* Aligned-regime walk of the phase magnitude: a in [0,1) grows by t in (0,0.5) per sample and
  * wraps at 1.0, from sample k to k_end.  Bit-identical to the literal loop (same binade jumps
@@ -504,7 +503,7 @@ E1_HD int e1_is_multiple_2m53(double x)
  *   - writes sign*a to o[(kt/tile)*stride].phi for every tile start kt with k < kt < n_emit
  *     (o == NULL: no checkpoints),
  *   - narrows tr->[lo,hi) to the translations that keep every visited value in its binade,
- *   - records the last wrap in tr->last_k / last_p.                                          */
+ *   - records the last wrap in tr->last_k / last_p and the first tie wrap in tr->tie_k / tie_dir. */
 E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile, int64_t n_emit, e1_tile_ck *o,
                           int stride, int neg, e1_span_track *tr)
 {
@@ -525,6 +524,15 @@ E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile
             double m = e1_add(1.0, -x1);
             if (m > lo)
                 lo = m;
+            if (tr->tie_k < 0) {
+                /* Fast2Sum (a >= 1/2 > t): err = (a + t) - x1 exactly.  x1 is on the 2^-52 grid, so the
+                   rounding was an exact tie iff |err| = 2^-53 */
+                const double err = e1_add(t, -e1_add(x1, -a));
+                if (err == 1.1102230246251565e-16 || err == -1.1102230246251565e-16) {
+                    tr->tie_k = k;
+                    tr->tie_dir = err > 0.0 ? 1 : -1;
+                }
+            }
             a = e1_add(x1, -1.0);
             tr->last_k = k;
             tr->last_p = a;
@@ -606,6 +614,8 @@ E1_HD double e1_carr_epoch_exact(double phi, double sp, int n_samp, int tile, in
     tr.hi = 2.0;
     tr.last_k = -1;
     tr.last_p = 0.0;
+    tr.tie_k = 0; /* not tracked */
+    tr.tie_dir = 0;
     o[0].phi = phi;
     double a = e1_span_walk(e1_fabs(phi), e1_fabs(sp), 0, n_samp, tile, n_samp, o, stride, neg, &tr);
     *last_k = (int32_t)tr.last_k;
@@ -708,7 +718,8 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     u->lo = 0.0;
     u->hi = 0.0;
     u->neg = 0;
-    u->reserved = 0.0;
+    u->tie_k = -1;
+    u->tie_dir = 0;
     if (!(pr->flags & E1_PREP_ACTIVE))
         return;
     const double sp = pr->sp;
@@ -726,13 +737,12 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
         return;
     if (!(e1_fabs(sp) < 0.5) || !(e1_fabs(sp0) < 0.5))
         return;
-    if (e1_is_multiple_2m53(sp) || e1_is_multiple_2m53(sp0))
-        return;
     const int neg = sp < 0.0;
-    if (est_prev != 0.0 && (est_prev < 0.0) != neg)
-        return; /* previous epoch started in the mixed regime */
-    const double a0 = e1_fabs(est_prev), t0 = e1_fabs(sp0), t1 = e1_fabs(sp);
-    if (!(a0 < 1.0))
+    /* start of the previous epoch measured along the direction of motion: negative when that epoch
+       started in the mixed regime (phase and Doppler of opposite sign) and first ran down to zero */
+    const double t0 = e1_fabs(sp0), t1 = e1_fabs(sp);
+    const double a0 = (est_prev == 0.0 || (est_prev < 0.0) == neg) ? e1_fabs(est_prev) : -e1_fabs(est_prev);
+    if (!(a0 < 1.0) || !(a0 > -1.0))
         return;
     /* last wrap of the previous epoch according to the estimate: unwrapped phase a0 + k*t0 */
     const double total = a0 + (double)n_samp * t0;
@@ -768,9 +778,12 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     tr.hi = 2.0;
     tr.last_k = -1;
     tr.last_p = 0.0;
+    tr.tie_k = 0;
+    tr.tie_dir = 0;
     double a = e1_span_walk(p, t0, kL, n_samp, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
     if (tr.last_k != -1)
         return; /* the guessed anchor was not the last wrap after all */
+    tr.tie_k = -1; /* ties only matter at this epoch's own wraps */
     o[0].phi = neg ? -a : a;
     a = e1_span_walk(a, t1, 0, n_samp, tile, n_samp, o, stride, neg, &tr);
     u->type = E1_UNIT_HAT;
@@ -782,11 +795,13 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     u->last_p = tr.last_p;
     u->lo = tr.lo;
     u->hi = tr.hi;
+    u->tie_k = (int32_t)tr.tie_k;
+    u->tie_dir = tr.tie_dir;
 }
 
 /* chain of one channel: validates HAT units, walks the others, writes the per-epoch translation
  * delta[e] (signed; the epoch's checkpoints are ck.phi + delta) and returns the final phase.
- * The state that runs along the chain is e1_chain_state; e1_v2_chain_step consumes one epoch, so
+ * (e1_trans).  The state that runs along the chain is e1_chain_state; e1_v2_chain_step consumes one epoch, so
  * the kernel can stage units / deltas through shared memory chunk by chunk.
  * stats[0] += epochs walked serially, stats[1] += HAT units accepted. */
 typedef struct e1_chain_state {
@@ -807,14 +822,17 @@ E1_HD void e1_chain_init(e1_chain_state *s, double phi0)
 
 /* u: this epoch's unit; sp: its carrier step; ck_e: this channel's first checkpoint of this epoch
  * (tiles `stride` apart), only touched when the epoch has to be walked serially. */
-E1_HD double e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, int n_samp, int tile, int tiles_per_epoch,
-                              e1_tile_ck *ck_e, int stride, unsigned long long *stats)
+E1_HD e1_trans e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, int n_samp, int tile, int tiles_per_epoch,
+                                e1_tile_ck *ck_e, int stride, unsigned long long *stats)
 {
     const int type = u->type;
-    double delta = 0.0;
+    e1_trans tr;
+    tr.a = tr.b = 0.0;
+    tr.k_split = 0;
+    tr.pad = 0;
     if (type == E1_UNIT_NONE) {
         s->prev_ok = 0;
-        return delta;
+        return tr;
     }
     int32_t last_k = u->last_k, neg = u->neg;
     double last_p = u->last_p;
@@ -823,12 +841,19 @@ E1_HD double e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, in
     } else {
         int ok = 0;
         if (type == E1_UNIT_HAT && s->prev_ok && s->prev_neg == neg && s->prev_k == u->anchor_k) {
-            const double D = e1_add(s->prev_p, -u->anchor_p);
-            if (D >= u->lo && D < u->hi) {
+            const double D = e1_add(s->prev_p, -u->anchor_p); /* a multiple of 2^-52, |D| < 1 */
+            double D2 = D;
+            if (u->tie_k >= 0 && ((long long)e1_mul(D, 4503599627370496.0) & 1LL))
+                D2 = e1_add(D, u->tie_dir > 0 ? 2.220446049250313e-16 : -2.220446049250313e-16);
+            if (D >= u->lo && D < u->hi && D2 >= u->lo && D2 < u->hi) {
                 ok = 1;
-                delta = neg ? -D : D;
-                s->phi = e1_add(u->end_phi, delta);
-                last_p = e1_add(last_p, D);
+                tr.a = neg ? -D : D;
+                tr.b = neg ? -D2 : D2;
+                tr.k_split = D2 != D ? u->tie_k : 0;
+                if (tr.k_split == 0)
+                    tr.a = tr.b;
+                s->phi = e1_add(u->end_phi, tr.b);
+                last_p = e1_add(last_p, D2); /* the last wrap is at or after the first tie wrap */
                 stats[1]++;
             }
         }
@@ -841,11 +866,11 @@ E1_HD double e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, in
     s->prev_neg = neg;
     s->prev_k = last_k;
     s->prev_p = last_p;
-    return delta;
+    return tr;
 }
 
 E1_HD double e1_v2_chain(const e1_prep *pp, int n_epochs, double phi0, int n_samp, int tile, int tiles_per_epoch,
-                         e1_unit *units, e1_tile_ck *ck, int stride, size_t ck_epoch_stride, double *delta,
+                         e1_unit *units, e1_tile_ck *ck, int stride, size_t ck_epoch_stride, e1_trans *delta,
                          unsigned long long *stats)
 {
     e1_chain_state s;
@@ -871,6 +896,9 @@ E1_HD uint64_t e1_bias_h(uint32_t tc_code) { return (uint64_t)tc_code << 19; }
 E1_HD uint32_t e1_lim_carr(uint32_t tc_carr, uint32_t thr_carr) { return tc_carr + thr_carr + 1u; }
 E1_HD uint32_t e1_lim_code(uint32_t tc_code, uint32_t thr_code) { return tc_code + 2u * thr_code + 1u; }
 
+/* translation of the checkpoint of the tile that starts at sample k0 of its epoch */
+E1_HD double e1_trans_at(const e1_trans *t, int k0) { return k0 >= t->k_split ? t->b : t->a; }
+
 /* Tile checkpoint + epoch record -> the per-channel parameters the sample loop reads. */
 E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, int tile, double delta, uint32_t tc_code,
                        e1_chan_par *p)
@@ -892,10 +920,14 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < 0.5) || !(p->sc < 0.4999))
         misc |= E1_PAR_FORCE;
     if (!aligned) {
-        /* |phi| shrinks; if it can reach zero inside the tile the sign regime changes
-           mid-tile: leave that (rare) tile to the exact path */
-        if (e1_fabs(p->phi) <= e1_mul(e1_fabs(p->sp), (double)(tile + 2)))
-            misc |= E1_PAR_FORCE;
+        /* |phi| shrinks by s per sample and, where it would go below zero, the phase changes sign and
+           the magnitude grows again (:531-532 keeps the sign of the sum).  In fixed point that is the
+           two's complement of U from the first sample j_z with U0 - j_z*s < 0 on. */
+        if (!(misc & E1_PAR_FORCE) && s != 0ull) {
+            const uint64_t jz = p->U0 / s + 1ull;
+            if (jz < (uint64_t)tile + 2ull && jz < 0x7fffull)
+                misc |= E1_PAR_HASZ | ((uint32_t)jz << 16);
+        }
         s = 0ull - s;
     }
     p->dU = s;
@@ -970,15 +1002,17 @@ E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const uns
     const uint64_t U0 = p->U0, dU = p->dU, HA = p->HA, dH = p->dH, HB = p->HB;
     const int jw = p->j_w;
     const uint32_t misc = p->misc;
+    const int jz = (misc & E1_PAR_HASZ) ? (int)(misc >> 16) : E1C_NO_WRAP;
     const uint32_t *code = codes + p->code_off;
-    const unsigned char *lut = lut_lane + ((misc & E1_PAR_NEG) ? E1C_LUT_REGIME_BYTES : 0);
     const uint32_t force = (misc >> 5) & 1u;
-    uint64_t U = U0 + (uint64_t)(uint32_t)j0 * dU;
+    uint64_t Ua = U0 + (uint64_t)(uint32_t)j0 * dU;
     for (int i = 0; i < R; i++) {
         const int j = j0 + i;
         const int after = j >= jw;
         const uint64_t H = (after ? HB : HA) + (uint64_t)(uint32_t)j * dH - bias_h;
         const uint32_t ds = after ? (misc >> 2) & 3u : misc & 3u;
+        const uint64_t U = j >= jz ? 0ull - Ua : Ua;
+        const uint32_t neg = ((misc & E1_PAR_NEG) ? 1u : 0u) ^ (j >= jz ? 1u : 0u);
         /* carrier: y = 511*|phi| in 9.32 fixed point */
         const uint32_t lo511 = e1_umulhi((uint32_t)U, 511u);
         const uint64_t y = (uint64_t)(uint32_t)(U >> 32) * 511u + lo511;
@@ -991,13 +1025,13 @@ E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const uns
         if (a) {
             uint32_t itx;
             e1_exact_indices(p, j, &h, &itx);
-            it = (misc & E1_PAR_NEG) ? ((0u - itx) & 511u) : itx; /* the table's regime half is already reflected */
+            it = neg ? ((0u - itx) & 511u) : itx; /* the table's negative half is stored reflected */
             (*n_exact)++;
         }
         const uint32_t f = ((code[h >> 4] >> (30u - 2u * (h & 15u))) ^ ds) & 3u; /* (x, x^y) */
         const int sgn = (f & 1u) ? ((f & 2u) ? -1 : 1) : 0;                      /* y - x */
-        add[i] = sgn * *(const int32_t *)(lut + it * (4u * E1C_LUT_REP));
-        U += dU;
+        add[i] = sgn * *(const int32_t *)(lut_lane + (neg ? E1C_LUT_REGIME_BYTES : 0) + it * (4u * E1C_LUT_REP));
+        Ua += dU;
     }
 }
 
@@ -1041,10 +1075,21 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
         win = (win & keep) | (wb & ~keep);
     }
     win &= (win << 1) | 0x55555555u; /* fields are now y - x in two's complement */
-    const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
+    uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU, dU = p->dU;
+    uint32_t neg = misc & E1_PAR_NEG;
+    if (misc & E1_PAR_HASZ) { /* rare: the phase changes sign inside this tile */
+        const int jz = (int)(misc >> 16);
+        if (j0 < jz && jz < j0 + R)
+            return 2u;
+        if (j0 >= jz) {
+            U = 0ull - U;
+            dU = 0ull - dU;
+            neg ^= E1_PAR_NEG;
+        }
+    }
     uint32_t uh = (uint32_t)(U >> 32);
-    const uint32_t duh = (uint32_t)(p->dU >> 32);
-    const unsigned char *lut = lut_lane + ((misc & E1_PAR_NEG) ? E1C_LUT_REGIME_BYTES : 0);
+    const uint32_t duh = (uint32_t)(dU >> 32);
+    const unsigned char *lut = lut_lane + (neg ? E1C_LUT_REGIME_BYTES : 0);
     uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
 #if defined(__CUDA_ARCH__)
 #pragma unroll

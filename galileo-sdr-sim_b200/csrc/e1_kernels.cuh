@@ -36,6 +36,7 @@ struct e1_synth_args {
     const int32_t *lut;
     int16_t *out;
     unsigned long long *counters; /* [0] ambiguous samples resolved exactly */
+    unsigned int *next_tile;      /* zeroed before the launch: tiles beyond the first wave are handed out dynamically */
     int n_epochs, n_samp, max_chan, tile, tiles_per_epoch;
     uint32_t thr_carr, thr_code; /* closed form vs serial recurrence (e1_thr_carr / e1_thr_code)  */
     uint32_t tc_carr, tc_code;   /* + the fast path's truncation slack (e1_tc_carr / e1_tc_code) */
@@ -45,8 +46,8 @@ struct e1_synth_args {
 struct e1_finalize_args {
     const e1_epoch_rec *recs;
     const e1_tile_ck *ck;
-    const double *delta; /* planner translation of each epoch's carrier checkpoints, channel-major:
-                            delta[ch * delta_stride + e]                                          */
+    const e1_trans *delta; /* planner translation of each epoch's carrier checkpoints, channel-major:
+                              delta[ch * delta_stride + e]                                        */
     int delta_stride;
     unsigned char *blk;
     unsigned long long *counters; /* [1] planner errors */
@@ -124,7 +125,8 @@ struct e1_plan_args {
     e1_tile_ck *ck;
     double *phase;   /* [max_chan] carried carrier phase (in: batch start, out: batch end) */
     e1_prep *prep;   /* channel-major [max_chan][n_epochs], like g, dend, est, delta and units */
-    double *g, *dend, *est, *delta;
+    double *g, *dend, *est;
+    e1_trans *delta;
     e1_unit *units;
     unsigned long long *counters; /* [2] serial epochs, [3] HAT epochs */
     double delt;
@@ -223,7 +225,8 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
 __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1_plan_args P)
 {
     __shared__ __align__(16) e1_unit s_units[E1_SERIAL_CHUNK];
-    __shared__ double s_sp[E1_SERIAL_CHUNK], s_delta[E1_SERIAL_CHUNK];
+    __shared__ double s_sp[E1_SERIAL_CHUNK];
+    __shared__ e1_trans s_delta[E1_SERIAL_CHUNK];
     const int ch = blockIdx.x, tid = threadIdx.x;
     if (ch >= P.max_chan)
         return;
@@ -282,8 +285,9 @@ __global__ void __launch_bounds__(128) e1_finalize_kernel(const e1_finalize_args
         const unsigned m = __ballot_sync(0xffffffffu, active);
         if (active) {
             e1_chan_par p;
-            e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + ch], A.delt, A.tile, A.delta[(size_t)ch * A.delta_stride + e],
-                        A.tc_code, &p);
+            const int t = (int)(tile_id - (long)e * A.tiles_per_epoch);
+            e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + ch], A.delt, A.tile,
+                        e1_trans_at(&A.delta[(size_t)ch * A.delta_stride + e], t * A.tile), A.tc_code, &p);
             if (c.sym & E1_CK_ERROR)
                 errs++;
             par[base + __popc(m & ((1u << lane) - 1u))] = p;
@@ -349,9 +353,12 @@ __device__ __noinline__ void e1_fix_run(const e1_chan_par *p, const uint32_t *co
 }
 
 /* Persistent CTA, one per SM.  Shared memory: code words of all PRNs (103 200 B) and the replicated
- * carrier table (65 536 B), both loaded once by bulk copy; two parameter-block buffers, tile i+1's
- * block in flight (bulk copy + mbarrier) while tile i is computed.  Thread t owns the R consecutive
- * samples [t*R, (t+1)*R) of the tile and walks the active channels with the I/Q sums in registers. */
+ * carrier table (65 536 B), both loaded once by bulk copy; two parameter-block buffers, the next
+ * tile's block in flight (bulk copy + mbarrier) while the current tile is computed.  The first wave of
+ * tiles is blockIdx.x; after that CTAs draw tile numbers from an atomic counter (one draw ahead, so
+ * the atomic's latency hides behind a tile), which keeps the SMs level when some tiles are slow.
+ * Thread t owns the R consecutive samples [t*R, (t+1)*R) of the tile and walks the active channels
+ * with the I/Q sums in registers. */
 template <int R>
 __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_synth_args A)
 {
@@ -362,9 +369,11 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
     unsigned char *s_blk0 = smem_raw + E1_CODES_BYTES + E1_LUT_BYTES;
     __shared__ __align__(8) uint64_t s_bar[3]; /* [0] tables, [1],[2] parameter buffers */
     __shared__ unsigned long long s_cnt;
+    __shared__ long s_tile[2]; /* tile number whose block is (being) loaded into buffer 0 / 1 */
 
     const int tid = threadIdx.x;
     const long total_tiles = (long)A.n_epochs * A.tiles_per_epoch;
+    long next_id = 0; /* thread 0: the tile after the one in s_tile[...] */
     if (tid == 0) {
         s_cnt = 0;
         e1_mbar_init(&s_bar[0], 1);
@@ -376,10 +385,12 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
             e1_bulk_g2s(s_codes, A.codes, E1_CODES_BYTES, &s_bar[0]);
             e1_bulk_g2s(s_lut, A.lut, E1_LUT_BYTES, &s_bar[0]);
         }
+        s_tile[0] = blockIdx.x;
         if ((long)blockIdx.x < total_tiles) {
             e1_mbar_expect(&s_bar[1], blk_bytes);
             e1_bulk_g2s(s_blk0, A.blk + (size_t)blockIdx.x * blk_bytes, blk_bytes, &s_bar[1]);
         }
+        next_id = (long)gridDim.x + atomicAdd(A.next_tile, 1u);
     }
     __syncthreads();
     if (A.use_bulk) {
@@ -396,14 +407,20 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
     const uint32_t lim_carr = e1_lim_carr(A.tc_carr, A.thr_carr), lim_code = e1_lim_code(A.tc_code, A.thr_code);
     const int j0 = tid * R;
     unsigned long long n_exact = 0;
-    int it = 0;
-    for (long tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, it++) {
+    for (int it = 0;; it++) {
         const int b = it & 1;
+        const long tile_id = s_tile[b];
+        if (tile_id >= total_tiles)
+            break;
         /* every thread is past the previous tile (barrier at the end of the loop body), so the other
-           buffer is free: start the next tile's block now */
-        if (tid == 0 && tile_id + gridDim.x < total_tiles) {
-            e1_mbar_expect(&s_bar[2 - b], blk_bytes);
-            e1_bulk_g2s(s_blk0 + (size_t)(1 - b) * blk_bytes, A.blk + (size_t)(tile_id + gridDim.x) * blk_bytes, blk_bytes, &s_bar[2 - b]);
+           buffer is free: start the next tile's block now, then draw the tile after it */
+        if (tid == 0) {
+            s_tile[1 - b] = next_id;
+            if (next_id < total_tiles) {
+                e1_mbar_expect(&s_bar[2 - b], blk_bytes);
+                e1_bulk_g2s(s_blk0 + (size_t)(1 - b) * blk_bytes, A.blk + (size_t)next_id * blk_bytes, blk_bytes, &s_bar[2 - b]);
+                next_id = (long)gridDim.x + atomicAdd(A.next_tile, 1u);
+            }
         }
         e1_mbar_wait(&s_bar[1 + b], (uint32_t)(it >> 1) & 1u);
         const unsigned char *blk = s_blk0 + (size_t)b * blk_bytes;
@@ -417,19 +434,15 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
 #pragma unroll
             for (int i = 0; i < R; i++)
                 acc[i] = 0;
-            unsigned long long redo = 0;
             for (int a = 0; a < nact; a++)
-                if (e1_run_fast<R>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code))
-                    redo |= 1ull << a;
-            while (redo) { /* rare: one (thread, channel) at a time through the generic form */
-                const int a = __ffsll((long long)redo) - 1;
-                redo &= redo - 1;
-                int d[R];
-                e1_fix_run<R>(&par[a], s_codes, lut_lane, j0, d, A.thr_carr, A.thr_code, A.tc_carr, A.tc_code, &n_exact);
+                if (e1_run_fast<R>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code)) {
+                    /* rare: this (thread, channel) goes through the generic form */
+                    int d[R];
+                    e1_fix_run<R>(&par[a], s_codes, lut_lane, j0, d, A.thr_carr, A.thr_code, A.tc_carr, A.tc_code, &n_exact);
 #pragma unroll
-                for (int i = 0; i < R; i++)
-                    acc[i] += d[i];
-            }
+                    for (int i = 0; i < R; i++)
+                        acc[i] += d[i];
+                }
             /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
             int16_t *dst = A.out + ((size_t)e * A.n_samp + (size_t)t * A.tile + j0) * 2;
             if (A.vec_ok && j0 + R <= n_valid) {
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
                         *reinterpret_cast<uint32_t *>(dst + 2 * i) = e1_pack_iq(acc[i]);
             }
         }
-        __syncthreads(); /* all reads of this tile's block are done */
+        __syncthreads(); /* all reads of this tile's block (and of s_tile[b]) are done */
     }
     if (n_exact)
         atomicAdd(&s_cnt, n_exact);

@@ -37,9 +37,11 @@ struct e1b200_ctx {
     int32_t *d_lut;
     double *d_phase;
     unsigned long long *d_counters; /* [0] exact-fallback samples [1] planner errors [2] serial epochs [3] HAT epochs */
+    unsigned int *d_next_tile;      /* dynamic tile counter of the synthesis kernel */
     e1_tile_ck *d_ck;
     unsigned char *d_blk;     /* per-tile parameter blocks of the current plan */
-    double *d_g, *d_dend, *d_est, *d_delta;
+    double *d_g, *d_dend, *d_est;
+    e1_trans *d_delta;
     e1_prep *d_prep;
     int plan_n;               /* epochs in the current plan (stride of the channel-major arrays) */
     e1_unit *d_units;
@@ -188,6 +190,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     CK(cudaMalloc(&ctx->d_lut, E1_LUT_BYTES));
     CK(cudaMalloc(&ctx->d_phase, sizeof(double) * E1B200_MAX_CHAN));
     CK(cudaMalloc(&ctx->d_counters, sizeof ctx->counters));
+    CK(cudaMalloc(&ctx->d_next_tile, sizeof(unsigned int)));
     CK(cudaMemcpy(ctx->d_codes, h_codes, E1_CODES_BYTES, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_lut, h_lut, E1_LUT_BYTES, cudaMemcpyHostToDevice));
     free(h_codes);
@@ -210,6 +213,7 @@ int e1b200_destroy(e1b200_ctx *ctx)
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_phase);
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_next_tile);
     cudaFree(ctx->d_ck);
     cudaFree(ctx->d_blk);
     cudaFree(ctx->d_g);
@@ -278,8 +282,8 @@ static int ensure_plan_scratch(e1b200_ctx *ctx)
     const size_t ne = (size_t)ctx->plan_epochs * ctx->cfg.max_chan;
     CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * ne * ctx->tiles_per_epoch));
     CK(cudaMalloc(&ctx->d_blk, e1_blk_bytes(ctx->cfg.max_chan) * (size_t)ctx->plan_epochs * ctx->tiles_per_epoch));
-    CK(cudaMalloc(&ctx->d_delta, sizeof(double) * ne));
-    CK(cudaMemset(ctx->d_delta, 0, sizeof(double) * ne));
+    CK(cudaMalloc(&ctx->d_delta, sizeof(e1_trans) * ne));
+    CK(cudaMemset(ctx->d_delta, 0, sizeof(e1_trans) * ne));
     if (!ctx->serial_planner) {
         CK(cudaMalloc(&ctx->d_g, sizeof(double) * ne));
         CK(cudaMalloc(&ctx->d_dend, sizeof(double) * ne));
@@ -327,7 +331,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
                                                                              ctx->tiles_per_epoch, ctx->delt);
         ctx->timing.kernel_launches += 2;
         /* the serial planner writes final checkpoints: translations are zero */
-        CK(cudaMemsetAsync(ctx->d_delta, 0, sizeof(double) * (size_t)nthr, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_delta, 0, sizeof(e1_trans) * (size_t)nthr, ctx->stream));
     } else {
         e1_plan_args P;
         P.recs = d_recs;
@@ -388,6 +392,7 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     A.lut = ctx->d_lut;
     A.out = d_out;
     A.counters = ctx->d_counters;
+    A.next_tile = ctx->d_next_tile;
     A.n_epochs = n;
     A.n_samp = cfg->samples_per_epoch;
     A.max_chan = cfg->max_chan;
@@ -403,6 +408,7 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     long grid = (long)ctx->sm_count * ctx->ctas_per_sm;
     if (grid > total_tiles)
         grid = total_tiles;
+    CK(cudaMemsetAsync(ctx->d_next_tile, 0, sizeof(unsigned int), ctx->stream));
     int rc = mark(ctx, 1, 0);
     if (rc)
         return rc;

@@ -93,7 +93,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
         for (int ch = 0; ch < max_chan; ch++)
             e1_plan_code_epoch(&recs[(size_t)e * max_chan + ch], &ck[(size_t)e * tpe * max_chan + ch], max_chan, n_samp, tile,
                                tpe, delt);
-    std::vector<double> delta((size_t)n_epochs * max_chan, 0.0);
+    std::vector<e1_trans> delta((size_t)n_epochs * max_chan, e1_trans{0.0, 0.0, 0, 0});
     stats[3] = stats[4] = 0;
     if (planner == 1) {
         for (int ch = 0; ch < max_chan; ch++) {
@@ -106,7 +106,8 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
     } else if (n_epochs > 0) {
         /* channel-major planner arrays, passes in kernel order */
         const size_t ne = (size_t)n_epochs * max_chan;
-        std::vector<double> g(ne), dend(ne), est(ne), dcm(ne, 0.0);
+        std::vector<double> g(ne), dend(ne), est(ne);
+        std::vector<e1_trans> dcm(ne, e1_trans{0.0, 0.0, 0, 0});
         std::vector<e1_unit> units(ne);
         std::vector<e1_prep> prep(ne);
         for (int e = 0; e < n_epochs; e++)
@@ -152,7 +153,8 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                     continue;
                 if (c->sym & E1_CK_ERROR)
                     stats[1]++;
-                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, delta[(size_t)e * max_chan + ch], tc_code, &par[nact++]);
+                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, e1_trans_at(&delta[(size_t)e * max_chan + ch], t * tile), tc_code,
+                            &par[nact++]);
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
             int16_t *o = out + ((size_t)e * n_samp + (size_t)t * tile) * 2;
@@ -206,7 +208,8 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
     std::vector<e1_tile_ck> ck1(ne * tpe), ck2(ne * tpe);
     memset(ck1.data(), 0, ck1.size() * sizeof(e1_tile_ck));
     memset(ck2.data(), 0, ck2.size() * sizeof(e1_tile_ck));
-    std::vector<double> g(ne), dend(ne), est(ne), delta(ne, 0.0), p1(max_chan), p2(max_chan);
+    std::vector<double> g(ne), dend(ne), est(ne), p1(max_chan), p2(max_chan);
+    std::vector<e1_trans> delta(ne, e1_trans{0.0, 0.0, 0, 0});
     std::vector<e1_unit> units(ne);
     stats[0] = stats[1] = stats[2] = 0;
     for (int ch = 0; ch < max_chan; ch++) {
@@ -217,7 +220,7 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
         p1[ch] = phi;
     }
     std::vector<e1_prep> prep(ne);
-    std::vector<double> dcm(ne, 0.0);
+    std::vector<e1_trans> dcm(ne, e1_trans{0.0, 0.0, 0, 0});
     for (int e = 0; e < n_epochs; e++)
         for (int ch = 0; ch < max_chan; ch++)
             e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, &prep[(size_t)ch * n_epochs + e]);
@@ -252,7 +255,8 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
             stats[2]++;
             for (int t = 0; t < tpe; t++) {
                 const size_t j = ((size_t)e * tpe + t) * max_chan + ch;
-                if (e1_bits(ck1[j].phi) != e1_bits(e1_add(ck2[j].phi, delta[i])) && !(ck1[j].phi == 0.0 && e1_add(ck2[j].phi, delta[i]) == 0.0))
+                const double v = e1_add(ck2[j].phi, e1_trans_at(&delta[i], t * tile));
+                if (e1_bits(ck1[j].phi) != e1_bits(v) && !(ck1[j].phi == 0.0 && v == 0.0))
                     bad++;
             }
         }
