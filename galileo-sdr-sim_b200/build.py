@@ -31,13 +31,16 @@ def nvcc_path():
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def build_lib(force=False, verbose=False):
-    if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
-        return LIB
-    LIB.parent.mkdir(exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB), str(SRC)]
+def build_lib(force=False, verbose=False, defines=(), out=None):
+    """defines / out: tuning builds (e.g. defines=["E1_VARIANT=2"], out=lib/libe1b200_v2.so)."""
+    lib = Path(out) if out else LIB
+    if not force and lib.exists() and all(lib.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
+        return lib
+    lib.parent.mkdir(exist_ok=True)
+    cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
+           + ["-o", str(lib), str(SRC)])
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

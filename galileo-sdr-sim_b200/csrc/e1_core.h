@@ -1091,16 +1091,34 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
     const uint32_t duh = (uint32_t)(dU >> 32);
     const unsigned char *lut = lut_lane + (neg ? E1C_LUT_REGIME_BYTES : 0);
     uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
+#ifndef E1_VARIANT
+#define E1_VARIANT 0
+#endif
+#if E1_VARIANT & 1
+    uint32_t uh1 = uh + duh; /* two interleaved chains, each stepping by duh + duh (three-input adds) */
+#endif
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < R; i++) {
-        const uint64_t y = (uint64_t)uh * 511u + tc_carr;
+#if E1_VARIANT & 1
+        const uint32_t uhi = (i & 1) ? uh1 : uh;
+#else
+        const uint32_t uhi = uh;
+#endif
+        const uint64_t y = (uint64_t)uhi * 511u + tc_carr;
         mY = (uint32_t)y < mY ? (uint32_t)y : mY;
         mF = F < mF ? F : mF;
         const int w = *(const int32_t *)(lut + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u));
         acc[i] += w * ((int)win >> 30);
+#if E1_VARIANT & 1
+        if (i & 1)
+            uh1 = uh1 + duh + duh;
+        else
+            uh = uh + duh + duh;
+#else
         uh += duh;
+#endif
         const uint32_t F2 = F + dF;
         if (F2 < F)
             win <<= 2;

@@ -30,7 +30,7 @@ struct e1b200_ctx {
     int sm_count, ctas_per_sm, smem_bytes;
     int use_bulk, amb_scale, serial_planner;
     cudaStream_t stream, copy_stream;
-    cudaEvent_t ev_buf[2], ev_copy[2];
+    std::vector<cudaEvent_t> ev_buf, ev_copy; /* per staging slot: synthesis done / D2H done */
     std::vector<cudaEvent_t> ev;   /* pairs (start, end) of the current call */
     std::vector<int> ev_kind;      /* 0 = planner pass, 1 = synthesis launch */
     uint32_t *d_codes;
@@ -47,7 +47,8 @@ struct e1b200_ctx {
     e1_unit *d_units;
     e1_epoch_rec *d_recs;     /* staging for the host entry points / restate output */
     e1_range_rec *d_ranges;
-    int16_t *d_out[2];        /* staging for the host entry points */
+    int16_t *d_stage;         /* staging ring for the host entry points: n_stage slots of batch_epochs blocks */
+    int n_stage;
     e1b200_timing timing;
     unsigned long long counters[4];
     char err[256];
@@ -168,10 +169,6 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        CK(cudaEventCreateWithFlags(&ctx->ev_buf[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
-    }
     synth_fn fn = synth_for(run);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
     int occ = 0;
@@ -224,14 +221,13 @@ int e1b200_destroy(e1b200_ctx *ctx)
     cudaFree(ctx->d_prep);
     cudaFree(ctx->d_recs);
     cudaFree(ctx->d_ranges);
-    cudaFree(ctx->d_out[0]);
-    cudaFree(ctx->d_out[1]);
+    cudaFree(ctx->d_stage);
     for (cudaEvent_t ev : ctx->ev)
         cudaEventDestroy(ev);
-    for (int i = 0; i < 2; i++) {
-        if (ctx->ev_buf[i]) cudaEventDestroy(ctx->ev_buf[i]);
-        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
-    }
+    for (cudaEvent_t ev : ctx->ev_buf)
+        cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->ev_copy)
+        cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -479,17 +475,35 @@ static int ensure_staging(e1b200_ctx *ctx, int want_ranges, int want_out)
         CK(cudaMalloc(&ctx->d_recs, nrec * sizeof(e1_epoch_rec)));
     if (want_ranges && !ctx->d_ranges)
         CK(cudaMalloc(&ctx->d_ranges, nrec * sizeof(e1_range_rec)));
-    if (want_out && !ctx->d_out[0]) {
-        size_t cap = (size_t)ctx->batch_epochs * cfg->samples_per_epoch * 4;
-        CK(cudaMalloc(&ctx->d_out[0], cap));
-        CK(cudaMalloc(&ctx->d_out[1], cap));
+    if (want_out > ctx->n_stage) {
+        /* a deep ring (up to 4 GiB of the 180 GB by default) lets the kernels run far ahead of the PCIe
+           copies, so a planner pass between two synthesis slices never starves the copy engine */
+        const size_t slot = (size_t)ctx->batch_epochs * cfg->samples_per_epoch * 4;
+        long cap = (long)(((size_t)env_int("E1B200_STAGE_MB", 4096) << 20) / slot);
+        cap = cap < 2 ? 2 : (cap > 64 ? 64 : cap);
+        int ns = want_out < 2 ? 2 : (want_out > cap ? (int)cap : want_out);
+        if (ns > ctx->n_stage) {
+            CK(cudaStreamSynchronize(ctx->copy_stream));
+            CK(cudaFree(ctx->d_stage));
+            ctx->d_stage = nullptr;
+            ctx->n_stage = 0;
+            CK(cudaMalloc(&ctx->d_stage, slot * ns));
+            while ((int)ctx->ev_buf.size() < ns) {
+                cudaEvent_t a, b;
+                CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+                ctx->ev_buf.push_back(a);
+                CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+                ctx->ev_copy.push_back(b);
+            }
+            ctx->n_stage = ns;
+        }
     }
     return E1B200_OK;
 }
 
 /* Host-buffer pipeline.  Per planner pass: records H2D, (restate,) planner kernels; then the
- * synthesis runs in slices of batch_epochs into two staging buffers, each slice's D2H on
- * `copy_stream` overlapping the next slice's kernel. */
+ * synthesis runs in slices of batch_epochs into a ring of staging slots, each slice's D2H on
+ * `copy_stream` overlapping the following kernels. */
 static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, const e1_range_rec *ranges, int16_t *out)
 {
     if (!ctx || n_epochs < 0 || (n_epochs && ((!recs && !ranges) || !out)))
@@ -497,15 +511,27 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
     CK(cudaSetDevice(ctx->cfg.device));
     int rc = ensure_plan_scratch(ctx);
     if (!rc)
-        rc = ensure_staging(ctx, ranges != nullptr, 1);
+        rc = ensure_staging(ctx, ranges != nullptr, n_epochs ? (n_epochs + ctx->batch_epochs - 1) / ctx->batch_epochs + 8 : 0);
     if (rc)
         return rc;
     reset_call(ctx);
     const e1b200_config *cfg = &ctx->cfg;
     const size_t epoch_i16 = (size_t)cfg->samples_per_epoch * 2;
     int slice = 0;
-    for (int p0 = 0; p0 < n_epochs; p0 += ctx->plan_epochs) {
-        int np = n_epochs - p0 < ctx->plan_epochs ? n_epochs - p0 : ctx->plan_epochs;
+    const int trace = env_int("E1B200_TRACE", 0);
+    std::vector<cudaEvent_t> tr_ev;
+    /* planner passes grow geometrically (256, 640, 1600, ... plan_epochs blocks): the first D2H starts
+       after a short pass instead of after the whole job's planning, and each pass's copies outlast the
+       next pass's planning (a pass costs ~5 ms of dependent walks however small it is, a block's D2H
+       ~20 us at 2.6 MS/s); the copies, not the kernels, bound this entry point */
+    int chunk = env_int("E1B200_FIRST_PASS", 256);
+    if (chunk < 1)
+        chunk = 1;
+    for (int p0 = 0, np = 0; p0 < n_epochs; p0 += np) {
+        np = chunk < ctx->plan_epochs ? chunk : ctx->plan_epochs;
+        if (np > n_epochs - p0)
+            np = n_epochs - p0;
+        chunk = chunk > (1 << 20) ? chunk : chunk * 5 / 2;
         size_t nrec = (size_t)np * cfg->max_chan;
         if (ranges) {
             CK(cudaMemcpyAsync(ctx->d_ranges, ranges + (size_t)p0 * cfg->max_chan, nrec * sizeof(e1_range_rec),
@@ -521,19 +547,48 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
             return rc;
         for (int e0 = 0; e0 < np; e0 += ctx->batch_epochs, slice++) {
             int n = np - e0 < ctx->batch_epochs ? np - e0 : ctx->batch_epochs;
-            int b = slice & 1;
-            if (slice >= 2) /* staging buffer b is free once its previous D2H finished */
+            int b = slice % ctx->n_stage;
+            int16_t *d_slot = ctx->d_stage + (size_t)b * ctx->batch_epochs * epoch_i16;
+            if (slice >= ctx->n_stage) /* slot b is free once its previous D2H finished */
                 CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-            if ((rc = enqueue_synth(ctx, e0, n, ctx->d_recs, ctx->d_out[b])))
+            if ((rc = enqueue_synth(ctx, e0, n, ctx->d_recs, d_slot)))
                 return rc;
             CK(cudaEventRecord(ctx->ev_buf[b], ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_buf[b], 0));
-            CK(cudaMemcpyAsync(out + (size_t)(p0 + e0) * epoch_i16, ctx->d_out[b], (size_t)n * epoch_i16 * 2,
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (trace) {
+                CK(cudaEventCreate(&t0));
+                CK(cudaEventCreate(&t1));
+                CK(cudaEventRecord(t0, ctx->copy_stream));
+            }
+            CK(cudaMemcpyAsync(out + (size_t)(p0 + e0) * epoch_i16, d_slot, (size_t)n * epoch_i16 * 2,
                                cudaMemcpyDeviceToHost, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+            if (trace) {
+                CK(cudaEventRecord(t1, ctx->copy_stream));
+                tr_ev.push_back(t0);
+                tr_ev.push_back(t1);
+            }
         }
     }
-    return e1b200_sync(ctx);
+    rc = e1b200_sync(ctx);
+    if (trace && !ctx->ev.empty()) { /* E1B200_TRACE=1: timeline of the call on stderr, ms since the first kernel */
+        for (size_t i = 0; i < ctx->ev_kind.size(); i++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ctx->ev.front(), ctx->ev[2 * i]);
+            cudaEventElapsedTime(&b, ctx->ev.front(), ctx->ev[2 * i + 1]);
+            fprintf(stderr, "e1b200 trace: %-5s %8.3f .. %8.3f ms\n", ctx->ev_kind[i] ? "synth" : "plan", a, b);
+        }
+        for (size_t i = 0; i + 1 < tr_ev.size(); i += 2) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ctx->ev.front(), tr_ev[i]);
+            cudaEventElapsedTime(&b, ctx->ev.front(), tr_ev[i + 1]);
+            fprintf(stderr, "e1b200 trace: d2h   %8.3f .. %8.3f ms\n", a, b);
+        }
+    }
+    for (cudaEvent_t ev : tr_ev)
+        cudaEventDestroy(ev);
+    return rc;
 }
 
 int e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, int16_t *out)

@@ -5,12 +5,13 @@ is C++ and its own integration is the patch in INTEGRATION.md.  There is no CPU 
 constructing a Synth without the built library or without a CUDA device raises.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libe1b200.so"
+LIB_PATH = Path(os.environ.get("E1B200_LIB") or PKG / "lib" / "libe1b200.so")   # E1B200_LIB: tuning builds (tools/variants.py)
 
 E1_REC_SET_PHASE = 1
 PAGE_BYTES = 64
