@@ -311,7 +311,7 @@ static void reset_call(e1b200_ctx *ctx)
 }
 
 /* planner kernels for n (<= plan_epochs) epochs whose records are on the device */
-static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
+static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int carrier_only = 0)
 {
     const e1b200_config *cfg = &ctx->cfg;
     int rc = mark(ctx, 0, 0);
@@ -319,8 +319,9 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
         return rc;
     const int nthr = n * cfg->max_chan;
     ctx->plan_n = n;
-    e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
-                                                                     ctx->tile, ctx->tiles_per_epoch, ctx->delt);
+    if (!carrier_only)
+        e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
+                                                                         ctx->tile, ctx->tiles_per_epoch, ctx->delt);
     if (ctx->serial_planner) {
         e1_plan_carr_kernel<<<(cfg->max_chan + 31) / 32, 32, 0, ctx->stream>>>(d_recs, ctx->d_ck, ctx->d_phase, n, cfg->max_chan,
                                                                              cfg->samples_per_epoch, ctx->tile,
@@ -355,7 +356,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs)
         e1_v2_chain_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         ctx->timing.kernel_launches += 7;
     }
-    {
+    if (!carrier_only) {
         e1_finalize_args F;
         F.recs = d_recs;
         F.ck = ctx->d_ck;
@@ -599,6 +600,31 @@ int e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs,
 int e1b200_synth_ranges(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *recs, int16_t *out)
 {
     return synth_host(ctx, n_epochs, nullptr, recs, out);
+}
+
+/* Carrier planner only: what chan[i].carr_phase would be after these blocks (src/galileo-sdr.cpp:531-532
+ * integrated over n_epochs * samples_per_epoch samples), without synthesising them.  The hand-off of a
+ * time-axis shard: rank r plans its segment, passes the phases on, then synthesises. */
+int e1b200_plan_phases(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs)
+{
+    if (!ctx || n_epochs < 0 || (n_epochs && !recs))
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_plan_scratch(ctx);
+    if (!rc)
+        rc = ensure_staging(ctx, 0, 0);
+    if (rc)
+        return rc;
+    reset_call(ctx);
+    for (int p0 = 0; p0 < n_epochs; p0 += ctx->plan_epochs) {
+        const int np = n_epochs - p0 < ctx->plan_epochs ? n_epochs - p0 : ctx->plan_epochs;
+        CK(cudaMemcpyAsync(ctx->d_recs, recs + (size_t)p0 * ctx->cfg.max_chan, (size_t)np * ctx->cfg.max_chan * sizeof(e1_epoch_rec),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = enqueue_plan(ctx, np, ctx->d_recs, 1)))
+            return rc;
+        CK(cudaStreamSynchronize(ctx->stream)); /* recs may be pageable: the copy must be done before the caller reuses it */
+    }
+    return e1b200_sync(ctx);
 }
 
 int e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *d_rr, int16_t *d_out)

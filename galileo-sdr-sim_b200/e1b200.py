@@ -50,7 +50,7 @@ class Stats(C.Structure):
 SYMBOLS = [
     "e1b200_create", "e1b200_destroy", "e1b200_set_channel", "e1b200_clear_channel",
     "e1b200_get_carrier_phase", "e1b200_set_carrier_phase", "e1b200_synth_epochs",
-    "e1b200_synth_epochs_device", "e1b200_sync", "e1b200_synth_ranges", "e1b200_synth_ranges_device",
+    "e1b200_synth_epochs_device", "e1b200_sync", "e1b200_synth_ranges", "e1b200_synth_ranges_device", "e1b200_plan_phases",
     "e1b200_restate", "e1b200_get_timing", "e1b200_get_stats", "e1b200_stream", "e1b200_last_error",
     "e1b200_version", "e1b200_host_alloc", "e1b200_host_free",
 ]
@@ -80,6 +80,7 @@ def load():
     lib.e1b200_set_carrier_phase.argtypes = [vp, C.c_int, C.c_double]
     for name in ("e1b200_synth_epochs", "e1b200_synth_epochs_device", "e1b200_synth_ranges", "e1b200_synth_ranges_device"):
         getattr(lib, name).argtypes = [vp, C.c_int, vp, vp]
+    lib.e1b200_plan_phases.argtypes = [vp, C.c_int, vp]
     lib.e1b200_sync.argtypes = [vp]
     lib.e1b200_restate.argtypes = [C.c_double] * 4 + [dp, dp, dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.e1b200_get_timing.argtypes = [vp, C.POINTER(Timing)]
@@ -183,6 +184,17 @@ class Synth:
 
     def carrier_phases(self):
         return np.array([self.get_carrier_phase(s) for s in range(self.max_chan)])
+
+    def set_carrier_phases(self, phases):
+        for slot, ph in enumerate(np.asarray(phases, dtype=np.float64)[: self.max_chan]):
+            self.set_carrier_phase(slot, float(ph))
+
+    def plan_phases(self, recs):
+        """Advance the carrier phases over recs [n_epochs, max_chan] without synthesising (shard hand-off)."""
+        recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        assert recs.ndim == 2 and recs.shape[1] == self.max_chan, recs.shape
+        self._check(self._lib.e1b200_plan_phases(self._h, recs.shape[0], recs.ctypes.data), "plan_phases")
+        return self.carrier_phases()
 
     def _host_call(self, fn, recs, dtype, out):
         recs = np.ascontiguousarray(recs, dtype=dtype)

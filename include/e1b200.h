@@ -122,6 +122,12 @@ int  e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs
 int  e1b200_synth_epochs_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *d_recs, int16_t *d_out);
 int  e1b200_sync(e1b200_ctx *ctx);
 
+/* Carrier planner only: advances the slots' carrier phases over n_epochs blocks (host records)
+ * without synthesising them -- the value chan[i].carr_phase has after the reference's loop ran
+ * over those blocks (src/galileo-sdr.cpp:531-532).  Used for the phase hand-off between
+ * time-axis shards and for checkpoint/resume.                                               */
+int  e1b200_plan_phases(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs);
+
 /* Same two, from pseudoranges (restate evaluated on the device).                            */
 int  e1b200_synth_ranges(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *recs, int16_t *out);
 int  e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *d_recs, int16_t *d_out);

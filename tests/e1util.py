@@ -313,3 +313,31 @@ def synthetic_recs_fast(n_epochs, n_chan, fs_hz, seed=0, max_chan=None, f_max=40
     v["page_cur"] = packed[c, pidx]
     v["page_next"] = packed[c, pidx + 1]
     return recs
+
+
+# ----------------------------------------------------------------------------- shard-test engine
+class OracleEngine:
+    """The engine interface galileo-sdr-sim_b200/shard.py drives (set_carrier_phases / plan_phases /
+    synth_epochs / carrier_phases / max_chan), backed by the CPU oracle.  TEST ONLY: lets the GPU-less
+    suite cover the split / phase hand-off / file-offset logic of the sharded path."""
+
+    def __init__(self, fs_hz, n_samp, max_chan, threads=1):
+        self.fs, self.n_samp, self.max_chan, self.threads = fs_hz, n_samp, max_chan, threads
+        self.ph = np.zeros(max_chan)
+
+    def set_carrier_phases(self, phases):
+        self.ph = np.array(phases, dtype=np.float64)[: self.max_chan].copy()
+
+    def carrier_phases(self):
+        return self.ph.copy()
+
+    def plan_phases(self, recs):
+        _, self.ph = oracle_synth(self.fs, self.n_samp, recs, self.ph, threads=self.threads)
+        return self.ph.copy()
+
+    def synth_epochs(self, recs, out=None):
+        res, self.ph = oracle_synth(self.fs, self.n_samp, recs, self.ph, threads=self.threads)
+        if out is not None:
+            out.reshape(-1)[: res.size] = res.reshape(-1)
+            return out
+        return res
