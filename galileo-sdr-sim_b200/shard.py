@@ -91,9 +91,11 @@ def gather_segments(seg, rank, world, dist, n_epochs, n_samp, dist_device="cpu")
     rank; the sizes are known from split_epochs).  Returns the whole stream on rank 0, None elsewhere."""
     import torch
     ranges = split_epochs(n_epochs, world)
+    # NCCL has no int16: one (I, Q) pair travels as one int32
     if rank != 0:
         if seg.shape[0]:
-            dist.send(torch.from_numpy(np.ascontiguousarray(seg)).to(dist_device), dst=0)
+            t = torch.from_numpy(np.ascontiguousarray(seg).view(np.int32).reshape(-1))
+            dist.send(t.to(dist_device), dst=0)
         return None
     out = np.empty((n_epochs * n_samp, 2), np.int16)
     out[: seg.shape[0]] = seg
@@ -101,7 +103,7 @@ def gather_segments(seg, rank, world, dist, n_epochs, n_samp, dist_device="cpu")
         lo, hi = ranges[r]
         if hi == lo:
             continue
-        t = torch.empty(((hi - lo) * n_samp, 2), dtype=torch.int16, device=dist_device)
+        t = torch.empty((hi - lo) * n_samp, dtype=torch.int32, device=dist_device)
         dist.recv(t, src=r)
-        out[lo * n_samp:hi * n_samp] = t.cpu().numpy()
+        out[lo * n_samp:hi * n_samp] = t.cpu().numpy().view(np.int16).reshape(-1, 2)
     return out

@@ -43,6 +43,39 @@ def test_carrier_walker_ties_and_sign_changes():
                     assert hs.hs_carr_advance(ps * phi, s * sp, 0, n) == hs.hs_carr_literal(ps * phi, s * sp, n), (sp, phi, s, ps)
 
 
+def test_carrier_walker_adversarial_steps():
+    """The jump length comes from RN_even(t / ulp) without probing: steps that are exact half-ulp ties in
+    one binade (lowest set bit of t = half that binade's ulp), steps with few mantissa bits, steps so
+    small the integer-division path or the stuck path is taken, and steps of nearly half a cycle."""
+    hs = U.hostsim()
+    rng = np.random.default_rng(99)
+    steps = []
+    for e in range(-30, -1):                      # one set bit, and neighbours that make ties in the binade two above
+        steps += [2.0 ** e, 2.0 ** e + 2.0 ** (e - 52), 2.0 ** e - 2.0 ** (e - 53), 3 * 2.0 ** e * 0.25 + 2.0 ** -54]
+    steps += [k * 2.0 ** -54 for k in (1, 3, 5, 2 ** 20 + 1, 2 ** 43 + 1, 2 ** 44 + 3)]   # ties in [1/2, 1)
+    steps += [k * 2.0 ** -55 for k in (1, 3, 2 ** 40 + 1)]                                 # ties in [1/4, 1/2)
+    steps += [1e-12, 7.3e-9, 2.0 ** -27 * 1.0000001, 2.0 ** -26, 1e-7, 0.4999999, 0.3333333333333333]
+    steps += list(rng.uniform(0, 2e-3, 40)) + list(rng.uniform(0, 1e-6, 20))
+    for sp in steps:
+        for phi in (0.0, rng.uniform(0, 1), 1 - 2.0 ** -53, 2.0 ** -52, 0.5, 0.25 - 2.0 ** -55):
+            n = int(rng.integers(1000, 30000)) if sp > 1e-4 else int(rng.integers(1000, 200000))
+            for sg in (1, -1):
+                assert hs.hs_carr_advance(sg * phi, sg * sp, 0, n) == hs.hs_carr_literal(sg * phi, sg * sp, n), (sp, phi, n, sg)
+
+
+def test_code_walker_adversarial_steps():
+    hs = U.hostsim()
+    rng = np.random.default_rng(98)
+    for sc in (0.5, 0.25, 0.39346153846153847, 2.0 ** -2 + 2.0 ** -43, 2.0 ** -2 + 2.0 ** -42, 1.0, 1.5, 0.04092, 2.0 ** -20,
+               0.4092 + 2.0 ** -41, 3.0 * 2.0 ** -3, 1e-9):
+        for cp in (0.0, 4091.999999, 2048.0, 2047.9999999999998, rng.uniform(0, 4092), 2.0 ** -40):
+            n = 60000
+            w1, w2 = C.c_long(), C.c_long()
+            a = hs.hs_code_advance(cp, sc, n, w1)
+            b = hs.hs_code_literal(cp, sc, n, w2)
+            assert a == b and w1.value == w2.value, (sc, cp)
+
+
 def test_code_walker_equals_literal_loop():
     hs = U.hostsim()
     rng = np.random.default_rng(12)

@@ -47,6 +47,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     fs = U.fs_as_reference(args.fs)
@@ -58,6 +59,8 @@ def main():
     h_out = E.PinnedBuffer(max(hi - lo, 1) * n_samp * 4)
     out_view = h_out.view(np.int16)[: (hi - lo) * n_samp * 2].reshape(-1, 2)
     eng.synth_epochs(recs[lo:min(hi, lo + 8)], out_view[: (min(hi, lo + 8) - lo) * n_samp])      # warm-up: allocations, tables
+    if world > 1:                                                                                  # ... and NCCL's lazy P2P set-up
+        S.handoff_start_phases(eng, recs[: 2 * world], rank, world, dist, dist_device=dev)
 
     def barrier():
         if world > 1:
