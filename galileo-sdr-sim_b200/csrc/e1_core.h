@@ -461,12 +461,40 @@ E1_HD double e1_plan_carr_epoch(const e1_epoch_rec *r, e1_tile_ck *o, int stride
  *                                        epoch's checkpoints are hat + D, else (rare) the epoch
  *                                        is walked serially from its true start
  * Correctness never depends on the guesses, only speed does.                                   */
+/* The unit of parallel work is a SPAN: a run of span_tiles consecutive tiles of one epoch of one
+ * channel (an epoch is cut into S = ceil(tiles_per_epoch / span_tiles) spans, e1_span_geometry), so
+ * even a single epoch gives every channel several walks to run side by side and the serial
+ * dependency per thread is a span, not an epoch.  Everything above holds with "epoch" read as "span":
+ * a span's records are its epoch's, E1_REC_SET_PHASE applies to the epoch's first span only.      */
+typedef struct e1_span_geo {
+    int span_tiles;      /* tiles per span (the epoch's last span may be shorter) */
+    int spans_per_epoch; /* S */
+} e1_span_geo;
+E1_HD e1_span_geo e1_span_geometry(int tiles_per_epoch)
+{
+    e1_span_geo g;
+    int st = (tiles_per_epoch + 7) / 8; /* at most 8 spans per epoch ... */
+    if (st < 8)
+        st = 8; /* ... of at least 8 tiles: the guesses need a wrap inside the span before */
+    if (st > tiles_per_epoch)
+        st = tiles_per_epoch;
+    g.span_tiles = st;
+    g.spans_per_epoch = (tiles_per_epoch + st - 1) / st;
+    return g;
+}
+/* samples in span s of an epoch of n_samp samples */
+E1_HD int e1_span_samples(const e1_span_geo *g, int s, int n_samp, int tile)
+{
+    const int64_t k0 = (int64_t)s * g->span_tiles * tile, k1 = k0 + (int64_t)g->span_tiles * tile;
+    return (int)((k1 < n_samp ? k1 : n_samp) - k0);
+}
+
 #define E1_UNIT_NONE 0   /* slot idle this epoch                                                   */
 #define E1_UNIT_EXACT 1  /* walked from an exactly known start (batch start / E1_REC_SET_PHASE)    */
 #define E1_UNIT_HAT 2    /* walked from a guessed anchor: needs the chain's translation            */
 #define E1_UNIT_SERIAL 3 /* not eligible for a guess: the chain walks it                           */
 
-typedef struct e1_unit { /* one per (epoch, channel), 64 bytes */
+typedef struct e1_unit { /* one per (span, channel), 64 bytes */
     double anchor_p;  /* HAT: guessed |phase| right after the anchor wrap (multiple of 2^-52)   */
     double end_phi;   /* signed phase after the epoch's last sample (hat for HAT units)         */
     double last_p;    /* |phase| right after the last wrap inside this epoch (hat for HAT)      */
@@ -631,18 +659,19 @@ typedef struct e1_prep {
     double sp;      /* fl(f_carr * delt): carrier phase step per sample (:531)                  */
     double init;    /* carr_phase_init (valid with E1_PREP_SET_PHASE)                            */
     uint32_t flags; /* E1_PREP_*                                                                 */
-    uint32_t pad;
+    int32_t n;      /* samples in this span                                                      */
 } e1_prep;
 #define E1_PREP_ACTIVE 1u
 #define E1_PREP_SET_PHASE 2u
 
-E1_HD void e1_v2_prep(const e1_epoch_rec *r, double delt, e1_prep *p)
+/* span s (n samples) of the epoch described by r */
+E1_HD void e1_v2_prep(const e1_epoch_rec *r, double delt, int s, int n, e1_prep *p)
 {
     const int act = e1_rec_active(r);
     p->sp = act ? e1_mul(r->f_carr, delt) : 0.0;
     p->init = r->carr_phase_init;
-    p->flags = (act ? E1_PREP_ACTIVE : 0u) | ((act && (r->flags & E1_REC_SET_PHASE)) ? E1_PREP_SET_PHASE : 0u);
-    p->pad = 0;
+    p->flags = (act ? E1_PREP_ACTIVE : 0u) | ((act && s == 0 && (r->flags & E1_REC_SET_PHASE)) ? E1_PREP_SET_PHASE : 0u);
+    p->n = n;
 }
 
 /* phase + whole-epoch advance, folded back into (-1,1) the way :532 does (sign kept) */
@@ -655,7 +684,7 @@ E1_HD double e1_ideal_next(double g, double sp, int n_samp)
 }
 
 /* K0: ideal (rounding-free, double precision) start phase of every epoch of one channel. */
-E1_HD void e1_v2_ideal_prefix(const e1_prep *pp, int n_epochs, double phi0, int n_samp, double *g_out)
+E1_HD void e1_v2_ideal_prefix(const e1_prep *pp, int n_epochs, double phi0, double *g_out)
 {
     double g = phi0;
     for (int e = 0; e < n_epochs; e++) {
@@ -664,16 +693,16 @@ E1_HD void e1_v2_ideal_prefix(const e1_prep *pp, int n_epochs, double phi0, int 
             g = pp[e].init;
         g_out[e] = g;
         if (f & E1_PREP_ACTIVE)
-            g = e1_ideal_next(g, pp[e].sp, n_samp);
+            g = e1_ideal_next(g, pp[e].sp, pp[e].n);
     }
 }
 
 /* drift pass: exact walk of one epoch from its ideal start; returns the end phase */
-E1_HD double e1_v2_drift_unit(const e1_prep *p, double g, int n_samp)
+E1_HD double e1_v2_drift_unit(const e1_prep *p, double g)
 {
     if (!(p->flags & E1_PREP_ACTIVE))
         return g;
-    return e1_carr_advance(g, p->sp, 0, n_samp);
+    return e1_carr_advance(g, p->sp, 0, p->n);
 }
 
 /* K1: refined start-phase estimates of one channel.  The drift pass walked epoch e exactly from
@@ -707,8 +736,9 @@ E1_HD double e1_v2_estimate_prefix(const e1_prep *pp, int n_epochs, double phi0,
 /* span pass for one (epoch, channel): p / p_prev are this channel's prep records of epoch e and
  * e-1, o its first tile checkpoint of epoch e (tile stride `stride`). */
 E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, double phi_batch_start, double est_prev,
-                           int n_samp, int tile, int tiles_per_epoch, e1_tile_ck *o, int stride, e1_unit *u)
+                           int tile, e1_tile_ck *o, int stride, e1_unit *u)
 {
+    const int n_samp = pr->n, tiles_per_epoch = (pr->n + tile - 1) / tile; /* of this span */
     u->type = E1_UNIT_NONE;
     u->last_k = -1;
     u->anchor_k = -1;
@@ -745,7 +775,8 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     if (!(a0 < 1.0) || !(a0 > -1.0))
         return;
     /* last wrap of the previous epoch according to the estimate: unwrapped phase a0 + k*t0 */
-    const double total = a0 + (double)n_samp * t0;
+    const int n_prev = pr_prev->n;
+    const double total = a0 + (double)n_prev * t0;
     const double W = (double)(long long)total;
     if (W < 1.0)
         return; /* no wrap to anchor on */
@@ -768,7 +799,7 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
         else
             break;
     }
-    if (!(p >= 0.0) || !(p < t0) || kL < 1 || kL > n_samp)
+    if (!(p >= 0.0) || !(p < t0) || kL < 1 || kL > n_prev)
         return;
     /* round the guess to the post-wrap grid */
     const double two52 = 4503599627370496.0;
@@ -780,7 +811,7 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     tr.last_p = 0.0;
     tr.tie_k = 0;
     tr.tie_dir = 0;
-    double a = e1_span_walk(p, t0, kL, n_samp, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
+    double a = e1_span_walk(p, t0, kL, n_prev, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
     if (tr.last_k != -1)
         return; /* the guessed anchor was not the last wrap after all */
     tr.tie_k = -1; /* ties only matter at this epoch's own wraps */
@@ -869,15 +900,19 @@ E1_HD e1_trans e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, 
     return tr;
 }
 
-E1_HD double e1_v2_chain(const e1_prep *pp, int n_epochs, double phi0, int n_samp, int tile, int tiles_per_epoch,
-                         e1_unit *units, e1_tile_ck *ck, int stride, size_t ck_epoch_stride, e1_trans *delta,
-                         unsigned long long *stats)
+/* ck points at this channel's first checkpoint of the batch; the tiles of consecutive spans follow
+ * each other `stride` apart (tile-major layout [epoch][tile][channel], stride = max_chan). */
+E1_HD double e1_v2_chain(const e1_prep *pp, int n_units, double phi0, int tile, e1_unit *units, e1_tile_ck *ck, int stride,
+                         e1_trans *delta, unsigned long long *stats)
 {
     e1_chain_state s;
     e1_chain_init(&s, phi0);
-    for (int e = 0; e < n_epochs; e++)
-        delta[e] = e1_v2_chain_step(&s, &units[e], pp[e].sp, n_samp, tile, tiles_per_epoch, ck + (size_t)e * ck_epoch_stride,
-                                    stride, stats);
+    size_t tile0 = 0;
+    for (int u = 0; u < n_units; u++) {
+        const int tiles = (pp[u].n + tile - 1) / tile;
+        delta[u] = e1_v2_chain_step(&s, &units[u], pp[u].sp, pp[u].n, tile, tiles, ck + tile0 * (size_t)stride, stride, stats);
+        tile0 += (size_t)tiles;
+    }
     return s.phi;
 }
 

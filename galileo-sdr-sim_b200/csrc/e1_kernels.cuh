@@ -46,9 +46,10 @@ struct e1_synth_args {
 struct e1_finalize_args {
     const e1_epoch_rec *recs;
     const e1_tile_ck *ck;
-    const e1_trans *delta; /* planner translation of each epoch's carrier checkpoints, channel-major:
-                              delta[ch * delta_stride + e]                                        */
+    const e1_trans *delta; /* planner translation of each span's carrier checkpoints, channel-major:
+                              delta[ch * delta_stride + e * geo.spans_per_epoch + span]           */
     int delta_stride;
+    e1_span_geo geo;
     unsigned char *blk;
     unsigned long long *counters; /* [1] planner errors */
     double delt;
@@ -124,13 +125,16 @@ struct e1_plan_args {
     const e1_epoch_rec *recs;
     e1_tile_ck *ck;
     double *phase;   /* [max_chan] carried carrier phase (in: batch start, out: batch end) */
-    e1_prep *prep;   /* channel-major [max_chan][n_epochs], like g, dend, est, delta and units */
+    e1_prep *prep;   /* channel-major [max_chan][n_units], like g, dend, est, delta and units;
+                        unit u = epoch * geo.spans_per_epoch + span                              */
     double *g, *dend, *est;
     e1_trans *delta;
     e1_unit *units;
     unsigned long long *counters; /* [2] serial epochs, [3] HAT epochs */
     double delt;
     int n_epochs, n_samp, max_chan, tile, tiles_per_epoch;
+    e1_span_geo geo;
+    int n_units; /* n_epochs * geo.spans_per_epoch */
 };
 
 __global__ void e1_v2_prep_kernel(const e1_plan_args P)
@@ -139,121 +143,253 @@ __global__ void e1_v2_prep_kernel(const e1_plan_args P)
     if (i >= P.n_epochs * P.max_chan)
         return;
     int e = i / P.max_chan, ch = i - e * P.max_chan;
-    e1_v2_prep(&P.recs[i], P.delt, &P.prep[(size_t)ch * P.n_epochs + e]);
+    for (int sp = 0; sp < P.geo.spans_per_epoch; sp++)
+        e1_v2_prep(&P.recs[i], P.delt, sp, e1_span_samples(&P.geo, sp, P.n_samp, P.tile),
+                   &P.prep[(size_t)ch * P.n_units + (size_t)e * P.geo.spans_per_epoch + sp]);
 }
 
-/* The three serial per-channel passes (ideal prefix, estimate prefix, chain) run one channel per
- * block: the block stages a chunk of that channel's (channel-major, contiguous) records through
- * shared memory with coalesced loads, thread 0 walks the chunk out of shared memory, the block
- * writes the results back coalesced.  Walking straight out of global memory costs one DRAM round
- * trip per epoch (measured: 7.9 us per epoch in the chain). */
+/* first checkpoint of (unit u, channel ch): [epoch][tile][channel] */
+__device__ __forceinline__ e1_tile_ck *e1_unit_ck(const e1_plan_args &P, int u, int ch)
+{
+    const int e = u / P.geo.spans_per_epoch, sp = u - e * P.geo.spans_per_epoch;
+    return P.ck + ((size_t)e * P.tiles_per_epoch + (size_t)sp * P.geo.span_tiles) * P.max_chan + ch;
+}
+
+/* The three per-channel passes (ideal prefix, estimate prefix, chain) run one channel per block of
+ * E1_SERIAL_THREADS threads over that channel's n_units spans (channel-major, contiguous).
+ *
+ * The two prefix passes only produce ESTIMATES (nothing exact depends on their last bit: the chain
+ * validates every guess), so they are evaluated as chunked scans: every thread folds its contiguous
+ * run of units from a zero start, thread 0 combines the 128 run summaries, every thread replays its
+ * run from its true start. */
 #define E1_SERIAL_THREADS 128
-#define E1_SERIAL_CHUNK 256
+#define E1_SERIAL_CHUNK 128
+
+__device__ __forceinline__ double e1_fold1(double v) /* into (-1,1), sign kept (like :532) */
+{
+    if (v >= 1.0 || v <= -1.0)
+        v -= (double)(long long)v;
+    return v;
+}
+__device__ __forceinline__ double e1_fold_half(double v) /* into (-1/2, 1/2] */
+{
+    v -= (double)(long long)v;
+    if (v > 0.5)
+        v -= 1.0;
+    else if (v <= -0.5)
+        v += 1.0;
+    return v;
+}
 
 __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_ideal_kernel(const e1_plan_args P)
 {
-    __shared__ e1_prep s_prep[E1_SERIAL_CHUNK];
-    __shared__ double s_g[E1_SERIAL_CHUNK];
+    __shared__ double s_val[E1_SERIAL_THREADS], s_start[E1_SERIAL_THREADS];
+    __shared__ int s_abs[E1_SERIAL_THREADS];
     const int ch = blockIdx.x, tid = threadIdx.x;
     if (ch >= P.max_chan)
         return;
-    const size_t o = (size_t)ch * P.n_epochs;
-    double g = P.phase[ch];
-    for (int e0 = 0; e0 < P.n_epochs; e0 += E1_SERIAL_CHUNK) {
-        const int n = min(E1_SERIAL_CHUNK, P.n_epochs - e0);
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
-            s_prep[i] = P.prep[o + e0 + i];
-        __syncthreads();
-        if (tid == 0)
-            for (int i = 0; i < n; i++) { /* e1_v2_ideal_prefix, one chunk */
-                const uint32_t f = s_prep[i].flags;
-                if (f & E1_PREP_SET_PHASE)
-                    g = s_prep[i].init;
-                s_g[i] = g;
-                if (f & E1_PREP_ACTIVE)
-                    g = e1_ideal_next(g, s_prep[i].sp, P.n_samp);
-            }
-        __syncthreads();
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
-            P.g[o + e0 + i] = s_g[i];
+    const size_t o = (size_t)ch * P.n_units;
+    const int L = (P.n_units + E1_SERIAL_THREADS - 1) / E1_SERIAL_THREADS;
+    const int u0 = min(tid * L, P.n_units), u1 = min(u0 + L, P.n_units);
+    double g = 0.0;
+    int abs = 0;
+    for (int u = u0; u < u1; u++) { /* this run from a zero start: displacement, or absolute value after a reset */
+        const e1_prep p = P.prep[o + u];
+        if (p.flags & E1_PREP_SET_PHASE) {
+            g = p.init;
+            abs = 1;
+        }
+        if (p.flags & E1_PREP_ACTIVE)
+            g = e1_ideal_next(g, p.sp, p.n);
+    }
+    s_val[tid] = g;
+    s_abs[tid] = abs;
+    __syncthreads();
+    if (tid == 0) {
+        double cur = P.phase[ch];
+        for (int t = 0; t < E1_SERIAL_THREADS; t++) {
+            s_start[t] = cur;
+            cur = s_abs[t] ? s_val[t] : e1_fold1(cur + s_val[t]);
+        }
+    }
+    __syncthreads();
+    g = s_start[tid];
+    for (int u = u0; u < u1; u++) { /* e1_v2_ideal_prefix from the run's true start */
+        const e1_prep p = P.prep[o + u];
+        if (p.flags & E1_PREP_SET_PHASE)
+            g = p.init;
+        P.g[o + u] = g;
+        if (p.flags & E1_PREP_ACTIVE)
+            g = e1_ideal_next(g, p.sp, p.n);
     }
 }
 
 __global__ void e1_v2_drift_kernel(const e1_plan_args P)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x; /* channel-major: a warp walks one channel's epochs */
-    if (i >= P.n_epochs * P.max_chan)
+    int i = blockIdx.x * blockDim.x + threadIdx.x; /* channel-major: a warp walks one channel's spans */
+    if (i >= P.n_units * P.max_chan)
         return;
-    P.dend[i] = e1_v2_drift_unit(&P.prep[i], P.g[i], P.n_samp);
+    P.dend[i] = e1_v2_drift_unit(&P.prep[i], P.g[i]);
 }
 
+/* e1_v2_estimate_prefix as a scan: est[u] = g[u] + eta[u] with eta[u+1] = eta[u] + (dend[u] - g[u+1])
+ * (the span's measured rounding drift), eta = 0 at the batch start and at every phase reset. */
 __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_estimate_kernel(const e1_plan_args P)
 {
-    __shared__ e1_prep s_prep[E1_SERIAL_CHUNK];
-    __shared__ double s_g[E1_SERIAL_CHUNK], s_end[E1_SERIAL_CHUNK], s_est[E1_SERIAL_CHUNK];
+    __shared__ double s_val[E1_SERIAL_THREADS], s_start[E1_SERIAL_THREADS];
+    __shared__ int s_abs[E1_SERIAL_THREADS];
     const int ch = blockIdx.x, tid = threadIdx.x;
     if (ch >= P.max_chan)
         return;
-    const size_t o = (size_t)ch * P.n_epochs;
-    double cur = P.phase[ch];
-    for (int e0 = 0; e0 < P.n_epochs; e0 += E1_SERIAL_CHUNK) {
-        const int n = min(E1_SERIAL_CHUNK, P.n_epochs - e0);
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS) {
-            s_prep[i] = P.prep[o + e0 + i];
-            s_g[i] = P.g[o + e0 + i];
-            s_end[i] = P.dend[o + e0 + i];
+    const size_t o = (size_t)ch * P.n_units;
+    const int L = (P.n_units + E1_SERIAL_THREADS - 1) / E1_SERIAL_THREADS;
+    const int u0 = min(tid * L, P.n_units), u1 = min(u0 + L, P.n_units);
+    /* eta at the START of unit u1 given eta = 0 at the start of unit u0 */
+    double eta = 0.0;
+    int abs = 0;
+    for (int u = u0; u < u1; u++) {
+        if (P.prep[o + u].flags & E1_PREP_SET_PHASE) {
+            eta = 0.0;
+            abs = 1;
         }
-        __syncthreads();
-        if (tid == 0) /* e1_v2_estimate_prefix continues from `cur` */
-            cur = e1_v2_estimate_prefix(s_prep, n, cur, s_g, s_end, s_est);
-        __syncthreads();
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
-            P.est[o + e0 + i] = s_est[i];
+        if (u + 1 < P.n_units)
+            eta += e1_fold_half(P.dend[o + u] - P.g[o + u + 1]);
+    }
+    s_val[tid] = eta;
+    s_abs[tid] = abs;
+    __syncthreads();
+    if (tid == 0) {
+        double cur = 0.0;
+        for (int t = 0; t < E1_SERIAL_THREADS; t++) {
+            s_start[t] = cur;
+            cur = s_abs[t] ? s_val[t] : cur + s_val[t];
+        }
+    }
+    __syncthreads();
+    eta = s_start[tid];
+    for (int u = u0; u < u1; u++) {
+        if (P.prep[o + u].flags & E1_PREP_SET_PHASE)
+            eta = 0.0;
+        P.est[o + u] = e1_fold1(P.g[o + u] + eta);
+        if (u + 1 < P.n_units)
+            eta += e1_fold_half(P.dend[o + u] - P.g[o + u + 1]);
     }
 }
 
 __global__ void e1_v2_span_kernel(const e1_plan_args P)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_epochs * P.max_chan)
+    if (i >= P.n_units * P.max_chan)
         return;
-    int ch = i / P.n_epochs, e = i - ch * P.n_epochs;
-    e1_v2_span_unit(&P.prep[i], e ? &P.prep[i - 1] : nullptr, e, P.phase[ch], e ? P.est[i - 1] : 0.0, P.n_samp, P.tile,
-                    P.tiles_per_epoch, P.ck + (size_t)e * P.tiles_per_epoch * P.max_chan + ch, P.max_chan, &P.units[i]);
+    int ch = i / P.n_units, u = i - ch * P.n_units;
+    e1_v2_span_unit(&P.prep[i], u ? &P.prep[i - 1] : nullptr, u, P.phase[ch], u ? P.est[i - 1] : 0.0, P.tile, e1_unit_ck(P, u, ch),
+                    P.max_chan, &P.units[i]);
 }
 
+/* Chain.  Exact, and serial in principle: the translation of span u is
+ *     D[u] = (true post-wrap value at its anchor) - (guessed one)
+ *          = (last_p[u-1] + D[u-1]) - anchor_p[u]
+ * where last_p / anchor_p are the span pass's hat values -- all multiples of 2^-52 below 1, so the sums
+ * are exact in any order.  A chunk of 128 consecutive spans is therefore first tried as a parallel
+ * inclusive scan of x[u] = last_p[u-1] - anchor_p[u] (x[first] uses the carried state); if every span
+ * of the chunk is an ordinary accepted guess (HAT unit, anchored on its predecessor's last wrap, no
+ * tie wrap, lo <= D < hi) the chunk is done; otherwise thread 0 walks that chunk with
+ * e1_v2_chain_step exactly as the serial chain would. */
 __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1_plan_args P)
 {
     __shared__ __align__(16) e1_unit s_units[E1_SERIAL_CHUNK];
     __shared__ double s_sp[E1_SERIAL_CHUNK];
+    __shared__ int s_n[E1_SERIAL_CHUNK];
     __shared__ e1_trans s_delta[E1_SERIAL_CHUNK];
-    const int ch = blockIdx.x, tid = threadIdx.x;
+    __shared__ double s_warp[E1_SERIAL_THREADS / 32];
+    __shared__ e1_chain_state s_cs;
+    __shared__ int s_bad;
+    const int ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (ch >= P.max_chan)
         return;
-    const size_t o = (size_t)ch * P.n_epochs;
-    const size_t ck_epoch_stride = (size_t)P.tiles_per_epoch * P.max_chan;
+    const size_t o = (size_t)ch * P.n_units;
     unsigned long long st[2] = {0, 0};
-    e1_chain_state cs;
-    e1_chain_init(&cs, P.phase[ch]);
-    for (int e0 = 0; e0 < P.n_epochs; e0 += E1_SERIAL_CHUNK) {
-        const int n = min(E1_SERIAL_CHUNK, P.n_epochs - e0);
+    if (tid == 0)
+        e1_chain_init(&s_cs, P.phase[ch]);
+    for (int e0 = 0; e0 < P.n_units; e0 += E1_SERIAL_CHUNK) {
+        const int n = min(E1_SERIAL_CHUNK, P.n_units - e0);
         const uint4 *src = reinterpret_cast<const uint4 *>(P.units + o + e0);
         uint4 *dst = reinterpret_cast<uint4 *>(s_units);
         for (int i = tid; i < n * (int)(sizeof(e1_unit) / 16); i += E1_SERIAL_THREADS)
             dst[i] = src[i];
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
+        for (int i = tid; i < n; i += E1_SERIAL_THREADS) {
             s_sp[i] = P.prep[o + e0 + i].sp;
-        __syncthreads();
+            s_n[i] = P.prep[o + e0 + i].n;
+        }
         if (tid == 0)
+            s_bad = 0;
+        __syncthreads();
+        /* optimistic pass: thread t owns span e0 + t */
+        double x = 0.0;
+        int ok = 1;
+        if (tid < n) {
+            const e1_unit *u = &s_units[tid];
+            int p_ok, p_neg, p_k;
+            double p_last;
+            if (tid == 0) {
+                p_ok = s_cs.prev_ok, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_last = s_cs.prev_p;
+            } else {
+                const e1_unit *q = &s_units[tid - 1];
+                p_ok = q->last_k >= 1, p_neg = q->neg, p_k = q->last_k, p_last = q->last_p;
+            }
+            ok = u->type == E1_UNIT_HAT && u->tie_k < 0 && p_ok && p_neg == u->neg && p_k == u->anchor_k;
+            x = ok ? __dadd_rn(p_last, -u->anchor_p) : 0.0;
+        }
+        /* inclusive scan of x over the block (exact additions) */
+        double D = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, D, d);
+            if (lane >= d)
+                D = __dadd_rn(D, y);
+        }
+        if (lane == 31)
+            s_warp[wid] = D;
+        __syncthreads();
+        for (int w = 0; w < wid; w++)
+            D = __dadd_rn(D, s_warp[w]);
+        if (tid < n) {
+            const e1_unit *u = &s_units[tid];
+            if (!(ok && D >= u->lo && D < u->hi))
+                atomicExch(&s_bad, 1);
+        }
+        __syncthreads();
+        if (!s_bad) {
+            if (tid < n) {
+                const e1_unit *u = &s_units[tid];
+                e1_trans tr;
+                tr.a = tr.b = u->neg ? -D : D;
+                tr.k_split = 0;
+                tr.pad = 0;
+                s_delta[tid] = tr;
+                if (tid == n - 1) { /* the state the serial chain would carry out of this chunk */
+                    s_cs.phi = __dadd_rn(u->end_phi, tr.b);
+                    s_cs.prev_p = __dadd_rn(u->last_p, D);
+                    s_cs.prev_k = u->last_k;
+                    s_cs.prev_ok = u->last_k >= 1;
+                    s_cs.prev_neg = u->neg;
+                }
+            }
+            if (tid == 0)
+                st[1] += (unsigned long long)n;
+        } else if (tid == 0) {
+            e1_chain_state cs = s_cs;
             for (int i = 0; i < n; i++)
-                s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], s_sp[i], P.n_samp, P.tile, P.tiles_per_epoch,
-                                              P.ck + (size_t)(e0 + i) * ck_epoch_stride + ch, P.max_chan, st);
+                s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], s_sp[i], s_n[i], P.tile, (s_n[i] + P.tile - 1) / P.tile,
+                                              e1_unit_ck(P, e0 + i, ch), P.max_chan, st);
+            s_cs = cs;
+        }
         __syncthreads();
         for (int i = tid; i < n; i += E1_SERIAL_THREADS)
             P.delta[o + e0 + i] = s_delta[i];
     }
     if (tid == 0) {
-        P.phase[ch] = cs.phi;
+        P.phase[ch] = s_cs.phi;
         if (st[0])
             atomicAdd(&P.counters[2], st[0]);
         if (st[1])
@@ -285,9 +421,11 @@ __global__ void __launch_bounds__(128) e1_finalize_kernel(const e1_finalize_args
         const unsigned m = __ballot_sync(0xffffffffu, active);
         if (active) {
             e1_chan_par p;
-            const int t = (int)(tile_id - (long)e * A.tiles_per_epoch);
+            const int t = (int)(tile_id - (long)e * A.tiles_per_epoch), sp = t / A.geo.span_tiles;
             e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + ch], A.delt, A.tile,
-                        e1_trans_at(&A.delta[(size_t)ch * A.delta_stride + e], t * A.tile), A.tc_code, &p);
+                        e1_trans_at(&A.delta[(size_t)ch * A.delta_stride + (size_t)e * A.geo.spans_per_epoch + sp],
+                                    (t - sp * A.geo.span_tiles) * A.tile),
+                        A.tc_code, &p);
             if (c.sym & E1_CK_ERROR)
                 errs++;
             par[base + __popc(m & ((1u << lane) - 1u))] = p;

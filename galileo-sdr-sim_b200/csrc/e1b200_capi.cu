@@ -43,7 +43,8 @@ struct e1b200_ctx {
     double *d_g, *d_dend, *d_est;
     e1_trans *d_delta;
     e1_prep *d_prep;
-    int plan_n;               /* epochs in the current plan (stride of the channel-major arrays) */
+    int plan_n;               /* spans in the current plan (stride of the channel-major arrays) */
+    e1_span_geo geo;          /* how an epoch is cut into planner spans */
     e1_unit *d_units;
     e1_epoch_rec *d_recs;     /* staging for the host entry points / restate output */
     e1_range_rec *d_ranges;
@@ -153,6 +154,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->run = run;
     ctx->tile = run * E1_SYNTH_THREADS;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
+    ctx->geo = e1_span_geometry(ctx->tiles_per_epoch);
     ctx->use_bulk = env_int("E1B200_NO_TMA", 0) ? 0 : 1;
     ctx->amb_scale = env_int("E1B200_AMB_SCALE", 1);
     if (ctx->amb_scale < 1)
@@ -275,8 +277,9 @@ static int ensure_plan_scratch(e1b200_ctx *ctx)
 {
     if (ctx->d_ck)
         return E1B200_OK;
-    const size_t ne = (size_t)ctx->plan_epochs * ctx->cfg.max_chan;
-    CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * ne * ctx->tiles_per_epoch));
+    const size_t nec = (size_t)ctx->plan_epochs * ctx->cfg.max_chan;
+    const size_t ne = nec * ctx->geo.spans_per_epoch; /* planner units */
+    CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * nec * ctx->tiles_per_epoch));
     CK(cudaMalloc(&ctx->d_blk, e1_blk_bytes(ctx->cfg.max_chan) * (size_t)ctx->plan_epochs * ctx->tiles_per_epoch));
     CK(cudaMalloc(&ctx->d_delta, sizeof(e1_trans) * ne));
     CK(cudaMemset(ctx->d_delta, 0, sizeof(e1_trans) * ne));
@@ -318,7 +321,8 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
     if (rc)
         return rc;
     const int nthr = n * cfg->max_chan;
-    ctx->plan_n = n;
+    const int n_units = n * ctx->geo.spans_per_epoch, nuthr = n_units * cfg->max_chan;
+    ctx->plan_n = n_units;
     if (!carrier_only)
         e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
                                                                          ctx->tile, ctx->tiles_per_epoch, ctx->delt);
@@ -328,7 +332,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
                                                                              ctx->tiles_per_epoch, ctx->delt);
         ctx->timing.kernel_launches += 2;
         /* the serial planner writes final checkpoints: translations are zero */
-        CK(cudaMemsetAsync(ctx->d_delta, 0, sizeof(e1_trans) * (size_t)nthr, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_delta, 0, sizeof(e1_trans) * (size_t)nuthr, ctx->stream));
     } else {
         e1_plan_args P;
         P.recs = d_recs;
@@ -347,12 +351,14 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         P.max_chan = cfg->max_chan;
         P.tile = ctx->tile;
         P.tiles_per_epoch = ctx->tiles_per_epoch;
+        P.geo = ctx->geo;
+        P.n_units = n_units;
         const int cb = cfg->max_chan; /* one channel per block */
         e1_v2_prep_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(P);
         e1_v2_ideal_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
-        e1_v2_drift_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
+        e1_v2_drift_kernel<<<(nuthr + 63) / 64, 64, 0, ctx->stream>>>(P);
         e1_v2_estimate_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
-        e1_v2_span_kernel<<<(nthr + 63) / 64, 64, 0, ctx->stream>>>(P);
+        e1_v2_span_kernel<<<(nuthr + 63) / 64, 64, 0, ctx->stream>>>(P);
         e1_v2_chain_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         ctx->timing.kernel_launches += 7;
     }
@@ -361,7 +367,8 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         F.recs = d_recs;
         F.ck = ctx->d_ck;
         F.delta = ctx->d_delta;
-        F.delta_stride = n;
+        F.delta_stride = n_units;
+        F.geo = ctx->geo;
         F.blk = ctx->d_blk;
         F.counters = ctx->d_counters;
         F.delt = ctx->delt;

@@ -93,7 +93,10 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
         for (int ch = 0; ch < max_chan; ch++)
             e1_plan_code_epoch(&recs[(size_t)e * max_chan + ch], &ck[(size_t)e * tpe * max_chan + ch], max_chan, n_samp, tile,
                                tpe, delt);
-    std::vector<e1_trans> delta((size_t)n_epochs * max_chan, e1_trans{0.0, 0.0, 0, 0});
+    // planner units: spans of span_tiles tiles (e1_span_geometry), channel-major [max_chan][n_units]
+    const e1_span_geo geo = e1_span_geometry(tpe);
+    const int S = geo.spans_per_epoch, n_units = n_epochs * S;
+    std::vector<e1_trans> delta((size_t)n_units * max_chan, e1_trans{0.0, 0.0, 0, 0}); // [ch][unit]
     stats[3] = stats[4] = 0;
     if (planner == 1) {
         for (int ch = 0; ch < max_chan; ch++) {
@@ -103,41 +106,38 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                                          n_samp, tile, tpe, delt);
             phase[ch] = phi;
         }
-    } else if (n_epochs > 0) {
-        /* channel-major planner arrays, passes in kernel order */
-        const size_t ne = (size_t)n_epochs * max_chan;
-        std::vector<double> g(ne), dend(ne), est(ne);
-        std::vector<e1_trans> dcm(ne, e1_trans{0.0, 0.0, 0, 0});
-        std::vector<e1_unit> units(ne);
+    } else {
+        const size_t ne = (size_t)n_units * max_chan;
         std::vector<e1_prep> prep(ne);
+        std::vector<double> g(ne), dend(ne), est(ne);
+        std::vector<e1_unit> units(ne);
         for (int e = 0; e < n_epochs; e++)
             for (int ch = 0; ch < max_chan; ch++)
-                e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, &prep[(size_t)ch * n_epochs + e]);
+                for (int sp = 0; sp < S; sp++)
+                    e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, sp, e1_span_samples(&geo, sp, n_samp, tile),
+                               &prep[(size_t)ch * n_units + (size_t)e * S + sp]);
         for (int ch = 0; ch < max_chan; ch++)
-            e1_v2_ideal_prefix(&prep[(size_t)ch * n_epochs], n_epochs, phase[ch], n_samp, &g[(size_t)ch * n_epochs]);
+            e1_v2_ideal_prefix(&prep[(size_t)ch * n_units], n_units, phase[ch], &g[(size_t)ch * n_units]);
         for (size_t i = 0; i < ne; i++)
-            dend[i] = e1_v2_drift_unit(&prep[i], g[i], n_samp);
+            dend[i] = e1_v2_drift_unit(&prep[i], g[i]);
         for (int ch = 0; ch < max_chan; ch++) {
-            const size_t o = (size_t)ch * n_epochs;
-            e1_v2_estimate_prefix(&prep[o], n_epochs, phase[ch], &g[o], &dend[o], &est[o]);
+            const size_t o = (size_t)ch * n_units;
+            e1_v2_estimate_prefix(&prep[o], n_units, phase[ch], &g[o], &dend[o], &est[o]);
         }
         for (int ch = 0; ch < max_chan; ch++)
-            for (int e = 0; e < n_epochs; e++) {
-                const size_t i = (size_t)ch * n_epochs + e;
-                e1_v2_span_unit(&prep[i], e ? &prep[i - 1] : nullptr, e, phase[ch], e ? est[i - 1] : 0.0, n_samp, tile, tpe,
-                                &ck[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
+            for (int u = 0; u < n_units; u++) {
+                const size_t i = (size_t)ch * n_units + u;
+                const int e = u / S, sp = u - e * S;
+                e1_v2_span_unit(&prep[i], u ? &prep[i - 1] : nullptr, u, phase[ch], u ? est[i - 1] : 0.0, tile,
+                                &ck[((size_t)e * tpe + (size_t)sp * geo.span_tiles) * max_chan + ch], max_chan, &units[i]);
             }
         for (int ch = 0; ch < max_chan; ch++) {
             unsigned long long st2[2] = {0, 0};
-            const size_t o = (size_t)ch * n_epochs;
-            phase[ch] = e1_v2_chain(&prep[o], n_epochs, phase[ch], n_samp, tile, tpe, &units[o], &ck[ch], max_chan,
-                                    (size_t)tpe * max_chan, &dcm[o], st2);
+            const size_t o = (size_t)ch * n_units;
+            phase[ch] = e1_v2_chain(&prep[o], n_units, phase[ch], tile, &units[o], &ck[ch], max_chan, &delta[o], st2);
             stats[3] += st2[0];
             stats[4] += st2[1];
         }
-        for (int ch = 0; ch < max_chan; ch++)
-            for (int e = 0; e < n_epochs; e++)
-                delta[(size_t)e * max_chan + ch] = dcm[(size_t)ch * n_epochs + e];
     }
     const uint32_t thr_carr = e1_thr_carr(tile, amb_scale), thr_code = e1_thr_code(tile, amb_scale);
     const uint32_t tc_carr = e1_tc_carr(thr_carr, run), tc_code = e1_tc_code(thr_code, run);
@@ -153,7 +153,9 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                     continue;
                 if (c->sym & E1_CK_ERROR)
                     stats[1]++;
-                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile, e1_trans_at(&delta[(size_t)e * max_chan + ch], t * tile), tc_code,
+                const int sp = t / geo.span_tiles;
+                e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile,
+                            e1_trans_at(&delta[(size_t)ch * n_units + (size_t)e * S + sp], (t - sp * geo.span_tiles) * tile), tc_code,
                             &par[nact++]);
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
@@ -204,8 +206,11 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
     const double delt = 1.0 / fs_hz;
     const int tile = groups * 4 * E1C_THREADS;
     const int tpe = (n_samp + tile - 1) / tile;
-    const size_t ne = (size_t)n_epochs * max_chan;
-    std::vector<e1_tile_ck> ck1(ne * tpe), ck2(ne * tpe);
+    const size_t nec = (size_t)n_epochs * max_chan;
+    const e1_span_geo geo = e1_span_geometry(tpe);
+    const int S = geo.spans_per_epoch, n_units = n_epochs * S;
+    const size_t ne = (size_t)n_units * max_chan;
+    std::vector<e1_tile_ck> ck1(nec * tpe), ck2(nec * tpe);
     memset(ck1.data(), 0, ck1.size() * sizeof(e1_tile_ck));
     memset(ck2.data(), 0, ck2.size() * sizeof(e1_tile_ck));
     std::vector<double> g(ne), dend(ne), est(ne), p1(max_chan), p2(max_chan);
@@ -220,42 +225,41 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
         p1[ch] = phi;
     }
     std::vector<e1_prep> prep(ne);
-    std::vector<e1_trans> dcm(ne, e1_trans{0.0, 0.0, 0, 0});
     for (int e = 0; e < n_epochs; e++)
         for (int ch = 0; ch < max_chan; ch++)
-            e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, &prep[(size_t)ch * n_epochs + e]);
+            for (int sp = 0; sp < S; sp++)
+                e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, sp, e1_span_samples(&geo, sp, n_samp, tile),
+                           &prep[(size_t)ch * n_units + (size_t)e * S + sp]);
     for (int ch = 0; ch < max_chan; ch++)
-        e1_v2_ideal_prefix(&prep[(size_t)ch * n_epochs], n_epochs, phase0[ch], n_samp, &g[(size_t)ch * n_epochs]);
+        e1_v2_ideal_prefix(&prep[(size_t)ch * n_units], n_units, phase0[ch], &g[(size_t)ch * n_units]);
     for (size_t i = 0; i < ne; i++)
-        dend[i] = e1_v2_drift_unit(&prep[i], g[i], n_samp);
+        dend[i] = e1_v2_drift_unit(&prep[i], g[i]);
     for (int ch = 0; ch < max_chan; ch++) {
-        const size_t o = (size_t)ch * n_epochs;
-        e1_v2_estimate_prefix(&prep[o], n_epochs, phase0[ch], &g[o], &dend[o], &est[o]);
+        const size_t o = (size_t)ch * n_units;
+        e1_v2_estimate_prefix(&prep[o], n_units, phase0[ch], &g[o], &dend[o], &est[o]);
     }
     for (int ch = 0; ch < max_chan; ch++)
-        for (int e = 0; e < n_epochs; e++) {
-            const size_t i = (size_t)ch * n_epochs + e;
-            e1_v2_span_unit(&prep[i], e ? &prep[i - 1] : nullptr, e, phase0[ch], e ? est[i - 1] : 0.0, n_samp, tile, tpe,
-                            &ck2[(size_t)e * tpe * max_chan + ch], max_chan, &units[i]);
+        for (int u = 0; u < n_units; u++) {
+            const size_t i = (size_t)ch * n_units + u;
+            const int e = u / S, sp = u - e * S;
+            e1_v2_span_unit(&prep[i], u ? &prep[i - 1] : nullptr, u, phase0[ch], u ? est[i - 1] : 0.0, tile,
+                            &ck2[((size_t)e * tpe + (size_t)sp * geo.span_tiles) * max_chan + ch], max_chan, &units[i]);
         }
     for (int ch = 0; ch < max_chan; ch++) {
-        const size_t o = (size_t)ch * n_epochs;
-        p2[ch] = e1_v2_chain(&prep[o], n_epochs, phase0[ch], n_samp, tile, tpe, &units[o], &ck2[ch], max_chan,
-                             (size_t)tpe * max_chan, &dcm[o], stats);
+        const size_t o = (size_t)ch * n_units;
+        p2[ch] = e1_v2_chain(&prep[o], n_units, phase0[ch], tile, &units[o], &ck2[ch], max_chan, &delta[o], stats);
     }
-    for (int ch = 0; ch < max_chan; ch++)
-        for (int e = 0; e < n_epochs; e++)
-            delta[(size_t)e * max_chan + ch] = dcm[(size_t)ch * n_epochs + e];
     long bad = 0;
     for (int e = 0; e < n_epochs; e++)
         for (int ch = 0; ch < max_chan; ch++) {
             const size_t i = (size_t)e * max_chan + ch;
             if (!e1_rec_active(&recs[i]))
                 continue;
-            stats[2]++;
+            stats[2] += S;
             for (int t = 0; t < tpe; t++) {
                 const size_t j = ((size_t)e * tpe + t) * max_chan + ch;
-                const double v = e1_add(ck2[j].phi, e1_trans_at(&delta[i], t * tile));
+                const int sp = t / geo.span_tiles;
+                const double v = e1_add(ck2[j].phi, e1_trans_at(&delta[(size_t)ch * n_units + (size_t)e * S + sp], (t - sp * geo.span_tiles) * tile));
                 if (e1_bits(ck1[j].phi) != e1_bits(v) && !(ck1[j].phi == 0.0 && v == 0.0))
                     bad++;
             }
