@@ -499,13 +499,17 @@ typedef struct e1_unit { /* one per (span, channel), 64 bytes */
     double end_phi;   /* signed phase after the epoch's last sample (hat for HAT units)         */
     double last_p;    /* |phase| right after the last wrap inside this epoch (hat for HAT)      */
     double lo, hi;    /* HAT: valid translations, lo <= D < hi                                  */
-    int32_t anchor_k; /* HAT: sample index (1..N) of the anchor wrap inside the previous epoch  */
-    int32_t last_k;   /* sample index (1..N) of the last wrap inside this epoch, -1 if none     */
+    int32_t anchor_k; /* HAT: sample index (1..N) of the anchor wrap inside its span            */
+    int32_t last_k;   /* sample index (1..N) of the last wrap inside this span; -1: none, the walk stayed
+                         in the aligned regime (an earlier wrap can still serve as anchor); -2: none and
+                         the walk was not aligned throughout                                       */
     int32_t type;
     int32_t neg;      /* sign of the walk (1: phase <= 0)                                       */
-    int32_t tie_k;    /* HAT: sample index (1..N) of the first tie wrap inside this epoch, -1 if none */
-    int32_t tie_dir;  /* HAT: +1 the guess rounded down there, -1 it rounded up                    */
+    int32_t tie;         /* HAT: +-k, k = sample index (1..N) of the first tie wrap inside this span; + the
+                            guess rounded down there, - it rounded up; 0: no tie wrap               */
+    int32_t anchor_back; /* HAT: the anchor wrap lies in the span this many units before this one (>= 1) */
 } e1_unit;
+#define E1_MAX_BACK 64 /* how far back the span pass looks for a wrap to anchor on */
 
 /* Translation of one (channel, epoch): its carrier checkpoints are ck.phi + a for tile starts before
  * sample k_split and ck.phi + b from there on (k_split = 0 and a = b unless a tie wrap split it). */
@@ -624,7 +628,7 @@ E1_HD double e1_carr_epoch_exact(double phi, double sp, int n_samp, int tile, in
 {
     const int neg = (phi < 0.0) || (phi == 0.0 && sp < 0.0);
     const int aligned = (phi == 0.0) || (neg == (sp < 0.0));
-    *last_k = -1;
+    *last_k = -2;
     *last_p = 0.0;
     *neg_out = neg;
     if (sp == 0.0 || !aligned) {
@@ -735,8 +739,12 @@ E1_HD double e1_v2_estimate_prefix(const e1_prep *pp, int n_epochs, double phi0,
 
 /* span pass for one (epoch, channel): p / p_prev are this channel's prep records of epoch e and
  * e-1, o its first tile checkpoint of epoch e (tile stride `stride`). */
-E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, double phi_batch_start, double est_prev,
-                           int tile, e1_tile_ck *o, int stride, e1_unit *u)
+/* span pass for one (span, channel): pr = &prep[u] and est = &est[u] of this channel (earlier spans of
+ * the batch at negative offsets), o its first tile checkpoint (tile stride `stride`).  The anchor is the
+ * last wrap before this span according to the estimates -- normally inside the span just before, at
+ * low Doppler up to E1_MAX_BACK spans back. */
+E1_HD void e1_v2_span_unit(const e1_prep *pr, int e, double phi_batch_start, const double *est, int tile, e1_tile_ck *o,
+                           int stride, e1_unit *u)
 {
     const int n_samp = pr->n, tiles_per_epoch = (pr->n + tile - 1) / tile; /* of this span */
     u->type = E1_UNIT_NONE;
@@ -748,8 +756,8 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     u->lo = 0.0;
     u->hi = 0.0;
     u->neg = 0;
-    u->tie_k = -1;
-    u->tie_dir = 0;
+    u->tie = 0;
+    u->anchor_back = 0;
     if (!(pr->flags & E1_PREP_ACTIVE))
         return;
     const double sp = pr->sp;
@@ -760,47 +768,55 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
         return;
     }
     u->type = E1_UNIT_SERIAL;
-    if (!(pr_prev->flags & E1_PREP_ACTIVE))
-        return;
-    const double sp0 = pr_prev->sp;
-    if (sp == 0.0 || sp0 == 0.0 || (sp < 0.0) != (sp0 < 0.0))
-        return;
-    if (!(e1_fabs(sp) < 0.5) || !(e1_fabs(sp0) < 0.5))
+    if (sp == 0.0 || !(e1_fabs(sp) < 0.5))
         return;
     const int neg = sp < 0.0;
-    /* start of the previous epoch measured along the direction of motion: negative when that epoch
-       started in the mixed regime (phase and Doppler of opposite sign) and first ran down to zero */
-    const double t0 = e1_fabs(sp0), t1 = e1_fabs(sp);
-    const double a0 = (est_prev == 0.0 || (est_prev < 0.0) == neg) ? e1_fabs(est_prev) : -e1_fabs(est_prev);
-    if (!(a0 < 1.0) || !(a0 > -1.0))
-        return;
-    /* last wrap of the previous epoch according to the estimate: unwrapped phase a0 + k*t0 */
-    const int n_prev = pr_prev->n;
-    const double total = a0 + (double)n_prev * t0;
-    const double W = (double)(long long)total;
-    if (W < 1.0)
-        return; /* no wrap to anchor on */
-    double kd = (W - a0) / t0;
-    int64_t kL = (int64_t)kd;
-    if ((double)kL < kd)
-        kL++;
-    double p = 0.0;
-    for (int tries = 0; tries < 3; tries++) { /* p = a0 + kL*t0 - W in double-double, want 0 <= p < t0 */
+    const double t1 = e1_fabs(sp);
+    /* find the span with the last wrap: unwrapped phase a0 + k*t0 along the direction of motion, a0 < 0
+       when that span started in the mixed regime (phase and Doppler of opposite sign) */
+    int back = 0;
+    double p = 0.0, t0 = 0.0;
+    int64_t kL = 0;
+    for (int b = 1; b <= E1_MAX_BACK && b <= e; b++) {
+        const e1_prep *q = pr - b;
+        if (!(q->flags & E1_PREP_ACTIVE) || q->sp == 0.0 || (q->sp < 0.0) != neg || !(e1_fabs(q->sp) < 0.5))
+            return;
+        const double eq = est[-b], tq = e1_fabs(q->sp);
+        const double a0 = (eq == 0.0 || (eq < 0.0) == neg) ? e1_fabs(eq) : -e1_fabs(eq);
+        if (!(a0 < 1.0) || !(a0 > -1.0))
+            return;
+        const double total = a0 + (double)q->n * tq;
+        const double W = (double)(long long)total;
+        if (W >= 1.0) {
+            double kd = (W - a0) / tq;
+            kL = (int64_t)kd;
+            if ((double)kL < kd)
+                kL++;
+            for (int tries = 0; tries < 3; tries++) { /* p = a0 + kL*tq - W in double-double, want 0 <= p < tq */
 #if defined(__CUDA_ARCH__)
-        const double hi_ = __dmul_rn((double)kL, t0), lo_ = __fma_rn((double)kL, t0, -hi_);
+                const double hi_ = __dmul_rn((double)kL, tq), lo_ = __fma_rn((double)kL, tq, -hi_);
 #else
-        const double hi_ = (double)kL * t0, lo_ = __builtin_fma((double)kL, t0, -hi_);
+                const double hi_ = (double)kL * tq, lo_ = __builtin_fma((double)kL, tq, -hi_);
 #endif
-        p = ((hi_ - W) + a0) + lo_;
-        if (p < 0.0)
-            kL++;
-        else if (p >= t0)
-            kL--;
-        else
+                p = ((hi_ - W) + a0) + lo_;
+                if (p < 0.0)
+                    kL++;
+                else if (p >= tq)
+                    kL--;
+                else
+                    break;
+            }
+            if (!(p >= 0.0) || !(p < tq) || kL < 1 || kL > q->n)
+                return;
+            back = b;
+            t0 = tq;
             break;
+        }
+        if (q->flags & E1_PREP_SET_PHASE)
+            return; /* the trajectory starts at q: nothing earlier to anchor on */
     }
-    if (!(p >= 0.0) || !(p < t0) || kL < 1 || kL > n_prev)
-        return;
+    if (!back)
+        return; /* no wrap within reach */
     /* round the guess to the post-wrap grid */
     const double two52 = 4503599627370496.0;
     p = (double)(long long)(p * two52 + 0.5) / two52;
@@ -811,23 +827,25 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
     tr.last_p = 0.0;
     tr.tie_k = 0;
     tr.tie_dir = 0;
-    double a = e1_span_walk(p, t0, kL, n_prev, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
+    double a = e1_span_walk(p, t0, kL, (pr - back)->n, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
+    for (int b = back - 1; b >= 1 && tr.last_k == -1; b--) /* the spans in between: no wrap expected */
+        a = e1_span_walk(a, e1_fabs((pr - b)->sp), 0, (pr - b)->n, tile, 0, (e1_tile_ck *)0, 0, neg, &tr);
     if (tr.last_k != -1)
         return; /* the guessed anchor was not the last wrap after all */
-    tr.tie_k = -1; /* ties only matter at this epoch's own wraps */
+    tr.tie_k = -1; /* ties only matter at this span's own wraps */
     o[0].phi = neg ? -a : a;
     a = e1_span_walk(a, t1, 0, n_samp, tile, n_samp, o, stride, neg, &tr);
     u->type = E1_UNIT_HAT;
     u->neg = neg;
     u->anchor_k = (int32_t)kL;
+    u->anchor_back = back;
     u->anchor_p = p;
     u->end_phi = neg ? -a : a;
     u->last_k = (int32_t)tr.last_k;
     u->last_p = tr.last_p;
     u->lo = tr.lo;
     u->hi = tr.hi;
-    u->tie_k = (int32_t)tr.tie_k;
-    u->tie_dir = tr.tie_dir;
+    u->tie = tr.tie_k >= 0 ? (int32_t)tr.tie_k * tr.tie_dir : 0;
 }
 
 /* chain of one channel: validates HAT units, walks the others, writes the per-epoch translation
@@ -837,9 +855,10 @@ E1_HD void e1_v2_span_unit(const e1_prep *pr, const e1_prep *pr_prev, int e, dou
  * stats[0] += epochs walked serially, stats[1] += HAT units accepted. */
 typedef struct e1_chain_state {
     double phi;    /* signed phase at the first sample of the next epoch                */
-    double prev_p; /* |phase| right after the last wrap of the previous epoch           */
-    int32_t prev_k;
-    int prev_ok, prev_neg;
+    double prev_p; /* |phase| right after the most recent wrap                           */
+    int32_t prev_k; /* ... its sample index inside span prev_u                            */
+    int32_t prev_u;
+    int prev_ok, prev_neg; /* prev_ok: there is such a wrap and the walk has been aligned since */
 } e1_chain_state;
 
 E1_HD void e1_chain_init(e1_chain_state *s, double phi0)
@@ -847,13 +866,15 @@ E1_HD void e1_chain_init(e1_chain_state *s, double phi0)
     s->phi = phi0;
     s->prev_p = 0.0;
     s->prev_k = -1;
+    s->prev_u = -1;
     s->prev_ok = 0;
     s->prev_neg = 0;
 }
 
 /* u: this epoch's unit; sp: its carrier step; ck_e: this channel's first checkpoint of this epoch
  * (tiles `stride` apart), only touched when the epoch has to be walked serially. */
-E1_HD e1_trans e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, int n_samp, int tile, int tiles_per_epoch,
+/* ui: index of this span in the batch. */
+E1_HD e1_trans e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, int ui, double sp, int n_samp, int tile, int tiles_per_epoch,
                                 e1_tile_ck *ck_e, int stride, unsigned long long *stats)
 {
     const int type = u->type;
@@ -869,18 +890,19 @@ E1_HD e1_trans e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, 
     double last_p = u->last_p;
     if (type == E1_UNIT_EXACT) {
         s->phi = u->end_phi;
+        s->prev_ok = 0; /* whatever wrap came before belongs to another trajectory */
     } else {
         int ok = 0;
-        if (type == E1_UNIT_HAT && s->prev_ok && s->prev_neg == neg && s->prev_k == u->anchor_k) {
+        if (type == E1_UNIT_HAT && s->prev_ok && s->prev_neg == neg && s->prev_u == ui - u->anchor_back && s->prev_k == u->anchor_k) {
             const double D = e1_add(s->prev_p, -u->anchor_p); /* a multiple of 2^-52, |D| < 1 */
             double D2 = D;
-            if (u->tie_k >= 0 && ((long long)e1_mul(D, 4503599627370496.0) & 1LL))
-                D2 = e1_add(D, u->tie_dir > 0 ? 2.220446049250313e-16 : -2.220446049250313e-16);
+            if (u->tie != 0 && ((long long)e1_mul(D, 4503599627370496.0) & 1LL))
+                D2 = e1_add(D, u->tie > 0 ? 2.220446049250313e-16 : -2.220446049250313e-16);
             if (D >= u->lo && D < u->hi && D2 >= u->lo && D2 < u->hi) {
                 ok = 1;
                 tr.a = neg ? -D : D;
                 tr.b = neg ? -D2 : D2;
-                tr.k_split = D2 != D ? u->tie_k : 0;
+                tr.k_split = D2 != D ? (u->tie > 0 ? u->tie : -u->tie) : 0;
                 if (tr.k_split == 0)
                     tr.a = tr.b;
                 s->phi = e1_add(u->end_phi, tr.b);
@@ -893,10 +915,15 @@ E1_HD e1_trans e1_v2_chain_step(e1_chain_state *s, const e1_unit *u, double sp, 
             stats[0]++;
         }
     }
-    s->prev_ok = last_k >= 1;
-    s->prev_neg = neg;
-    s->prev_k = last_k;
-    s->prev_p = last_p;
+    if (last_k >= 1) {
+        s->prev_ok = 1;
+        s->prev_neg = neg;
+        s->prev_k = last_k;
+        s->prev_u = ui;
+        s->prev_p = last_p;
+    } else if (last_k != -1 || s->prev_neg != neg) {
+        s->prev_ok = 0; /* no wrap and not (or not in the same direction) aligned: the older wrap is no anchor any more */
+    }
     return tr;
 }
 
@@ -910,7 +937,7 @@ E1_HD double e1_v2_chain(const e1_prep *pp, int n_units, double phi0, int tile, 
     size_t tile0 = 0;
     for (int u = 0; u < n_units; u++) {
         const int tiles = (pp[u].n + tile - 1) / tile;
-        delta[u] = e1_v2_chain_step(&s, &units[u], pp[u].sp, pp[u].n, tile, tiles, ck + tile0 * (size_t)stride, stride, stats);
+        delta[u] = e1_v2_chain_step(&s, &units[u], u, pp[u].sp, pp[u].n, tile, tiles, ck + tile0 * (size_t)stride, stride, stats);
         tile0 += (size_t)tiles;
     }
     return s.phi;

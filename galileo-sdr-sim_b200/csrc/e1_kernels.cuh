@@ -282,8 +282,7 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
     if (i >= P.n_units * P.max_chan)
         return;
     int ch = i / P.n_units, u = i - ch * P.n_units;
-    e1_v2_span_unit(&P.prep[i], u ? &P.prep[i - 1] : nullptr, u, P.phase[ch], u ? P.est[i - 1] : 0.0, P.tile, e1_unit_ck(P, u, ch),
-                    P.max_chan, &P.units[i]);
+    e1_v2_span_unit(&P.prep[i], u, P.phase[ch], &P.est[i], P.tile, e1_unit_ck(P, u, ch), P.max_chan, &P.units[i]);
 }
 
 /* Chain.  Exact, and serial in principle: the translation of span u is
@@ -332,12 +331,12 @@ __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1
             int p_ok, p_neg, p_k;
             double p_last;
             if (tid == 0) {
-                p_ok = s_cs.prev_ok, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_last = s_cs.prev_p;
+                p_ok = s_cs.prev_ok && s_cs.prev_u == e0 - 1, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_last = s_cs.prev_p;
             } else {
                 const e1_unit *q = &s_units[tid - 1];
                 p_ok = q->last_k >= 1, p_neg = q->neg, p_k = q->last_k, p_last = q->last_p;
             }
-            ok = u->type == E1_UNIT_HAT && u->tie_k < 0 && p_ok && p_neg == u->neg && p_k == u->anchor_k;
+            ok = u->type == E1_UNIT_HAT && u->tie == 0 && u->anchor_back == 1 && p_ok && p_neg == u->neg && p_k == u->anchor_k;
             x = ok ? __dadd_rn(p_last, -u->anchor_p) : 0.0;
         }
         /* inclusive scan of x over the block (exact additions) */
@@ -370,7 +369,9 @@ __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1
                 if (tid == n - 1) { /* the state the serial chain would carry out of this chunk */
                     s_cs.phi = __dadd_rn(u->end_phi, tr.b);
                     s_cs.prev_p = __dadd_rn(u->last_p, D);
-                    s_cs.prev_k = u->last_k;
+                    s_cs.prev_k = u->last_k; /* >= 1: every span of an accepted chunk but the last is an anchor, and
+                                                a last span without a wrap sends the next chunk to the serial path */
+                    s_cs.prev_u = e0 + n - 1;
                     s_cs.prev_ok = u->last_k >= 1;
                     s_cs.prev_neg = u->neg;
                 }
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1
         } else if (tid == 0) {
             e1_chain_state cs = s_cs;
             for (int i = 0; i < n; i++)
-                s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], s_sp[i], s_n[i], P.tile, (s_n[i] + P.tile - 1) / P.tile,
+                s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], e0 + i, s_sp[i], s_n[i], P.tile, (s_n[i] + P.tile - 1) / P.tile,
                                               e1_unit_ck(P, e0 + i, ch), P.max_chan, st);
             s_cs = cs;
         }

@@ -128,7 +128,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
             for (int u = 0; u < n_units; u++) {
                 const size_t i = (size_t)ch * n_units + u;
                 const int e = u / S, sp = u - e * S;
-                e1_v2_span_unit(&prep[i], u ? &prep[i - 1] : nullptr, u, phase[ch], u ? est[i - 1] : 0.0, tile,
+                e1_v2_span_unit(&prep[i], u, phase[ch], &est[i], tile,
                                 &ck[((size_t)e * tpe + (size_t)sp * geo.span_tiles) * max_chan + ch], max_chan, &units[i]);
             }
         for (int ch = 0; ch < max_chan; ch++) {
@@ -242,7 +242,7 @@ long hs_plan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const
         for (int u = 0; u < n_units; u++) {
             const size_t i = (size_t)ch * n_units + u;
             const int e = u / S, sp = u - e * S;
-            e1_v2_span_unit(&prep[i], u ? &prep[i - 1] : nullptr, u, phase0[ch], u ? est[i - 1] : 0.0, tile,
+            e1_v2_span_unit(&prep[i], u, phase0[ch], &est[i], tile,
                             &ck2[((size_t)e * tpe + (size_t)sp * geo.span_tiles) * max_chan + ch], max_chan, &units[i]);
         }
     for (int ch = 0; ch < max_chan; ch++) {

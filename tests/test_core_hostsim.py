@@ -219,6 +219,27 @@ def test_parallel_planner_equals_serial_walk(fs, n_samp, n_chan, n_epochs, seed)
     assert hat > 0.95 * (active - n_chan) and serial < 0.05 * active
 
 
+def low_doppler_recs(n_epochs, fs):
+    """Dopplers that sit near zero or run through it: spans without a carrier wrap, anchors several
+    spans back, sign changes, a channel below the look-back reach."""
+    recs = U.synthetic_recs_fast(n_epochs, 8, fs, seed=3)
+    e = np.arange(n_epochs)
+    for c, (f0, rate) in enumerate([(30, -0.1), (-5, 0.02), (0.3, 0.0), (100, -0.5), (-0.7, 0.01), (12, 0.0), (-45, 0.15), (2, -0.01)]):
+        f = f0 + rate * e
+        recs[:, c]["f_carr"] = f
+        recs[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+    return recs
+
+
+def test_parallel_planner_low_doppler_anchors_further_back():
+    recs = low_doppler_recs(600, FS26)
+    bad, (serial, hat, active) = U.hostsim_plan_compare(FS26, 260000, recs)
+    assert bad == 0 and hat > 0.8 * active
+    a, pa = U.oracle_synth(FS26, 26000, recs[:40], threads=8)
+    b, pb, st = U.hostsim_synth(FS26, 26000, recs[:40])
+    assert np.array_equal(a, b) and np.array_equal(pa, pb), st
+
+
 def test_parallel_planner_on_reference_trace():
     z = np.load(GOLD / "paris45_recs.npz")
     bad, (serial, hat, active) = U.hostsim_plan_compare(FS26, 260000, z["recs"])

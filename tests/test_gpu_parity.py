@@ -142,6 +142,21 @@ def test_parallel_planner_equals_serial_planner(monkeypatch):
     assert np.array_equal(a[:4 * n_samp], ref)
 
 
+def test_low_doppler_and_zero_crossings():
+    """Dopplers near and through zero: planner spans without a wrap anchor several spans back (or are
+    walked by the chain); bytes and carried phase still equal the oracle's."""
+    from test_core_hostsim import low_doppler_recs
+    fs, n_samp = FS26, 65536 * 2 + 1000
+    recs = low_doppler_recs(120, fs)
+    ref, ph = U.oracle_synth(fs, n_samp, recs, threads=8)
+    s = E.Synth(fs, n_samp, 8)
+    out = s.synth_epochs(recs)
+    assert np.array_equal(out, ref) and np.array_equal(s.carrier_phases(), ph)
+    st = s.stats()
+    assert st.hat_epochs > 0.7 * (st.hat_epochs + st.serial_epochs)
+    s.close()
+
+
 def test_result_independent_of_ambiguity_threshold(monkeypatch):
     fs, n_samp, nch = FS25, 500000, 12
     recs = U.synthetic_recs(2, nch, fs, seed=21)
