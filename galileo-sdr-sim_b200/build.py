@@ -43,5 +43,34 @@ def build_lib(force=False, verbose=False, defines=(), out=None):
     return lib
 
 
+HOST_SRC = PKG / "host" / "e1_scenario.cpp"
+HOST_LIB = PKG / "lib" / "libe1host.so"
+CLI_SRC = PKG / "host" / "e1sim_main.cpp"
+CLI_BIN = PKG / "lib" / "e1sim"
+
+
+def build_host(force=False):
+    """Host side of the drop-in (RINEX -> records, plain C++, no CUDA): lib/libe1host.so.
+    -ffp-contract=off: the records must be bit-identical to the reference's (see e1_scenario.h)."""
+    deps = [HOST_SRC, PKG / "host" / "e1_scenario.h", PKG / "csrc" / "e1_core.h", PKG.parent / "include" / "e1b200.h"]
+    if not force and HOST_LIB.exists() and all(HOST_LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return HOST_LIB
+    HOST_LIB.parent.mkdir(exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", str(HOST_LIB), str(HOST_SRC)])
+    return HOST_LIB
+
+
+def build_cli(force=False):
+    """lib/e1sim: the reference's command line (src/main.cpp:216) over libe1host + libe1b200."""
+    build_lib()
+    build_host()
+    deps = [CLI_SRC, HOST_LIB, LIB]
+    if not force and CLI_BIN.exists() and all(CLI_BIN.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return CLI_BIN
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", str(CLI_BIN), str(CLI_SRC), "-L", str(LIB.parent), "-le1host", "-le1b200",
+                           "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    return CLI_BIN
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,200 @@
+/* e1sim -- the reference's command line over the B200 synthesiser.
+ *
+ * Same option letters and defaults as usrp_galileo (getopt string "e:n:o:u:g:l:T:t:d:G:a:p:iI:U:b:v",
+ * src/main.cpp:216; default output name galileosim.ishort, :339; "-o -" = stdout,
+ * src/galileo-sdr.cpp:330-341) and the same byte stream: headerless little-endian int16 I,Q,
+ * (10 d - 1) blocks of 260 000 samples.  Host work (RINEX, orbits, pages) is libe1host; the sample
+ * loop is libe1b200 (CUDA, no CPU fallback).  Options that only matter to the USRP / UDP plumbing
+ * (-a -G -p -i -n -u -g -U -b) are accepted and ignored, as the file-sink path of the reference does.
+ *
+ *   e1sim -e rinex_files/week171.rnx -l -6,51,100 -d 10 -o out.ishort
+ */
+#include <fcntl.h>
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <thread>
+#include <vector>
+
+#include "../../include/e1b200.h"
+#include "e1_scenario.h"
+
+/* The sink is the slow part once the GPU does the sample loop (a single writer into the page cache
+   moves ~3 GB/s, the synthesiser delivers > 10 GB/s): regular files are written by several threads,
+   each pwrite()-ing its slice at its own offset. */
+static bool write_parallel(int fd, const char *buf, size_t bytes, off_t offset, int n_threads)
+{
+    std::vector<std::thread> th;
+    std::vector<int> ok((size_t)n_threads, 1);
+    const size_t per = (bytes / (size_t)n_threads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < n_threads; t++) {
+        const size_t lo = (size_t)t * per, hi = lo + per < bytes ? lo + per : bytes;
+        if (lo >= hi)
+            break;
+        th.emplace_back([=, &ok] {
+            size_t done = lo;
+            while (done < hi) {
+                const ssize_t w = pwrite(fd, buf + done, hi - done, offset + (off_t)done);
+                if (w <= 0) {
+                    ok[(size_t)t] = 0;
+                    return;
+                }
+                done += (size_t)w;
+            }
+        });
+    }
+    for (auto &x : th)
+        x.join();
+    for (int v : ok)
+        if (!v)
+            return false;
+    return true;
+}
+
+static void usage(const char *prog)
+{
+    fprintf(stderr,
+            "Usage: %s [options]\n"
+            "  -e <Ephemeris>   RINEX navigation file for Galileo ephemerides (required)\n"
+            "  -o <File sink>   File to store IQ samples (default: galileosim.ishort, '-' = stdout)\n"
+            "  -l <location>    Lat,Lon,Hgt (static mode) e.g. 35.274,137.014,100\n"
+            "  -t <date,time>   Scenario start time YYYY/MM/DD,hh:mm:ss\n"
+            "  -d <duration>    Duration [sec] (max. 300)\n"
+            "  -I               Disable ionospheric delay\n"
+            "  -v               Print the channel allocation\n"
+            "  -B <blocks>      0.1 s blocks per GPU call (default 512)\n",
+            prog);
+}
+
+int main(int argc, char **argv)
+{
+    e1h_options opt;
+    e1h_default_options(&opt);
+    char outfile[512] = "galileosim.ishort";
+    int batch = 512;
+    opt.verbose = 1; /* the reference always prints its allocation lines */
+    int c;
+    while ((c = getopt(argc, argv, "e:n:o:u:g:l:T:t:d:G:a:p:iI:U:b:vB:")) != -1) {
+        switch (c) {
+        case 'e':
+            snprintf(opt.navfile, sizeof opt.navfile, "%s", optarg);
+            break;
+        case 'o':
+            snprintf(outfile, sizeof outfile, "%s", optarg);
+            break;
+        case 'l':
+            sscanf(optarg, "%lf,%lf,%lf", &opt.llh[0], &opt.llh[1], &opt.llh[2]);
+            break;
+        case 't':
+            if (sscanf(optarg, "%d/%d/%d,%d:%d:%lf", &opt.y, &opt.m, &opt.d, &opt.hh, &opt.mm, &opt.sec) != 6) {
+                fprintf(stderr, "ERROR: Invalid date and time.\n");
+                return 1;
+            }
+            opt.have_start = 1;
+            break;
+        case 'd':
+            opt.iduration = (int)(atof(optarg) * 10.0 + 0.5);
+            break;
+        case 'I':
+            opt.iono_enable = 0;
+            break;
+        case 'B':
+            batch = atoi(optarg) > 0 ? atoi(optarg) : batch;
+            break;
+        case 'T':
+            fprintf(stderr, "ERROR: -T (overwrite TOC/TOE) is not supported.\n"); /* the reference's path for it reads an uninitialised count */
+            return 1;
+        case '?':
+            usage(argv[0]);
+            return 1;
+        default: /* -n -u -g -G -a -p -i -U -b -v: plumbing of sinks this tool does not have */
+            break;
+        }
+    }
+    if (!opt.navfile[0]) {
+        usage(argv[0]);
+        return 1;
+    }
+    char err[256] = "";
+    e1h_scenario *scn = e1h_open(&opt, err, sizeof err);
+    if (!scn) {
+        fprintf(stderr, "%s\n", err);
+        return 1;
+    }
+    e1b200_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.fs_hz = opt.fs_hz;
+    cfg.samples_per_epoch = opt.samples_per_epoch;
+    cfg.max_chan = opt.max_chan;
+    e1b200_ctx *gpu = nullptr;
+    if (e1b200_create(&cfg, &gpu) != E1B200_OK) {
+        fprintf(stderr, "ERROR: no usable CUDA device (%s)\n", e1b200_last_error(gpu));
+        if (gpu)
+            e1b200_destroy(gpu);
+        return 1;
+    }
+    FILE *fp = nullptr;
+    int fd = -1;
+    if (strcmp(outfile, "-") == 0)
+        fp = stdout;
+    else
+        fd = open(outfile, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (!fp && fd < 0) {
+        fprintf(stderr, "ERROR: Failed to open output file.\n");
+        return 1;
+    }
+    off_t file_off = 0;
+    const int n_writers = 8;
+    const int total = e1h_total_epochs(scn);
+    const size_t block_i16 = (size_t)opt.samples_per_epoch * 2;
+    int16_t *iq = nullptr;
+    if (e1b200_host_alloc((void **)&iq, (size_t)batch * block_i16 * sizeof(int16_t)) != E1B200_OK) {
+        fprintf(stderr, "ERROR: pinned allocation failed\n");
+        return 1;
+    }
+    std::vector<e1_epoch_rec> recs((size_t)batch * opt.max_chan);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    double t_host = 0, t_gpu = 0, t_io = 0;
+    int done = 0;
+    while (done < total) {
+        struct timespec a, b, d, e;
+        clock_gettime(CLOCK_MONOTONIC, &a);
+        const int n = e1h_next(scn, batch, recs.data(), nullptr);
+        if (n <= 0)
+            break;
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        if (e1b200_synth_epochs(gpu, n, recs.data(), iq) != E1B200_OK) {
+            fprintf(stderr, "ERROR: %s\n", e1b200_last_error(gpu));
+            return 1;
+        }
+        clock_gettime(CLOCK_MONOTONIC, &d);
+        const size_t bytes = (size_t)n * block_i16 * sizeof(int16_t);
+        const bool wrote = fp ? fwrite(iq, 1, bytes, fp) == bytes : write_parallel(fd, (const char *)iq, bytes, file_off, n_writers);
+        if (!wrote) {
+            fprintf(stderr, "ERROR: short write\n");
+            return 1;
+        }
+        file_off += (off_t)bytes;
+        clock_gettime(CLOCK_MONOTONIC, &e);
+        t_host += (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+        t_gpu += (d.tv_sec - b.tv_sec) + 1e-9 * (d.tv_nsec - b.tv_nsec);
+        t_io += (e.tv_sec - d.tv_sec) + 1e-9 * (e.tv_nsec - d.tv_nsec);
+        done += n;
+        fprintf(stderr, "\rTime into run = %4.1f", done / 10.0);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (fd >= 0)
+        close(fd);
+    const double wall = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    fprintf(stderr, "\nDone!\nProcess time = %.3f [sec]  (records %.3f, synthesis incl. copies %.3f, file %.3f)  %.1f Msamples/s\n", wall, t_host,
+            t_gpu, t_io, (double)done * opt.samples_per_epoch / wall / 1e6);
+    e1b200_host_free(iq);
+    e1b200_destroy(gpu);
+    e1h_close(scn);
+    return 0;
+}
