@@ -38,7 +38,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = {
     # name: (fs, samples/epoch, channels, epochs, description)
-    "cfg1": (2.6e6, 260000, 8, 99, "BASELINE configs[0] shape: 2.6 MS/s, 8 ch, 10 s (99 blocks), synthetic records"),
+    "cfg1": (2.6e6, 260000, 8, 99, "BASELINE configs[0]: static -l -6,51,100 -e week171.rnx, 2.6 MS/s, 8 satellites, 10 s (99 blocks)"),
     "cfg2": (2.6e6, 260000, 36, 2999, "BASELINE configs[1]: static, 2.6 MS/s, 36 ch, 300 s (2999 blocks)"),
     "cfg3": (25e6, 2500000, 36, 2999, "BASELINE configs[2]: static, 25 MS/s, 36 ch, 300 s (2999 blocks)"),
     "cfg3s": (25e6, 2500000, 36, 300, "BASELINE configs[2] slice: 25 MS/s, 36 ch, 30 s (300 blocks)"),
@@ -138,6 +138,41 @@ def cpu_baseline(fs, n_samp, n_chan, seconds_target=15.0):
                       f"oracle/e1_oracle.c (channels split over {threads} threads)"}
 
 
+REF_BIN = ROOT / "oracle" / "_ref" / "usrp_galileo"
+NAV_SUBSET = ROOT / "tests" / "golden" / "week171_subset.rnx"
+
+
+def reference_binary_cfg1(seconds=10):
+    """The reference's OWN executable (oracle/_ref/usrp_galileo: its unmodified sources, built by
+    oracle/Makefile where /root/reference exists; the binary travels with the repo) on BASELINE
+    configs[0]: `-l -6,51,100 -e week171 -d 10`, 8 satellites, 2.6 MS/s, one thread (the reference's
+    generator is single-threaded).  It aborts on exit by design flaw after closing its file (SURVEY
+    fact 9), so only the file and its own "Process time" line count.  Returns None if unavailable."""
+    if not (REF_BIN.exists() and NAV_SUBSET.exists()):
+        return None
+    import hashlib
+    import re
+    import tempfile
+    out = Path(tempfile.gettempdir()) / f"e1_ref_{os.getpid()}.ishort"
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run([str(REF_BIN), "-l", "-6,51,100", "-e", str(NAV_SUBSET), "-o", str(out), "-U", "1", "-b", "1", "-d", str(seconds)],
+                           capture_output=True, text=True, timeout=600)
+    except Exception:
+        return None
+    wall = time.perf_counter() - t0
+    if not out.exists():
+        return None
+    n_samples = out.stat().st_size // 4
+    md5 = hashlib.md5(out.read_bytes()).hexdigest() if n_samples * 4 < 2e8 else None
+    out.unlink()
+    m = re.search(r"Process time = ([0-9.]+)", r.stderr + r.stdout)
+    t = float(m.group(1)) if m and float(m.group(1)) > 0 else wall
+    return {"value": n_samples / t / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"oracle/_ref/usrp_galileo -l -6,51,100 -e week171_subset.rnx -d {seconds}: {n_samples} samples, 8 satellites, "
+                      f"process time {t:.1f} s (wall {wall:.1f} s), md5 {md5}"}
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's CPU algorithm on the host cores (rank 0 only)."""
     import e1util as U
@@ -147,6 +182,21 @@ def run_reference(args, wl):
     fs_nom, n_samp, n_chan, n_epochs, desc = wl
     fs = U.fs_as_reference(fs_nom)
     threads = min(os.cpu_count() or 1, n_chan)
+    if args.workload == "cfg1" and REF_BIN.exists() and NAV_SUBSET.exists():
+        # the reference's own binary on its own runnable case: every step is one full run
+        vals = [reference_binary_cfg1() for _ in range(args.warmup + args.steps)][args.warmup:]
+        vals = [v for v in vals if v]
+        if vals:
+            val = sum(v["value"] for v in vals) / len(vals)
+            ms = 1e3 * 99 * n_samp / (val * 1e6)
+            print(json.dumps({
+                "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 phase + int32 accumulate", "data": "real: RINEX week171 subset, -l -6,51,100, 8 satellites",
+                "config": {"workload": desc, "fs_hz": fs_nom, "channels": 8, "blocks_per_step": 99},
+                "cpu_baseline": dict(vals[-1], value=val),
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+            return
     # bounded sample per step so the whole run ends within minutes
     recs1 = U.synthetic_recs_fast(2, n_chan, fs, seed=5)
     t0 = time.perf_counter()
@@ -208,7 +258,22 @@ def main():
 
     fs_nom, n_samp, n_chan, n_epochs, desc = wl
     fs = U.fs_as_reference(fs_nom)
-    recs = U.synthetic_recs_fast(n_epochs, n_chan, fs, seed=1000 + rank)     # each rank: its own time shard
+    data_desc = "synthetic"
+    recs = None
+    if args.workload == "cfg1" and NAV_SUBSET.exists():
+        try:                                                                 # the reference's own case from its own navigation data
+            import build as B
+            B.build_host()
+            import e1host as H
+            n_chan = 16                                                      # MAX_CHAN of the reference build
+            recs, _ = H.Scenario(NAV_SUBSET, llh=(-6, 51, 100), duration_s=10, max_chan=n_chan).all()
+            recs = np.ascontiguousarray(recs.astype(U.REC_DTYPE))
+            data_desc = "real: RINEX week171 subset, -l -6,51,100, 8 satellites (records by galileo-sdr-sim_b200/host)"
+        except Exception as ex:
+            print(f"bench: host records unavailable ({ex}); synthetic records instead", file=sys.stderr)
+            recs = None
+    if recs is None:
+        recs = U.synthetic_recs_fast(n_epochs, n_chan, fs, seed=1000 + rank)     # each rank: its own time shard
     rec_bytes = recs.nbytes
     out_bytes = n_epochs * n_samp * 4
     samples_per_step = n_epochs * n_samp
@@ -289,7 +354,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 phase + int32 accumulate", "data": "synthetic",
+            "dtype": "f64 phase + int32 accumulate", "data": data_desc,
             "config": {"workload": desc, "fs_hz": fs_nom, "channels": n_chan, "blocks_per_step": n_epochs,
                        "samples_per_step_per_gpu": samples_per_step, "tile": st.tile, "ctas_per_sm": st.ctas_per_sm,
                        "l2": f"each step writes {out_bytes / 1e9:.2f} GB per GPU (> 126 MB L2), no flush needed",
@@ -310,7 +375,12 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(fs, n_samp, n_chan)
+            ref = reference_binary_cfg1() if args.workload == "cfg1" else None
+            line["cpu_baseline"] = ref or cpu_baseline(fs, n_samp, n_chan)
+            if args.workload != "cfg1":
+                rb = reference_binary_cfg1()
+                if rb:
+                    line["reference_binary_configs0"] = rb      # the real executable on its own runnable case, for scale
         print(json.dumps(line))
     synth.close()
     if dist is not None:
