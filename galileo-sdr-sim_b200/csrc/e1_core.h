@@ -277,16 +277,22 @@ E1_HD uint32_t e1_thr_code(int T, int scale)
  * two's-complement value of  y - x = (B*d - C*s)/2  in {-1, 0, +1}  (:520-521).
  * 512 data words plus zero padding (a window read touches word i and i+1).                       */
 #define E1C_CODE_WORDS_PER_PRN 516
-/* Carrier table: int32 [2][512][E1C_LUT_REP], value for (regime r, index i, copy l):
- *   2*(cos + 65536*sin) of table index i (r = 0, phase >= 0) or (-i)&511 (r = 1, phase < 0)
- * (include/constants.h:216-284, src/galileo-sdr.cpp:509-510).  Sixteen copies of every entry,
- * one per (lane & 15), so a warp's 32 lookups fall into 16 distinct banks: at most a 2-way
- * shared-memory conflict whatever the indices are.                                               */
+/* Carrier table: int32 [2][E1C_LUT_IDX][E1C_LUT_REP], value for (regime r, index i, copy l), with
+ * i' = i mod 511:  2*(cos + 65536*sin) of table index i' (r = 0, phase >= 0) or (-i')&511 (r = 1,
+ * phase < 0) (include/constants.h:216-284, src/galileo-sdr.cpp:509-510).  trunc(511*|phi|) of a
+ * wrapped phase is at most 510; the entries from 511 on repeat the table from index 0, so a run of
+ * samples can keep multiplying an UNWRAPPED phase across a carrier wrap (phi -= (long)phi, :532):
+ * 511*(phi + 1) = 511*phi + 511 has the same fraction and an index exactly 511 higher.  Sixteen
+ * copies of every entry, one per (lane & 15), so a warp's 32 lookups fall into 16 distinct banks:
+ * at most a 2-way shared-memory conflict whatever the indices are.                               */
 #define E1C_LUT_REP 16
-#define E1C_LUT_ENTRIES (2 * 512 * E1C_LUT_REP)
-#define E1C_LUT_REGIME_BYTES (512 * E1C_LUT_REP * 4)
+#define E1C_LUT_IDX 576 /* 511 + 65: a run may overshoot the wrap by up to 64 index steps */
+#define E1C_LUT_ENTRIES (2 * E1C_LUT_IDX * E1C_LUT_REP)
+#define E1C_LUT_REGIME_BYTES (E1C_LUT_IDX * E1C_LUT_REP * 4)
 #define E1C_THREADS 512 /* synthesis CTA: thread t owns samples [t*R, (t+1)*R) of the tile */
 #define E1C_MAX_RUN 16
+/* fast path: |carrier step| such that E1C_MAX_RUN samples move the table index by < 64 */
+#define E1C_FAST_SP_MAX (63.0 / (511.0 * E1C_MAX_RUN))
 /* GALILEO_E1_SECONDARY_CODE (include/constants.h:213), bit i = symbol i */
 #define E1C_SEC25_MASK 0x009B501Cu
 #define E1C_NO_WRAP 0x7fffffff
@@ -977,9 +983,10 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     const uint32_t sa = c->sym & 3u, sb = (c->sym >> 2) & 3u;
     const uint32_t da = ((sa & 1u) << 1) | ((sa ^ (sa >> 1)) & 1u), db = ((sb & 1u) << 1) | ((sb ^ (sb >> 1)) & 1u);
     uint32_t misc = da | (db << 2) | (neg ? E1_PAR_NEG : 0u);
-    /* outside the fast path's domain (|phase| < 1, |step| < 1/2 cycle, at most one half-chip per
-       sample so the code window advances by carries): generic path */
-    if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < 0.5) || !(p->sc < 0.4999))
+    /* outside the fast path's domain (|phase| < 1, a run's index excursion inside the table's
+       extension -- 20 kHz of Doppler at 2.6 MS/s --, at most one half-chip per sample so the code
+       window advances by carries): generic path */
+    if (!(e1_fabs(p->phi) < 1.0) || !(e1_fabs(p->sp) < E1C_FAST_SP_MAX) || !(p->sc < 0.4999))
         misc |= E1_PAR_FORCE;
     if (!aligned) {
         /* |phi| shrinks by s per sample and, where it would go below zero, the phase changes sign and
@@ -1097,13 +1104,71 @@ E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const uns
     }
 }
 
-/* Fast form for the common run: the channel is inside the closed form's domain.  Per sample it costs one 32x32->64 multiply-add (carrier index and
- * its fraction), one address multiply-add, one shared-memory load, one 32-bit add whose carry says
- * "next half-chip" (the code window then moves up by one 2-bit field), one arithmetic shift (the
- * signed chip value), one multiply-add into the accumulator, and half a 3-input minimum for each of
- * the two ambiguity fractions.  Everything is conservative with respect to the generic form:
- *   - carrier: only the high word of U is stepped, by the high word of dU; sample i is low by less
- *     than i+1 units, the bias tc_carr = thr_carr + 511 R covers it;
+/* The sample loop of the fast form (see e1_run_fast).  DEC: duh is the two's complement of a
+ * negative step; the unsigned product duh * 511 i is then too high by 511 i * 2^32, i.e. the index
+ * word is too high by exactly 511 i and the fraction word is right -- the excess is a compile-time
+ * constant that folds into the load's address offset. */
+#ifndef E1_VARIANT
+#define E1_VARIANT 0
+#endif
+template <int R, bool DEC>
+E1_HD uint32_t e1_run_loop(uint64_t y0, uint32_t duh, const unsigned char *lut, uint32_t F, uint32_t dF, uint32_t win, int *acc,
+                           uint32_t lim_carr, uint32_t lim_code)
+{
+    uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
+    uint64_t y = y0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < R; i++) {
+#if defined(__CUDA_ARCH__)
+        if (i) /* spelled out so it stays ONE 32x32+64 multiply-add per sample */
+            asm("mad.wide.u32 %0, %1, 511, %0;" : "+l"(y) : "r"(duh));
+#else
+        y = y0 + (uint64_t)duh * (uint32_t)(511 * i);
+#endif
+        mY = (uint32_t)y < mY ? (uint32_t)y : mY;
+        mF = F < mF ? F : mF;
+        const int w = *(const int32_t *)(lut + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u) - (DEC ? 511 * i * 4 * E1C_LUT_REP : 0));
+        acc[i] += w * ((int)win >> 30);
+        /* F += dF; a carry = the next half-chip: the window moves up by one field.  On the device the
+           add is spelled with its carry flag so it is ONE add on the ALU pipe whose carry-out
+           predicates the shift (instead of an add on the multiplier pipe plus a compare). */
+#if defined(__CUDA_ARCH__)
+        uint32_t cy;
+        asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(F), "=r"(cy) : "r"(dF));
+        if (cy) {
+#if (E1_VARIANT & 3) == 1
+            if (i & 1)
+                asm("shf.l.wrap.b32 %0, 0, %0, 2;" : "+r"(win));
+            else
+                win <<= 2;
+#elif (E1_VARIANT & 3) == 2
+            asm("shf.l.wrap.b32 %0, 0, %0, 2;" : "+r"(win));
+#else
+            win <<= 2;
+#endif
+        }
+#else
+        const uint32_t F2 = F + dF;
+        if (F2 < F)
+            win <<= 2;
+        F = F2;
+#endif
+    }
+    return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
+}
+
+/* Fast form for the common run: the channel is inside the closed form's domain.  Per sample it costs
+ * one 32x32+64 multiply-add (carrier index and its fraction, straight from the run's start value),
+ * one address multiply-add, one shared-memory load, one 32-bit add whose carry-out says "next
+ * half-chip" and predicates the shift that moves the code window up by one 2-bit field, one
+ * arithmetic shift (the signed chip value), one multiply-add into the accumulator, and half a
+ * 3-input minimum for each of the two ambiguity fractions: 8 instructions, 4 on the multiplier
+ * pipe and 3-4 on the ALU pipe (tools/sass_mix.py).  Everything is conservative with respect to
+ * the generic form:
+ *   - carrier: only the high words of U and dU are used; sample i is low by less than i+1 units,
+ *     the bias tc_carr = thr_carr + 511 R covers it;
  *   - code: the fraction F (2^-32 half-chip) is stepped by dF = dH >> 19, same argument, bias in HA/HB;
  *   - a run is ambiguous when the smallest biased fraction it saw is below lim = tc + thr + 1
  *     (the serial value lies in [biased - tc - thr, biased)).
@@ -1141,7 +1206,9 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
     uint32_t neg = misc & E1_PAR_NEG;
     if (misc & E1_PAR_HASZ) { /* rare: the phase changes sign inside this tile */
         const int jz = (int)(misc >> 16);
-        if (j0 < jz && jz < j0 + R)
+        /* the run that contains the crossing, and the one that ends on the last sample before it
+           (the magnitude there can be smaller than the stepping error below): generic form */
+        if (j0 < jz && jz <= j0 + R)
             return 2u;
         if (j0 >= jz) {
             U = 0ull - U;
@@ -1149,44 +1216,17 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
             neg ^= E1_PAR_NEG;
         }
     }
-    uint32_t uh = (uint32_t)(U >> 32);
+    /* y_i = 511 * (uh + i*duh) + tc with the 32-bit truncations uh, duh of U, dU: one multiply-add
+       per sample from the run's start value, multiplier 511*i a compile-time constant, no chain.
+       uh + i*duh is NOT reduced mod 2^32 when the phase wraps inside the run; the table repeats from
+       index 511 on for exactly that (E1C_LUT_IDX; e1_make_par sends steps too large for the
+       extension to the generic form).  A phase magnitude that shrinks towards zero has dU = -step
+       (it cannot reach zero inside a run that gets here); its loop is a second instantiation. */
+    const uint64_t y0 = (uint64_t)(uint32_t)(U >> 32) * 511u + tc_carr;
     const uint32_t duh = (uint32_t)(dU >> 32);
     const unsigned char *lut = lut_lane + (neg ? E1C_LUT_REGIME_BYTES : 0);
-    uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
-#ifndef E1_VARIANT
-#define E1_VARIANT 0
-#endif
-#if E1_VARIANT & 1
-    uint32_t uh1 = uh + duh; /* two interleaved chains, each stepping by duh + duh (three-input adds) */
-#endif
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < R; i++) {
-#if E1_VARIANT & 1
-        const uint32_t uhi = (i & 1) ? uh1 : uh;
-#else
-        const uint32_t uhi = uh;
-#endif
-        const uint64_t y = (uint64_t)uhi * 511u + tc_carr;
-        mY = (uint32_t)y < mY ? (uint32_t)y : mY;
-        mF = F < mF ? F : mF;
-        const int w = *(const int32_t *)(lut + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u));
-        acc[i] += w * ((int)win >> 30);
-#if E1_VARIANT & 1
-        if (i & 1)
-            uh1 = uh1 + duh + duh;
-        else
-            uh = uh + duh + duh;
-#else
-        uh += duh;
-#endif
-        const uint32_t F2 = F + dF;
-        if (F2 < F)
-            win <<= 2;
-        F = F2;
-    }
-    return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
+    return (int64_t)dU < 0 ? e1_run_loop<R, true>(y0, duh, lut, F, dF, win, acc, lim_carr, lim_code)
+                           : e1_run_loop<R, false>(y0, duh, lut, F, dF, win, acc, lim_carr, lim_code);
 }
 
 /* acc = I + 65536*Q  ->  the sink's little-endian (int16 I, int16 Q) pair (:536-537) */
@@ -1202,11 +1242,12 @@ E1_HD uint32_t e1_pack_iq(int acc)
 E1_HD void e1_build_lut(const int *cos512, const int *sin512, int32_t *lut)
 {
     for (int r = 0; r < 2; r++)
-        for (int i = 0; i < 512; i++) {
-            const int k = r ? ((-i) & 511) : i;
+        for (int i = 0; i < E1C_LUT_IDX; i++) {
+            const int iw = i % 511;
+            const int k = r ? ((-iw) & 511) : iw;
             const int32_t w2 = 2 * (cos512[k] + 65536 * sin512[k]);
             for (int l = 0; l < E1C_LUT_REP; l++)
-                lut[(r * 512 + i) * E1C_LUT_REP + l] = w2;
+                lut[(r * E1C_LUT_IDX + i) * E1C_LUT_REP + l] = w2;
         }
 }
 E1_HD void e1_build_code_words(const uint32_t *b_words, const uint32_t *c_words, uint32_t *out)

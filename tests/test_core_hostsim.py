@@ -126,16 +126,18 @@ def test_code_table_matches_oracle_halfchips():
 
 
 def test_carrier_table_layout():
-    """int32[2][512][16]: 2*(cos + 65536*sin) of the reference's tables, 16 copies per entry, second
-    half reflected for negative phase ((-i) & 511, src/galileo-sdr.cpp:509-510 with phi < 0)."""
+    """int32[2][576][16]: 2*(cos + 65536*sin) of the reference's tables, 16 copies per entry, second
+    regime reflected for negative phase ((-i) & 511, src/galileo-sdr.cpp:509-510 with phi < 0); the
+    entries from 511 on repeat the table from 0 (511*(phi+1) has index 511 higher, same fraction)."""
     c, s = (C.c_int * 512)(), (C.c_int * 512)()
     U.oracle().e1o_carrier_lut(c, s)
     c, s = np.array(c), np.array(s)
-    lut = U.product_lut().reshape(2, 512, 16)
+    lut = U.product_lut().reshape(2, 576, 16)
     w2 = 2 * (c + 65536 * s)
     assert (lut == lut[:, :, :1]).all()
-    assert np.array_equal(lut[0, :, 0], w2)
-    assert np.array_equal(lut[1, :, 0], w2[(-np.arange(512)) & 511])
+    i = np.arange(576) % 511
+    assert np.array_equal(lut[0, :, 0], w2[i])
+    assert np.array_equal(lut[1, :, 0], w2[(-i) & 511])
 
 
 @pytest.mark.parametrize("name,epochs", [("cfg1", (0, 1, 2, 28, 29, 30, 98)), ("paris45", (0, 1, 190, 191, 300, 301, 448))])
