@@ -277,22 +277,28 @@ E1_HD uint32_t e1_thr_code(int T, int scale)
  * two's-complement value of  y - x = (B*d - C*s)/2  in {-1, 0, +1}  (:520-521).
  * 512 data words plus zero padding (a window read touches word i and i+1).                       */
 #define E1C_CODE_WORDS_PER_PRN 516
-/* Carrier table: int32 [2][E1C_LUT_IDX][E1C_LUT_REP], value for (regime r, index i, copy l), with
- * i' = i mod 511:  2*(cos + 65536*sin) of table index i' (r = 0, phase >= 0) or (-i')&511 (r = 1,
- * phase < 0) (include/constants.h:216-284, src/galileo-sdr.cpp:509-510).  trunc(511*|phi|) of a
- * wrapped phase is at most 510; the entries from 511 on repeat the table from index 0, so a run of
- * samples can keep multiplying an UNWRAPPED phase across a carrier wrap (phi -= (long)phi, :532):
- * 511*(phi + 1) = 511*phi + 511 has the same fraction and an index exactly 511 higher.  Sixteen
- * copies of every entry, one per (lane & 15), so a warp's 32 lookups fall into 16 distinct banks:
- * at most a 2-way shared-memory conflict whatever the indices are.                               */
-#define E1C_LUT_REP 16
-#define E1C_LUT_IDX 576 /* 511 + 65: a run may overshoot the wrap by up to 64 index steps */
-#define E1C_LUT_ENTRIES (2 * E1C_LUT_IDX * E1C_LUT_REP)
-#define E1C_LUT_REGIME_BYTES (E1C_LUT_IDX * E1C_LUT_REP * 4)
+/* Carrier table: int32 [E1C_LUT_IDX][E1C_LUT_REP]; entry E = e + E1C_LUT_EXT holds, in every copy l,
+ * 2*(cos + 65536*sin) of the reference's table index t(e) (include/constants.h:216-284):
+ *     e in [0, 512]          t = e & 511
+ *     e in [-EXT, -1]        t = 511 + e        (below: where a run that will wrap starts, phase >= 0)
+ *     e in [513, 512 + EXT]  t = e - 511        (above: the same for phase < 0)
+ * With i = trunc(511 |phi|) in [0, 510] the reference reads index i for phi >= 0 and (-i) & 511 for
+ * phi < 0 (src/galileo-sdr.cpp:509-510).  The sample loop multiplies an UNWRAPPED magnitude across a
+ * carrier wrap (phi -= (long)phi, :532): 511 (|phi| + 1) has the same fraction and an index exactly
+ * 511 higher.  So phase >= 0 reads e = i, or e = i - 511 from the start when the run is about to
+ * wrap (i - 511 < 0 before the wrap, the true index after it); phase < 0 reads e = 512 - i, or
+ * e = 512 - i + 511 when about to wrap (1 + m, m = 511 - i, before the wrap -- which is (-i) & 511 --
+ * and 512 - i' after it).  One table serves both signs, which leaves room for THIRTY-TWO copies of
+ * every entry, one per lane: a warp's 32 lookups fall into 32 distinct banks whatever the indices
+ * are (with 16 copies lanes l and l+16 collided on almost every load).                           */
+#define E1C_LUT_REP 32
+#define E1C_LUT_EXT 64
+#define E1C_LUT_IDX (513 + 2 * E1C_LUT_EXT)
+#define E1C_LUT_ENTRIES (E1C_LUT_IDX * E1C_LUT_REP)
 #define E1C_THREADS 512 /* synthesis CTA: thread t owns samples [t*R, (t+1)*R) of the tile */
 #define E1C_MAX_RUN 16
-/* fast path: |carrier step| such that E1C_MAX_RUN samples move the table index by < 64 */
-#define E1C_FAST_SP_MAX (63.0 / (511.0 * E1C_MAX_RUN))
+/* fast path: |carrier step| such that E1C_MAX_RUN samples move the table index by < E1C_LUT_EXT */
+#define E1C_FAST_SP_MAX ((E1C_LUT_EXT - 1.0) / (511.0 * E1C_MAX_RUN))
 /* GALILEO_E1_SECONDARY_CODE (include/constants.h:213), bit i = symbol i */
 #define E1C_SEC25_MASK 0x009B501Cu
 #define E1C_NO_WRAP 0x7fffffff
@@ -1064,7 +1070,7 @@ E1_HD uint32_t e1_mad_u32(uint32_t a, uint32_t b, uint32_t c)
  * j0 (src/galileo-sdr.cpp:509-525): full-precision closed form, full-precision ambiguity test, any
  * position of the code wrap; ambiguous samples are resolved by e1_exact_indices and counted in
  * *n_exact.  add[i] receives the term I + 65536*Q of sample j0+i.  lut_lane = carrier table + the
- * caller's copy offset (4 * (lane & 15)).  Used for the rare runs the fast form hands back. */
+ * caller's copy offset (4 * lane).  Used for the rare runs the fast form hands back. */
 E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int R, int *add,
                           uint32_t thr_carr, uint32_t thr_code, uint64_t bias_h, unsigned long long *n_exact)
 {
@@ -1091,72 +1097,17 @@ E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const uns
         uint32_t h = (uint32_t)(H >> 51);
         const uint32_t hf = (uint32_t)(H >> 19);
         const uint32_t a = (uint32_t)((yf + thr_carr) < 2u * thr_carr + 1u) | (uint32_t)((hf + thr_code) < 2u * thr_code + 1u) | force;
+        if (neg)
+            it = (0u - it) & 511u; /* src/galileo-sdr.cpp:509-510 with phi < 0 */
         if (a) {
-            uint32_t itx;
-            e1_exact_indices(p, j, &h, &itx);
-            it = neg ? ((0u - itx) & 511u) : itx; /* the table's negative half is stored reflected */
+            e1_exact_indices(p, j, &h, &it);
             (*n_exact)++;
         }
         const uint32_t f = ((code[h >> 4] >> (30u - 2u * (h & 15u))) ^ ds) & 3u; /* (x, x^y) */
         const int sgn = (f & 1u) ? ((f & 2u) ? -1 : 1) : 0;                      /* y - x */
-        add[i] = sgn * *(const int32_t *)(lut_lane + (neg ? E1C_LUT_REGIME_BYTES : 0) + it * (4u * E1C_LUT_REP));
+        add[i] = sgn * *(const int32_t *)(lut_lane + (it + E1C_LUT_EXT) * (4u * E1C_LUT_REP));
         Ua += dU;
     }
-}
-
-/* The sample loop of the fast form (see e1_run_fast).  DEC: duh is the two's complement of a
- * negative step; the unsigned product duh * 511 i is then too high by 511 i * 2^32, i.e. the index
- * word is too high by exactly 511 i and the fraction word is right -- the excess is a compile-time
- * constant that folds into the load's address offset. */
-#ifndef E1_VARIANT
-#define E1_VARIANT 0
-#endif
-template <int R, bool DEC>
-E1_HD uint32_t e1_run_loop(uint64_t y0, uint32_t duh, const unsigned char *lut, uint32_t F, uint32_t dF, uint32_t win, int *acc,
-                           uint32_t lim_carr, uint32_t lim_code)
-{
-    uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
-    uint64_t y = y0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < R; i++) {
-#if defined(__CUDA_ARCH__)
-        if (i) /* spelled out so it stays ONE 32x32+64 multiply-add per sample */
-            asm("mad.wide.u32 %0, %1, 511, %0;" : "+l"(y) : "r"(duh));
-#else
-        y = y0 + (uint64_t)duh * (uint32_t)(511 * i);
-#endif
-        mY = (uint32_t)y < mY ? (uint32_t)y : mY;
-        mF = F < mF ? F : mF;
-        const int w = *(const int32_t *)(lut + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u) - (DEC ? 511 * i * 4 * E1C_LUT_REP : 0));
-        acc[i] += w * ((int)win >> 30);
-        /* F += dF; a carry = the next half-chip: the window moves up by one field.  On the device the
-           add is spelled with its carry flag so it is ONE add on the ALU pipe whose carry-out
-           predicates the shift (instead of an add on the multiplier pipe plus a compare). */
-#if defined(__CUDA_ARCH__)
-        uint32_t cy;
-        asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(F), "=r"(cy) : "r"(dF));
-        if (cy) {
-#if (E1_VARIANT & 3) == 1
-            if (i & 1)
-                asm("shf.l.wrap.b32 %0, 0, %0, 2;" : "+r"(win));
-            else
-                win <<= 2;
-#elif (E1_VARIANT & 3) == 2
-            asm("shf.l.wrap.b32 %0, 0, %0, 2;" : "+r"(win));
-#else
-            win <<= 2;
-#endif
-        }
-#else
-        const uint32_t F2 = F + dF;
-        if (F2 < F)
-            win <<= 2;
-        F = F2;
-#endif
-    }
-    return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
 }
 
 /* Fast form for the common run: the channel is inside the closed form's domain.  Per sample it costs
@@ -1216,17 +1167,53 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
             neg ^= E1_PAR_NEG;
         }
     }
-    /* y_i = 511 * (uh + i*duh) + tc with the 32-bit truncations uh, duh of U, dU: one multiply-add
-       per sample from the run's start value, multiplier 511*i a compile-time constant, no chain.
-       uh + i*duh is NOT reduced mod 2^32 when the phase wraps inside the run; the table repeats from
-       index 511 on for exactly that (E1C_LUT_IDX; e1_make_par sends steps too large for the
-       extension to the generic form).  A phase magnitude that shrinks towards zero has dU = -step
-       (it cannot reach zero inside a run that gets here); its loop is a second instantiation. */
+    /* y_i = 511 * (uh + i*duh) + tc with the 32-bit truncations uh, duh of U, dU: index i in the high
+       word, its fraction in the low word; stepped from the run's start value without reducing
+       uh + i*duh mod 2^32 when the phase wraps inside the run -- the table is laid out for that
+       (E1C_LUT_IDX; e1_make_par sends steps too large for its extension to the generic form).  A
+       magnitude that shrinks towards zero has dU = -step (it cannot reach zero inside a run that
+       gets here) and never wraps.  The loop steps the table POSITION, entry in the high word:
+         phase >= 0:  EXT + i (- 511 when the run may wrap)                  = y + EXT 2^32 - wrap
+         phase <  0:  EXT + 512 - i (+ 511 ...): (513 + EXT) 2^32 - 1 - y + wrap has exactly that high
+                      word and the COMPLEMENT of the fraction below it; adding lim_carr carries into
+                      the high word iff fraction < lim_carr, so "ambiguous" reads "low word < lim_carr"
+                      here too (the entry is then one too high, in a run that is redone anyway). */
     const uint64_t y0 = (uint64_t)(uint32_t)(U >> 32) * 511u + tc_carr;
-    const uint32_t duh = (uint32_t)(dU >> 32);
-    const unsigned char *lut = lut_lane + (neg ? E1C_LUT_REGIME_BYTES : 0);
-    return (int64_t)dU < 0 ? e1_run_loop<R, true>(y0, duh, lut, F, dF, win, acc, lim_carr, lim_code)
-                           : e1_run_loop<R, false>(y0, duh, lut, F, dF, win, acc, lim_carr, lim_code);
+    int64_t D = (int64_t)(int32_t)(uint32_t)(dU >> 32) * 511; /* floor of the signed step, times 511 */
+    const uint64_t wrap = (D >= 0 && (uint32_t)(y0 >> 32) >= 511u - E1C_LUT_EXT) ? (511ull << 32) : 0ull;
+    uint64_t y;
+    if (!neg) {
+        y = y0 + ((uint64_t)E1C_LUT_EXT << 32) - wrap;
+    } else {
+        y = (((uint64_t)(513 + E1C_LUT_EXT) << 32) - 1ull) - y0 + wrap + lim_carr;
+        D = -D;
+    }
+    uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < R; i++) {
+        mY = (uint32_t)y < mY ? (uint32_t)y : mY;
+        mF = F < mF ? F : mF;
+        const int w = *(const int32_t *)(lut_lane + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u));
+        acc[i] += w * ((int)win >> 30);
+        y += (uint64_t)D;
+        /* F += dF; a carry = the next half-chip: the window moves up by one field.  On the device the
+           add is spelled with its carry flag so it is ONE add on the ALU pipe whose carry-out
+           predicates the shift (instead of an add on the multiplier pipe plus a compare). */
+#if defined(__CUDA_ARCH__)
+        uint32_t cy;
+        asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(F), "=r"(cy) : "r"(dF));
+        if (cy)
+            win <<= 2;
+#else
+        const uint32_t F2 = F + dF;
+        if (F2 < F)
+            win <<= 2;
+        F = F2;
+#endif
+    }
+    return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
 }
 
 /* acc = I + 65536*Q  ->  the sink's little-endian (int16 I, int16 Q) pair (:536-537) */
@@ -1241,14 +1228,13 @@ E1_HD uint32_t e1_pack_iq(int acc)
  * the E1-B / E1-C primary codes of one PRN, chip j = bit 31-(j%32) of word j/32.              */
 E1_HD void e1_build_lut(const int *cos512, const int *sin512, int32_t *lut)
 {
-    for (int r = 0; r < 2; r++)
-        for (int i = 0; i < E1C_LUT_IDX; i++) {
-            const int iw = i % 511;
-            const int k = r ? ((-iw) & 511) : iw;
-            const int32_t w2 = 2 * (cos512[k] + 65536 * sin512[k]);
-            for (int l = 0; l < E1C_LUT_REP; l++)
-                lut[(r * E1C_LUT_IDX + i) * E1C_LUT_REP + l] = w2;
-        }
+    for (int E = 0; E < E1C_LUT_IDX; E++) {
+        const int e = E - E1C_LUT_EXT;
+        const int t = e < 0 ? 511 + e : (e <= 512 ? (e & 511) : e - 511);
+        const int32_t w2 = 2 * (cos512[t] + 65536 * sin512[t]);
+        for (int l = 0; l < E1C_LUT_REP; l++)
+            lut[E * E1C_LUT_REP + l] = w2;
+    }
 }
 E1_HD void e1_build_code_words(const uint32_t *b_words, const uint32_t *c_words, uint32_t *out)
 {

@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
         __syncthreads();
     }
 
-    const unsigned char *lut_lane = s_lut + 4 * (tid & (E1C_LUT_REP - 1));
+    const unsigned char *lut_lane = s_lut + 4 * (tid & (E1C_LUT_REP - 1)); /* this lane's copy of every entry */
     const uint32_t lim_carr = e1_lim_carr(A.tc_carr, A.thr_carr), lim_code = e1_lim_code(A.tc_code, A.thr_code);
     const int j0 = tid * R;
     unsigned long long n_exact = 0;

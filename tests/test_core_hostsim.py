@@ -126,18 +126,23 @@ def test_code_table_matches_oracle_halfchips():
 
 
 def test_carrier_table_layout():
-    """int32[2][576][16]: 2*(cos + 65536*sin) of the reference's tables, 16 copies per entry, second
-    regime reflected for negative phase ((-i) & 511, src/galileo-sdr.cpp:509-510 with phi < 0); the
-    entries from 511 on repeat the table from 0 (511*(phi+1) has index 511 higher, same fraction)."""
+    """int32[641][32]: 2*(cos + 65536*sin) of the reference's tables, 32 copies per entry (one per lane).
+    Entry E = e + 64: e in [0, 512] -> table index e & 511; below 0 -> 511 + e; above 512 -> e - 511
+    (where runs that are about to wrap start; see E1C_LUT_IDX in e1_core.h).  Checked against what the
+    reference reads (src/galileo-sdr.cpp:509-510) for every index of a wrapped and an unwrapped phase."""
     c, s = (C.c_int * 512)(), (C.c_int * 512)()
     U.oracle().e1o_carrier_lut(c, s)
     c, s = np.array(c), np.array(s)
-    lut = U.product_lut().reshape(2, 576, 16)
+    lut = U.product_lut().reshape(641, 32)
     w2 = 2 * (c + 65536 * s)
-    assert (lut == lut[:, :, :1]).all()
-    i = np.arange(576) % 511
-    assert np.array_equal(lut[0, :, 0], w2[i])
-    assert np.array_equal(lut[1, :, 0], w2[(-i) & 511])
+    assert (lut == lut[:, :1]).all()
+    L, EXT = lut[:, 0], 64
+    i = np.arange(511)                      # trunc(511 |phi|) of a wrapped phase
+    assert np.array_equal(L[EXT + i], w2[i])                    # phi >= 0: index i
+    assert np.array_equal(L[EXT + 512 - i], w2[(-i) & 511])     # phi < 0: index (-i) & 511
+    m = np.arange(1, EXT + 1)               # runs that start m index steps before the wrap
+    assert np.array_equal(L[EXT - m], w2[511 - m])              # phi >= 0, i = 511 - m, read at e = i - 511
+    assert np.array_equal(L[EXT + 512 + m], w2[(-(511 - m)) & 511])   # phi < 0, read at e = 512 - i + 511
 
 
 @pytest.mark.parametrize("name,epochs", [("cfg1", (0, 1, 2, 28, 29, 30, 98)), ("paris45", (0, 1, 190, 191, 300, 301, 448))])
@@ -202,6 +207,25 @@ def test_doppler_sign_flip_and_phase_reset_mid_run():
     recs[5, 2]["carr_phase_init"] = 0.987654321
     recs[2:4, 3]["prn"] = 0                               # idle for two epochs
     recs[6, 3]["f_carr"] = 0.0
+    a, pa = U.oracle_synth(fs, N, recs)
+    b, pb, st = U.hostsim_synth(fs, N, recs)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb), st
+
+
+def test_fast_path_edges_of_the_carrier_table():
+    """Doppler just inside / outside the fast path's step bound (a run of 16 samples may move the
+    table index by at most 63 entries: 20 kHz at 2.6 MS/s), both signs and both phase signs, so runs
+    start anywhere in the table's extensions and wrap inside; plus steps of +-1 table index per
+    sample and exactly zero."""
+    fs, N = FS26, 26000
+    sp_max = 63.0 / (511.0 * 16)
+    f_edge = sp_max * fs
+    freqs = [0.999 * f_edge, -0.999 * f_edge, 1.001 * f_edge, -1.001 * f_edge, fs / 511.0, -fs / 511.0, 0.5 * f_edge, -0.5 * f_edge, 0.0]
+    recs = U.synthetic_recs(3, len(freqs), fs, seed=5)
+    for c, f in enumerate(freqs):
+        recs[:, c]["f_carr"] = f
+        recs[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+        recs[0, c]["carr_phase_init"] = (0.3 + 0.07 * c) * (1 if c % 3 else -1)   # phase sign independent of Doppler sign
     a, pa = U.oracle_synth(fs, N, recs)
     b, pb, st = U.hostsim_synth(fs, N, recs)
     assert np.array_equal(a, b) and np.array_equal(pa, pb), st

@@ -190,6 +190,27 @@ def test_doppler_sign_flip_phase_reset_and_idle_slots():
     s.close()
 
 
+def test_fast_path_edges_of_the_carrier_table():
+    """Doppler just inside / outside the fast path's step bound (16 samples may move the table index
+    by at most 63 entries: 20 kHz at 2.6 MS/s), both Doppler signs and both phase signs, +-1 table
+    index per sample, exactly zero: runs start anywhere in the table's extensions and wrap inside;
+    all four loop instantiations (position up / down, plain / reflected) and the generic form."""
+    fs, N = FS26, 26000
+    f_edge = 63.0 / (511.0 * 16) * fs
+    freqs = [0.999 * f_edge, -0.999 * f_edge, 1.001 * f_edge, -1.001 * f_edge, fs / 511.0, -fs / 511.0, 0.5 * f_edge, -0.5 * f_edge, 0.0]
+    recs = U.synthetic_recs(3, len(freqs), fs, seed=5)
+    for c, f in enumerate(freqs):
+        recs[:, c]["f_carr"] = f
+        recs[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+        recs[0, c]["carr_phase_init"] = (0.3 + 0.07 * c) * (1 if c % 3 else -1)
+    ref, ph = U.oracle_synth(fs, N, recs, threads=8)
+    s = E.Synth(fs, N, len(freqs))
+    out = s.synth_epochs(recs)
+    assert np.array_equal(out, ref), f"{np.count_nonzero((out != ref).any(1))} samples differ"
+    assert np.array_equal(s.carrier_phases(), ph)
+    s.close()
+
+
 def test_set_channel_mirrors_allocate_channel():
     """e1b200_set_channel seeds the slot's carrier phase (src/channel.cpp:98-99) without a flag in
     the record; get/set_carrier_phase round-trip."""
