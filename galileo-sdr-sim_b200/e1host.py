@@ -15,6 +15,12 @@ REC_DTYPE = np.dtype([
 ])
 
 
+RANGE_DTYPE = np.dtype([
+    ("prn", "<i4"), ("flags", "<u4"), ("rho_prev", "<f8"), ("rho_cur", "<f8"), ("grx_sec", "<f8"), ("carr_phase_init", "<f8"),
+    ("page_cur", "u1", 64), ("page_next", "u1", 64),
+])
+
+
 class Options(C.Structure):
     _fields_ = [("navfile", C.c_char * 512), ("llh", C.c_double * 3), ("have_start", C.c_int32),
                 ("y", C.c_int32), ("m", C.c_int32), ("d", C.c_int32), ("hh", C.c_int32), ("mm", C.c_int32),
@@ -37,6 +43,10 @@ def load():
         lib.e1h_close.argtypes = [C.c_void_p]
         lib.e1h_total_epochs.argtypes = [C.c_void_p]
         lib.e1h_next.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.e1h_next_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.e1h_set_location.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        lib.e1h_set_motion.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.e1h_ecef_to_llh_deg.argtypes = [C.c_void_p, C.c_void_p]
         lib.e1h_page_symbols.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
         lib.e1h_crc24q_bits.argtypes = [C.c_void_p, C.c_int]
         lib.e1h_crc24q_bits.restype = C.c_uint
@@ -75,6 +85,24 @@ class Scenario:
         grx = np.zeros(n)
         got = load().e1h_next(self._h, n, recs.ctypes.data, grx.ctypes.data)
         return recs[:got], grx[:got]
+
+    def next_ranges(self, n, with_recs=False):
+        """The next n blocks as pseudoranges (e1_range_rec) for the device-side restate; with_recs also
+        returns the host-restated e1_epoch_rec of the same blocks."""
+        rng = np.zeros((n, self.max_chan), RANGE_DTYPE)
+        recs = np.zeros((n, self.max_chan), REC_DTYPE) if with_recs else None
+        grx = np.zeros(n)
+        got = load().e1h_next_ex(self._h, n, recs.ctypes.data if with_recs else None, rng.ctypes.data, grx.ctypes.data)
+        return (rng[:got], recs[:got], grx[:got]) if with_recs else (rng[:got], grx[:got])
+
+    def set_location(self, lat_deg, lon_deg, height_m):
+        """What the reference's UDP location thread writes into llhr (include/socket.h:165-178)."""
+        load().e1h_set_location(self._h, float(lat_deg), float(lon_deg), float(height_m))
+
+    def set_motion(self, llh_deg):
+        """Table of (lat, lon [deg], height [m]) indexed by block number (entry 0 unused)."""
+        a = np.ascontiguousarray(llh_deg, np.float64).reshape(-1, 3)
+        load().e1h_set_motion(self._h, a.shape[0], a.ctypes.data)
 
     def all(self):
         return self.next(self.n_epochs)

@@ -600,6 +600,7 @@ struct e1h_scenario {
     double xyz[3];
     double delt;
     int numd = 0, iumd = 1;
+    std::vector<double> motion; /* optional: lat, lon [deg], height [m] per block index (e1h_set_motion) */
 
     /* allocateChannel (src/channel.cpp:21-122): runs on a COPY of the current-ephemeris indices */
     void allocate(const GalTime &g, const double *pos)
@@ -735,16 +736,52 @@ void e1h_close(e1h_scenario *s) { delete s; }
 
 int e1h_total_epochs(const e1h_scenario *s) { return s ? s->numd - 1 : 0; }
 
-int e1h_next(e1h_scenario *s, int n, e1_epoch_rec *recs, double *grx_sec)
+int e1h_set_location(e1h_scenario *s, double lat_deg, double lon_deg, double height_m)
 {
-    if (!s || !recs || n < 0)
+    if (!s)
+        return -1;
+    s->llh_deg[0] = lat_deg, s->llh_deg[1] = lon_deg, s->llh_deg[2] = height_m;
+    return 0;
+}
+
+int e1h_set_motion(e1h_scenario *s, int n_blocks, const double *llh_deg)
+{
+    if (!s || n_blocks < 0 || (n_blocks && !llh_deg))
+        return -1;
+    s->motion.assign(llh_deg, llh_deg + (size_t)n_blocks * 3);
+    return 0;
+}
+
+int e1h_ecef_to_llh_deg(const double *xyz, double *llh_deg)
+{
+    double llh[3];
+    ecef_to_llh(xyz, llh);
+    llh_deg[0] = llh[0] * kRadToDeg, llh_deg[1] = llh[1] * kRadToDeg, llh_deg[2] = llh[2];
+    return 0;
+}
+
+int e1h_next(e1h_scenario *s, int n, e1_epoch_rec *recs, double *grx_sec) { return e1h_next_ex(s, n, recs, nullptr, grx_sec); }
+
+int e1h_next_ex(e1h_scenario *s, int n, e1_epoch_rec *recs, e1_range_rec *ranges, double *grx_sec)
+{
+    if (!s || (!recs && !ranges) || n < 0)
         return -1;
     const int max_chan = s->opt.max_chan, n_samp = s->opt.samples_per_epoch;
+    std::vector<e1_epoch_rec> scratch;
+    if (!recs)
+        scratch.resize((size_t)max_chan);
     int done = 0;
     for (; done < n && s->iumd < s->numd; done++, s->iumd++) {
-        e1_epoch_rec *out = recs + (size_t)done * max_chan;
+        e1_epoch_rec *out = recs ? recs + (size_t)done * max_chan : scratch.data();
+        e1_range_rec *rout = ranges ? ranges + (size_t)done * max_chan : nullptr;
         memset(out, 0, sizeof(e1_epoch_rec) * (size_t)max_chan);
-        /* position of this block: the location thread's degrees, converted again (src/galileo-sdr.cpp:443-448) */
+        if (rout)
+            memset(rout, 0, sizeof(e1_range_rec) * (size_t)max_chan);
+        /* position of this block: the location thread's degrees (llhr, include/socket.h:69,165-178 --
+           here e1h_set_location or the motion table), converted again (src/galileo-sdr.cpp:443-448) */
+        if ((size_t)s->iumd * 3 + 2 < s->motion.size())
+            for (int i = 0; i < 3; i++)
+                s->llh_deg[i] = s->motion[(size_t)s->iumd * 3 + i];
         double llh[3] = {s->llh_deg[0] / kRadToDeg, s->llh_deg[1] / kRadToDeg, s->llh_deg[2]};
         llh_to_ecef(llh, s->xyz);
         if (grx_sec)
@@ -767,6 +804,12 @@ int e1h_next(e1h_scenario *s, int n, e1_epoch_rec *recs, double *grx_sec)
             ms -= ibit * 4;
             const double code_phase = ms / 4 * E1_CODE_LEN;
             ibit = (ibit + (E1_SYM_PER_PAGE / 2)) % E1_SYM_PER_PAGE;
+            if (rout) { /* the same block as pseudoranges: computeCodePhase is then evaluated on the device */
+                rout[i].prn = c.prn;
+                rout[i].rho_prev = c.rho0;
+                rout[i].rho_cur = rho.range;
+                rout[i].grx_sec = s->grx.sec;
+            }
             c.rho0 = rho.range;
 
             e1_epoch_rec &r = out[i];
@@ -779,6 +822,10 @@ int e1h_next(e1h_scenario *s, int n, e1_epoch_rec *recs, double *grx_sec)
                 r.flags = E1_REC_SET_PHASE;
                 r.carr_phase_init = c.carr_phase0;
                 c.fresh = false;
+            }
+            if (rout) {
+                rout[i].flags = r.flags;
+                rout[i].carr_phase_init = r.carr_phase_init;
             }
             pack_symbols(c.page, r.page_cur);
             /* does the symbol counter pass 499 inside this block (src/galileo-sdr.cpp:491-506)?  Count the
@@ -806,6 +853,10 @@ int e1h_next(e1h_scenario *s, int n, e1_epoch_rec *recs, double *grx_sec)
                 memcpy(c.page, next, sizeof next);
             } else {
                 memcpy(r.page_next, r.page_cur, E1_PAGE_BYTES);
+            }
+            if (rout) {
+                memcpy(rout[i].page_cur, r.page_cur, E1_PAGE_BYTES);
+                memcpy(rout[i].page_next, r.page_next, E1_PAGE_BYTES);
             }
         }
         /* every 30 s of receiver time: re-match ephemerides, add / drop satellites (:545-562) */

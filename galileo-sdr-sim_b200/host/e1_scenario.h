@@ -51,6 +51,19 @@ int e1h_total_epochs(const e1h_scenario *s);
  * number of blocks written.  grx_sec (optional, [n]) receives the receiver time of each block. */
 int e1h_next(e1h_scenario *s, int n, e1_epoch_rec *recs, double *grx_sec);
 
+/* Same blocks as pseudoranges (e1_range_rec: rho_prev, rho_cur, receiver time, pages) for the
+ * device-side restate, e1b200_synth_ranges (BASELINE configs[3]).  recs and/or ranges may be NULL. */
+int e1h_next_ex(e1h_scenario *s, int n, e1_epoch_rec *recs, e1_range_rec *ranges, double *grx_sec);
+
+/* Receiver position.  The reference re-reads `llhr` -- latitude, longitude [deg], height [m], written
+ * by its UDP location thread (include/socket.h:69,165-178) -- at the top of every block
+ * (src/galileo-sdr.cpp:443-448).  e1h_set_location is that write; e1h_set_motion installs a table
+ * indexed by block number iumd = 1 .. iduration-1 (entry 0 is unused, like xyz[0]) that is applied
+ * the same way, for reproducible dynamic scenarios (e1sim -u). */
+int e1h_set_location(e1h_scenario *s, double lat_deg, double lon_deg, double height_m);
+int e1h_set_motion(e1h_scenario *s, int n_blocks, const double *llh_deg);
+int e1h_ecef_to_llh_deg(const double *xyz, double *llh_deg);
+
 /* Pieces exposed for the tests. */
 int e1h_page_symbols(const e1h_scenario *s, int prn, double grx_sec, int week, int *symbols500);
 unsigned int e1h_crc24q_bits(const int *bits, int length);

@@ -5,9 +5,19 @@
  * src/galileo-sdr.cpp:330-341) and the same byte stream: headerless little-endian int16 I,Q,
  * (10 d - 1) blocks of 260 000 samples.  Host work (RINEX, orbits, pages) is libe1host; the sample
  * loop is libe1b200 (CUDA, no CPU fallback).  Options that only matter to the USRP / UDP plumbing
- * (-a -G -p -i -n -u -g -U -b) are accepted and ignored, as the file-sink path of the reference does.
+ * (-a -G -p -i -n -g -U -b) are accepted and ignored, as the file-sink path of the reference does.
  *
  *   e1sim -e rinex_files/week171.rnx -l -6,51,100 -d 10 -o out.ishort
+ *
+ * Beyond the reference's file-sink path:
+ *   -u <file>  receiver motion, one line per 0.1 s block: "t,x,y,z" (ECEF metres, the gps-sdr-sim
+ *              convention the option letter comes from) or "lat,lon,height" (degrees, metres) -- what
+ *              the reference's UDP location thread would have written into llhr block by block
+ *              (include/socket.h:165-178, src/galileo-sdr.cpp:443-448), made reproducible;
+ *   -R         hand the blocks to the GPU as pseudoranges: computeCodePhase (src/gal-sig.cpp:308-347)
+ *              is then evaluated on the device (e1b200_synth_ranges, BASELINE configs[3]);
+ *   -r         pace the sink to real time (one 0.1 s block per 0.1 s), as a FIFO / radio consumer
+ *              would drain it (src/fifo.cpp, src/usrp.cpp).
  */
 #include <fcntl.h>
 #include <getopt.h>
@@ -66,6 +76,9 @@ static void usage(const char *prog)
             "  -d <duration>    Duration [sec] (max. 300)\n"
             "  -I               Disable ionospheric delay\n"
             "  -v               Print the channel allocation\n"
+            "  -u <motion>      Receiver motion file, one line per 0.1 s: t,x,y,z (ECEF) or lat,lon,hgt\n"
+            "  -R               Evaluate the per-block code-phase/Doppler restate on the GPU\n"
+            "  -r               Pace the output to real time (FIFO / radio style consumer)\n"
             "  -B <blocks>      0.1 s blocks per GPU call (default 512)\n",
             prog);
 }
@@ -76,10 +89,21 @@ int main(int argc, char **argv)
     e1h_default_options(&opt);
     char outfile[512] = "galileosim.ishort";
     int batch = 512;
+    bool device_restate = false, realtime = false, have_duration = false, have_batch = false;
+    char motion_file[512] = "";
     opt.verbose = 1; /* the reference always prints its allocation lines */
     int c;
-    while ((c = getopt(argc, argv, "e:n:o:u:g:l:T:t:d:G:a:p:iI:U:b:vB:")) != -1) {
+    while ((c = getopt(argc, argv, "e:n:o:u:g:l:T:t:d:G:a:p:iI:U:b:vB:Rr")) != -1) {
         switch (c) {
+        case 'u':
+            snprintf(motion_file, sizeof motion_file, "%s", optarg);
+            break;
+        case 'R':
+            device_restate = true;
+            break;
+        case 'r':
+            realtime = true;
+            break;
         case 'e':
             snprintf(opt.navfile, sizeof opt.navfile, "%s", optarg);
             break;
@@ -98,12 +122,14 @@ int main(int argc, char **argv)
             break;
         case 'd':
             opt.iduration = (int)(atof(optarg) * 10.0 + 0.5);
+            have_duration = true;
             break;
         case 'I':
             opt.iono_enable = 0;
             break;
         case 'B':
             batch = atoi(optarg) > 0 ? atoi(optarg) : batch;
+            have_batch = true;
             break;
         case 'T':
             fprintf(stderr, "ERROR: -T (overwrite TOC/TOE) is not supported.\n"); /* the reference's path for it reads an uninitialised count */
@@ -111,7 +137,7 @@ int main(int argc, char **argv)
         case '?':
             usage(argv[0]);
             return 1;
-        default: /* -n -u -g -G -a -p -i -U -b -v: plumbing of sinks this tool does not have */
+        default: /* -n -g -G -a -p -i -U -b -v: plumbing of sinks this tool does not have */
             break;
         }
     }
@@ -119,12 +145,48 @@ int main(int argc, char **argv)
         usage(argv[0]);
         return 1;
     }
+    /* -u: one position per block; line 0 is the position the first channels are allocated from */
+    std::vector<double> motion;
+    if (motion_file[0]) {
+        FILE *mf = fopen(motion_file, "r");
+        if (!mf) {
+            fprintf(stderr, "ERROR: Failed to open user motion file.\n");
+            return 1;
+        }
+        char line[256];
+        while (fgets(line, sizeof line, mf)) {
+            double v[4];
+            const int nf = sscanf(line, "%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3]);
+            double llh[3];
+            if (nf == 4)
+                e1h_ecef_to_llh_deg(v + 1, llh);
+            else if (nf == 3)
+                llh[0] = v[0], llh[1] = v[1], llh[2] = v[2];
+            else
+                continue;
+            motion.insert(motion.end(), llh, llh + 3);
+        }
+        fclose(mf);
+        const int rows = (int)(motion.size() / 3);
+        if (rows < 2) {
+            fprintf(stderr, "ERROR: Failed to read user motion file.\n");
+            return 1;
+        }
+        if (!have_duration || opt.iduration > rows)
+            opt.iduration = rows;
+        opt.llh[0] = motion[0], opt.llh[1] = motion[1], opt.llh[2] = motion[2];
+        fprintf(stderr, "Using user motion file: %d positions (%.1f s).\n", rows, rows / 10.0);
+    }
+    if (realtime && !have_batch)
+        batch = 10; /* one second of latency */
     char err[256] = "";
     e1h_scenario *scn = e1h_open(&opt, err, sizeof err);
     if (!scn) {
         fprintf(stderr, "%s\n", err);
         return 1;
     }
+    if (!motion.empty())
+        e1h_set_motion(scn, (int)(motion.size() / 3), motion.data());
     e1b200_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.fs_hz = opt.fs_hz;
@@ -156,7 +218,8 @@ int main(int argc, char **argv)
         fprintf(stderr, "ERROR: pinned allocation failed\n");
         return 1;
     }
-    std::vector<e1_epoch_rec> recs((size_t)batch * opt.max_chan);
+    std::vector<e1_epoch_rec> recs(device_restate ? 0 : (size_t)batch * opt.max_chan);
+    std::vector<e1_range_rec> ranges(device_restate ? (size_t)batch * opt.max_chan : 0);
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     double t_host = 0, t_gpu = 0, t_io = 0;
@@ -164,11 +227,11 @@ int main(int argc, char **argv)
     while (done < total) {
         struct timespec a, b, d, e;
         clock_gettime(CLOCK_MONOTONIC, &a);
-        const int n = e1h_next(scn, batch, recs.data(), nullptr);
+        const int n = device_restate ? e1h_next_ex(scn, batch, nullptr, ranges.data(), nullptr) : e1h_next(scn, batch, recs.data(), nullptr);
         if (n <= 0)
             break;
         clock_gettime(CLOCK_MONOTONIC, &b);
-        if (e1b200_synth_epochs(gpu, n, recs.data(), iq) != E1B200_OK) {
+        if ((device_restate ? e1b200_synth_ranges(gpu, n, ranges.data(), iq) : e1b200_synth_epochs(gpu, n, recs.data(), iq)) != E1B200_OK) {
             fprintf(stderr, "ERROR: %s\n", e1b200_last_error(gpu));
             return 1;
         }
@@ -185,6 +248,17 @@ int main(int argc, char **argv)
         t_gpu += (d.tv_sec - b.tv_sec) + 1e-9 * (d.tv_nsec - b.tv_nsec);
         t_io += (e.tv_sec - d.tv_sec) + 1e-9 * (e.tv_nsec - d.tv_nsec);
         done += n;
+        if (realtime) { /* the consumer drains 0.1 s of signal per 0.1 s: do not run ahead of it */
+            struct timespec now;
+            clock_gettime(CLOCK_MONOTONIC, &now);
+            const double ahead = done * 0.1 - ((now.tv_sec - t0.tv_sec) + 1e-9 * (now.tv_nsec - t0.tv_nsec));
+            if (ahead > 0.0) {
+                struct timespec ts;
+                ts.tv_sec = (time_t)ahead;
+                ts.tv_nsec = (long)((ahead - (double)ts.tv_sec) * 1e9);
+                nanosleep(&ts, nullptr);
+            }
+        }
         fprintf(stderr, "\rTime into run = %4.1f", done / 10.0);
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);

@@ -98,6 +98,61 @@ def test_bad_inputs(H):
         H.Scenario(NAV, start=(2021, 6, 25, 0, 0, 0))         # outside the file's span
 
 
+def test_range_records_restate_to_the_epoch_records(H):
+    """e1h_next_ex hands the same blocks over as pseudoranges; computeCodePhase (src/gal-sig.cpp:308-347)
+    applied to them -- e1b200_restate, the host twin of the device kernel -- gives the epoch records'
+    f_carr, f_code, code_phase0 and ibit0 bit for bit, pages and phase initialisation are copied."""
+    import ctypes as C
+    lib = C.CDLL(str(B.build_lib()))
+    lib.e1b200_restate.argtypes = [C.c_double] * 4 + [C.c_void_p] * 5
+    rng, recs, grx = H.Scenario(NAV, **SCENARIOS["paris45"]).next_ranges(449, with_recs=True)
+    gold = np.load(GOLD / "paris45_recs.npz")["recs"]
+    assert np.array_equal(recs["f_carr"], gold["f_carr"]) and np.array_equal(rng["prn"], gold["prn"])
+    out = [C.c_double() for _ in range(3)]
+    ib, ip = C.c_int32(), C.c_int32()
+    for e in list(range(0, 449, 7)) + [299, 300, 301]:
+        for c in np.nonzero(rng[e]["prn"] > 0)[0]:
+            r = rng[e, c]
+            assert r["grx_sec"] == grx[e]
+            lib.e1b200_restate(r["rho_prev"], r["rho_cur"], 0.100000023142, r["grx_sec"], *[C.byref(x) for x in out], C.byref(ib), C.byref(ip))
+            g = recs[e, c]
+            assert (out[0].value, out[1].value, out[2].value, ib.value) == (g["f_carr"], g["f_code"], g["code_phase0"], g["ibit0"]), (e, c)
+    for f in ("flags", "carr_phase_init", "page_cur", "page_next"):
+        assert np.array_equal(rng[f], recs[f]), f
+
+
+def test_receiver_motion_table_and_location_updates(H):
+    """Dynamic mode: the reference re-reads the location thread's llhr at every block
+    (src/galileo-sdr.cpp:443-448).  A table that repeats the static position changes nothing; a table
+    and per-block set_location calls are the same thing; a receiver moving east at 100 m/s shifts every
+    channel's Doppler by -(v . line of sight)/lambda, i.e. by at most 100 / 0.1903 = 525 Hz."""
+    kw = dict(SCENARIOS["cfg1"])
+    static, _ = H.Scenario(NAV, **kw).all()
+    n = static.shape[0] + 1
+    s = H.Scenario(NAV, **kw)
+    s.set_motion(np.tile(np.array(kw["llh"], float), (n, 1)))
+    same, _ = s.all()
+    assert np.array_equal(same, static)
+
+    lat, lon, h = kw["llh"]
+    dlon = np.degrees(100.0 * 0.1 / (6378137.0 * np.cos(np.radians(lat))))       # 10 m per block
+    table = np.array([[lat, lon + k * dlon, h] for k in range(n)])
+    s = H.Scenario(NAV, **kw)
+    s.set_motion(table)
+    moving, _ = s.all()
+    s = H.Scenario(NAV, **kw)
+    parts = []
+    for k in range(1, n):
+        s.set_location(*table[k])
+        parts.append(s.next(1)[0])
+    assert np.array_equal(np.concatenate(parts), moving)
+    act = static["prn"][5:] > 0
+    assert np.array_equal(moving["prn"], static["prn"])
+    df = (moving["f_carr"] - static["f_carr"])[5:][act]                          # block 1 sees a position JUMP from xyz[0]
+    assert 20.0 < np.abs(df).max() < 526.0 and np.abs(df).min() < 500.0
+    assert len(np.unique(np.sign(df))) == 2                                      # satellites ahead and behind
+
+
 def test_oracle_on_host_records_reproduces_reference_file(H):
     """End to end on the CPU: host records -> oracle sample loop -> the reference's own bytes."""
     recs, _ = H.Scenario(NAV, **SCENARIOS["cfg1"]).all()
@@ -120,6 +175,27 @@ def test_cli_writes_the_reference_file(tmp_path):
     assert len(data) == 102960000
     assert hashlib.md5(data).hexdigest() == "419622c87f06f4048858bce54df72d29"
     assert "Done!" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_device_restate_and_motion_file(tmp_path):
+    """-R (pseudoranges to the GPU, computeCodePhase on the device) and -u with a motion file that
+    stays put both write the reference's bytes; -r paces a 1 s run to about a second."""
+    import time
+    exe = B.build_cli()
+    out = tmp_path / "r.ishort"
+    r = subprocess.run([str(exe), "-e", str(NAV), "-l", "-6,51,100", "-d", "10", "-R", "-o", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert hashlib.md5(out.read_bytes()).hexdigest() == "419622c87f06f4048858bce54df72d29"
+    mot = tmp_path / "static.csv"
+    mot.write_text("".join("-6,51,100\n" for _ in range(100)))
+    r = subprocess.run([str(exe), "-e", str(NAV), "-u", str(mot), "-o", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert hashlib.md5(out.read_bytes()).hexdigest() == "419622c87f06f4048858bce54df72d29"
+    t0 = time.time()
+    r = subprocess.run([str(exe), "-e", str(NAV), "-l", "-6,51,100", "-d", "2", "-r", "-B", "2", "-o", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and len(out.read_bytes()) == 19 * 260000 * 4
+    assert time.time() - t0 > 1.5
 
 
 @pytest.mark.gpu
