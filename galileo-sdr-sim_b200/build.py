@@ -44,6 +44,7 @@ def build_lib(force=False, verbose=False, defines=(), out=None):
 
 
 HOST_SRC = PKG / "host" / "e1_scenario.cpp"
+FIFO_SRC = PKG / "host" / "e1_fifo.cpp"
 HOST_LIB = PKG / "lib" / "libe1host.so"
 CLI_SRC = PKG / "host" / "e1sim_main.cpp"
 CLI_BIN = PKG / "lib" / "e1sim"
@@ -52,11 +53,13 @@ CLI_BIN = PKG / "lib" / "e1sim"
 def build_host(force=False):
     """Host side of the drop-in (RINEX -> records, plain C++, no CUDA): lib/libe1host.so.
     -ffp-contract=off: the records must be bit-identical to the reference's (see e1_scenario.h)."""
-    deps = [HOST_SRC, PKG / "host" / "e1_scenario.h", PKG / "csrc" / "e1_core.h", PKG.parent / "include" / "e1b200.h"]
+    deps = [HOST_SRC, FIFO_SRC, PKG / "host" / "e1_scenario.h", PKG / "host" / "e1_fifo.h", PKG / "csrc" / "e1_core.h",
+            PKG.parent / "include" / "e1b200.h"]
     if not force and HOST_LIB.exists() and all(HOST_LIB.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return HOST_LIB
     HOST_LIB.parent.mkdir(exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", str(HOST_LIB), str(HOST_SRC)])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-o", str(HOST_LIB), str(HOST_SRC), str(FIFO_SRC),
+                           "-lpthread"])
     return HOST_LIB
 
 

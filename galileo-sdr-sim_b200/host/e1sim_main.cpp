@@ -16,8 +16,9 @@
  *              (include/socket.h:165-178, src/galileo-sdr.cpp:443-448), made reproducible;
  *   -R         hand the blocks to the GPU as pseudoranges: computeCodePhase (src/gal-sig.cpp:308-347)
  *              is then evaluated on the device (e1b200_synth_ranges, BASELINE configs[3]);
- *   -r         pace the sink to real time (one 0.1 s block per 0.1 s), as a FIFO / radio consumer
- *              would drain it (src/fifo.cpp, src/usrp.cpp).
+ *   -r         streaming mode: the blocks go through the sample FIFO (host/e1_fifo.h, the reference's
+ *              fifo_read contract, src/fifo.cpp) and a consumer thread drains it in radio-sized
+ *              buffers at the sample rate, like the reference's TX thread (src/usrp.cpp), into -o.
  */
 #include <fcntl.h>
 #include <getopt.h>
@@ -31,6 +32,7 @@
 #include <vector>
 
 #include "../../include/e1b200.h"
+#include "e1_fifo.h"
 #include "e1_scenario.h"
 
 /* The sink is the slow part once the GPU does the sample loop (a single writer into the page cache
@@ -218,6 +220,44 @@ int main(int argc, char **argv)
         fprintf(stderr, "ERROR: pinned allocation failed\n");
         return 1;
     }
+    /* -r: FIFO of two batches + the consumer ("TX") thread: radio-sized reads, paced to the sample rate */
+    e1_fifo *fifo = nullptr;
+    std::thread consumer;
+    bool consumer_ok = true;
+    if (realtime) {
+        fifo = e1_fifo_create((size_t)2 * batch * opt.samples_per_epoch, nullptr);
+        if (!fifo) {
+            fprintf(stderr, "ERROR: FIFO allocation failed\n");
+            return 1;
+        }
+        consumer = std::thread([&] {
+            const size_t chunk = 32 * 1024; /* SAMPLES_PER_BUFFER, include/constants.h:78 */
+            std::vector<int16_t> tx(chunk * 2);
+            struct timespec c0;
+            clock_gettime(CLOCK_MONOTONIC, &c0);
+            unsigned long long sent = 0;
+            for (;;) {
+                const size_t got = e1_fifo_read_wait(fifo, tx.data(), chunk);
+                if (got == 0 && e1_fifo_finished(fifo))
+                    break;
+                if (fp ? fwrite(tx.data(), 4, got, fp) != got : write(fd, tx.data(), got * 4) != (ssize_t)(got * 4)) {
+                    consumer_ok = false;
+                    e1_fifo_finish(fifo);
+                    break;
+                }
+                sent += got;
+                struct timespec now;
+                clock_gettime(CLOCK_MONOTONIC, &now);
+                const double ahead = (double)sent / opt.fs_hz - ((now.tv_sec - c0.tv_sec) + 1e-9 * (now.tv_nsec - c0.tv_nsec));
+                if (ahead > 0.0) {
+                    struct timespec ts;
+                    ts.tv_sec = (time_t)ahead;
+                    ts.tv_nsec = (long)((ahead - (double)ts.tv_sec) * 1e9);
+                    nanosleep(&ts, nullptr);
+                }
+            }
+        });
+    }
     std::vector<e1_epoch_rec> recs(device_restate ? 0 : (size_t)batch * opt.max_chan);
     std::vector<e1_range_rec> ranges(device_restate ? (size_t)batch * opt.max_chan : 0);
     struct timespec t0, t1;
@@ -237,7 +277,13 @@ int main(int argc, char **argv)
         }
         clock_gettime(CLOCK_MONOTONIC, &d);
         const size_t bytes = (size_t)n * block_i16 * sizeof(int16_t);
-        const bool wrote = fp ? fwrite(iq, 1, bytes, fp) == bytes : write_parallel(fd, (const char *)iq, bytes, file_off, n_writers);
+        bool wrote = true;
+        if (fifo) { /* producer side of the FIFO, block by block (src/galileo-sdr.cpp:581-596) */
+            for (int e = 0; e < n && wrote; e++)
+                wrote = e1_fifo_write(fifo, iq + (size_t)e * block_i16, (size_t)opt.samples_per_epoch) == 0;
+        } else {
+            wrote = fp ? fwrite(iq, 1, bytes, fp) == bytes : write_parallel(fd, (const char *)iq, bytes, file_off, n_writers);
+        }
         if (!wrote) {
             fprintf(stderr, "ERROR: short write\n");
             return 1;
@@ -248,18 +294,16 @@ int main(int argc, char **argv)
         t_gpu += (d.tv_sec - b.tv_sec) + 1e-9 * (d.tv_nsec - b.tv_nsec);
         t_io += (e.tv_sec - d.tv_sec) + 1e-9 * (e.tv_nsec - d.tv_nsec);
         done += n;
-        if (realtime) { /* the consumer drains 0.1 s of signal per 0.1 s: do not run ahead of it */
-            struct timespec now;
-            clock_gettime(CLOCK_MONOTONIC, &now);
-            const double ahead = done * 0.1 - ((now.tv_sec - t0.tv_sec) + 1e-9 * (now.tv_nsec - t0.tv_nsec));
-            if (ahead > 0.0) {
-                struct timespec ts;
-                ts.tv_sec = (time_t)ahead;
-                ts.tv_nsec = (long)((ahead - (double)ts.tv_sec) * 1e9);
-                nanosleep(&ts, nullptr);
-            }
-        }
         fprintf(stderr, "\rTime into run = %4.1f", done / 10.0);
+    }
+    if (fifo) {
+        e1_fifo_finish(fifo);
+        consumer.join();
+        e1_fifo_destroy(fifo);
+        if (!consumer_ok) {
+            fprintf(stderr, "ERROR: short write\n");
+            return 1;
+        }
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (fd >= 0)
