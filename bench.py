@@ -47,18 +47,23 @@ METRIC = "E1B/C IQ Msamples/sec"
 UNIT = "Msamples/s"
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of e1_synth_kernel from the newest committed
-    `ncu --set full` summary of the default workload (profiles/*synth_ncu_summary.txt, one launch)."""
+def ncu_summary_numbers():
+    """From the newest committed `ncu --set full` summary of e1_synth_kernel on the default workload
+    (profiles/*synth_ncu_summary.txt, one launch): DRAM traffic (dram__bytes_read.sum +
+    dram__bytes_write.sum) and warp instructions executed (smsp__inst_executed.sum)."""
     best = None
     for f in sorted((ROOT / "profiles").glob("*synth_ncu_summary.txt")):
-        tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        if "cfg3" in f.name:
+            continue
+        tot, inst, mult = 0.0, None, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for ln in f.read_text().splitlines():
             p = ln.split()
             if len(p) >= 3 and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and p[2] in mult:
                 tot += float(p[1]) * mult[p[2]]
+            if len(p) >= 2 and p[0] == "smsp__inst_executed.sum":
+                inst = float(p[1])
         if tot:
-            best = (tot, f.name)
+            best = (tot, f.name, inst)
     return best
 
 
@@ -349,8 +354,18 @@ def main():
         per_launch_ms = synth_ms / max(synth_launches, 1)
         bytes_per_launch = out_bytes * args.steps / max(synth_launches, 1)
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-        tr = ncu_traffic_bytes() if args.workload == "cfg2" else None
+        tr = ncu_summary_numbers() if args.workload == "cfg2" else None
         traffic, traffic_src = (tr[0], f"profiles/{tr[1]} (ncu --set full, one launch of this workload)") if tr else (None, None)
+        # what actually bounds the kernel: warp-instruction issue slots (4 schedulers per SM, one instruction
+        # per clock each).  Instructions per launch from the committed ncu capture of this workload, duration live.
+        issue = None
+        if tr and tr[2] and clocks and clocks.get("sm_mhz"):
+            peak_issue = st.sm_count * 4 * clocks["sm_mhz"] * 1e6
+            ach_issue = tr[2] / (per_launch_ms * 1e-3)
+            issue = {"bound": "issue slots (integer pipes; no tensor-core or HBM-bound formulation of this loop exists)",
+                     "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-inst/s", "frac": ach_issue / peak_issue,
+                     "warp_inst_per_launch": tr[2], "inst_per_channel_sample": tr[2] * 32 / (samples_per_step * n_chan),
+                     "source": f"smsp__inst_executed.sum in profiles/{tr[1]}; peak = {st.sm_count} SMs x 4 schedulers x SM clock under load"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,9 +379,10 @@ def main():
                          "kernel": "e1_synth_kernel", "peak_source": peak_src,
                          "ms_per_launch": per_launch_ms, "launches_per_step": synth_launches / args.steps,
                          "planner_ms_per_step": plan_ms / args.steps, "synth_ms_per_step": synth_ms / args.steps,
-                         "note": "issue-bound, not HBM-bound: 36 channel visits x ~14 integer instructions per 4-byte sample "
-                                 "(ncu: profiles/*synth_ncu_summary.txt, issue slots ~65% busy); HBM time of the same bytes "
+                         "note": f"issue-bound, not HBM-bound: {n_chan} channel visits x ~14 integer instructions per 4-byte sample "
+                                 "(see roofline_issue; ncu: profiles/*synth_ncu_summary.txt); HBM time of the same bytes "
                                  f"would be {bytes_per_launch / peak / 1e6:.2f} ms"},
+            "roofline_issue": issue,
             "clocks": clocks, "gpu_launches": launches,
             "exact_fallback_samples": int(synth.stats().exact_samples),
             "planner": {"hat_epochs": int(synth.stats().hat_epochs), "serial_epochs": int(synth.stats().serial_epochs),
