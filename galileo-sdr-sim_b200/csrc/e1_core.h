@@ -1126,68 +1126,56 @@ E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const uns
  * A code wrap inside the run only changes how the 16-field window is assembled.
  * Returns 0: terms added, final.  1: terms added but some sample is ambiguous (the caller takes them
  * back out and uses the generic form).  2: nothing added, generic form needed.                      */
-template <int R>
-E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *acc,
-                           uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
+/* Shared-memory operands of the sample loop.  On the device the tables are addressed as 32-bit
+ * shared-window addresses and read with ld.shared spelled out: through generic pointers the compiler
+ * may carry the window base in a register and add it to every lookup address (it did, in the
+ * two-team kernel: one extra add per channel-sample).  On the host they are plain pointers. */
+#if defined(__CUDA_ARCH__)
+typedef uint32_t e1_sptr;
+static __device__ __forceinline__ e1_sptr e1_sp(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ uint32_t e1_ld32(e1_sptr a)
 {
-    const int jw = p->j_w;
-    const uint32_t misc = p->misc;
-    if (misc & E1_PAR_FORCE)
-        return 2u;
-    const int after = j0 >= jw;
-    const uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * p->dH;
-    const uint32_t h0 = (uint32_t)(H >> 51);
-    uint32_t F = (uint32_t)(H >> 19);
-    const uint32_t dF = p->dF;
-    const uint32_t *code = codes + p->code_off;
-    uint32_t win = e1_funnel_l(code[(h0 >> 4) + 1], code[h0 >> 4], 2u * (h0 & 15u)); /* half-chips h0..h0+15, h0 on top */
-    win ^= after ? p->pat_b : p->pat_a;
-    if (j0 < jw && jw < j0 + R) {
-        /* the code wraps inside this run (:491-494): half-chip 8184 is half-chip 0 of the next code
-           period, under the next symbol.  The fraction keeps running from the pre-wrap checkpoint;
-           what that costs in accuracy is inside tc_code (see e1_tc_code). */
-        int k0 = 2 * E1C_CODE_LEN - (int)h0; /* window position of half-chip 0 */
-        k0 = k0 < 0 ? 0 : (k0 > 16 ? 16 : k0);
-        const uint32_t keep = k0 >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * k0));
-        const uint32_t wb = (k0 >= 16 ? 0u : (code[0] >> (2 * k0))) ^ p->pat_b;
-        win = (win & keep) | (wb & ~keep);
-    }
-    win &= (win << 1) | 0x55555555u; /* fields are now y - x in two's complement */
-    uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU, dU = p->dU;
-    uint32_t neg = misc & E1_PAR_NEG;
-    if (misc & E1_PAR_HASZ) { /* rare: the phase changes sign inside this tile */
-        const int jz = (int)(misc >> 16);
-        /* the run that contains the crossing, and the one that ends on the last sample before it
-           (the magnitude there can be smaller than the stepping error below): generic form */
-        if (j0 < jz && jz <= j0 + R)
-            return 2u;
-        if (j0 >= jz) {
-            U = 0ull - U;
-            dU = 0ull - dU;
-            neg ^= E1_PAR_NEG;
-        }
-    }
-    /* y_i = 511 * (uh + i*duh) + tc with the 32-bit truncations uh, duh of U, dU: index i in the high
-       word, its fraction in the low word; stepped from the run's start value without reducing
-       uh + i*duh mod 2^32 when the phase wraps inside the run -- the table is laid out for that
-       (E1C_LUT_IDX; e1_make_par sends steps too large for its extension to the generic form).  A
-       magnitude that shrinks towards zero has dU = -step (it cannot reach zero inside a run that
-       gets here) and never wraps.  The loop steps the table POSITION, entry in the high word:
-         phase >= 0:  EXT + i (- 511 when the run may wrap)                  = y + EXT 2^32 - wrap
-         phase <  0:  EXT + 512 - i (+ 511 ...): (513 + EXT) 2^32 - 1 - y + wrap has exactly that high
-                      word and the COMPLEMENT of the fraction below it; adding lim_carr carries into
-                      the high word iff fraction < lim_carr, so "ambiguous" reads "low word < lim_carr"
-                      here too (the entry is then one too high, in a run that is redone anyway). */
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+#else
+typedef const unsigned char *e1_sptr;
+static inline e1_sptr e1_sp(const void *p) { return (const unsigned char *)p; }
+static inline uint32_t e1_ld32(e1_sptr a) { return *(const uint32_t *)a; }
+#endif
+
+/* Table position of the first sample of a run and its per-sample step, from the carrier magnitude U
+ * (2^-64 cycle) and its step dU.  y_i = 511 * (uh + i*duh) + tc with the 32-bit truncations uh, duh:
+ * index i in the high word, its fraction in the low word; stepped from the run's start value without
+ * reducing uh + i*duh mod 2^32 when the phase wraps inside the run -- the table is laid out for that
+ * (E1C_LUT_IDX; e1_make_par sends steps too large for its extension to the generic form).  A magnitude
+ * that shrinks towards zero has dU = -step (it cannot reach zero inside a run that gets here) and
+ * never wraps.  The loop steps the table POSITION, entry in the high word:
+ *   phase >= 0:  EXT + i (- 511 when the run may wrap)                  = y + EXT 2^32 - wrap
+ *   phase <  0:  EXT + 512 - i (+ 511 ...): (513 + EXT) 2^32 - 1 - y + wrap has exactly that high word
+ *                and the COMPLEMENT of the fraction below it; adding lim_carr carries into the high
+ *                word iff fraction < lim_carr, so "ambiguous" reads "low word < lim_carr" here too
+ *                (the entry is then one too high, in a run that is redone anyway).               */
+E1_HD uint64_t e1_carrier_start(uint64_t U, uint64_t dU, uint32_t neg, uint32_t tc_carr, uint32_t lim_carr, int64_t *D_out)
+{
     const uint64_t y0 = (uint64_t)(uint32_t)(U >> 32) * 511u + tc_carr;
-    int64_t D = (int64_t)(int32_t)(uint32_t)(dU >> 32) * 511; /* floor of the signed step, times 511 */
+    const int64_t D = (int64_t)(int32_t)(uint32_t)(dU >> 32) * 511; /* floor of the signed step, times 511 */
     const uint64_t wrap = (D >= 0 && (uint32_t)(y0 >> 32) >= 511u - E1C_LUT_EXT) ? (511ull << 32) : 0ull;
-    uint64_t y;
     if (!neg) {
-        y = y0 + ((uint64_t)E1C_LUT_EXT << 32) - wrap;
-    } else {
-        y = (((uint64_t)(513 + E1C_LUT_EXT) << 32) - 1ull) - y0 + wrap + lim_carr;
-        D = -D;
+        *D_out = D;
+        return y0 + ((uint64_t)E1C_LUT_EXT << 32) - wrap;
     }
+    *D_out = -D;
+    return (((uint64_t)(513 + E1C_LUT_EXT) << 32) - 1ull) - y0 + wrap + lim_carr;
+}
+
+/* The sample loop proper: R samples from table position y (step D), code fraction F (step dF) and the
+ * window of signed chip fields win.  Returns the ambiguity flag of the run. */
+template <int R>
+E1_HD uint32_t e1_sample_loop(uint64_t y, int64_t D, e1_sptr lut_lane, uint32_t F, uint32_t dF, uint32_t win, int *acc,
+                              uint32_t lim_carr, uint32_t lim_code)
+{
     uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -1195,7 +1183,11 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
     for (int i = 0; i < R; i++) {
         mY = (uint32_t)y < mY ? (uint32_t)y : mY;
         mF = F < mF ? F : mF;
-        const int w = *(const int32_t *)(lut_lane + e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, 0u));
+#if defined(__CUDA_ARCH__)
+        const int w = (int)e1_ld32(e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, lut_lane));
+#else
+        const int w = (int)e1_ld32(lut_lane + (uint32_t)(y >> 32) * (4u * E1C_LUT_REP));
+#endif
         acc[i] += w * ((int)win >> 30);
         y += (uint64_t)D;
         /* F += dF; a carry = the next half-chip: the window moves up by one field.  On the device the
@@ -1214,6 +1206,103 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
 #endif
     }
     return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
+}
+
+/* The 16-field code window of the run that starts at tile sample j (code phase H, 2^-51 half-chip, bias
+ * included): half-chips h0..h0+15 with h0 on top, symbol pattern applied, fields turned into the signed
+ * chip value.  A code wrap inside the run (:491-494) only changes how the window is assembled:
+ * half-chip 8184 is half-chip 0 of the next code period, under the next symbol.  The fraction keeps
+ * running from the pre-wrap checkpoint; what that costs in accuracy is inside tc_code (e1_tc_code). */
+E1_HD uint32_t e1_code_window(const e1_chan_par *p, e1_sptr code, uint64_t H, int j, int R, int jw)
+{
+    const uint32_t h0 = (uint32_t)(H >> 51);
+    const e1_sptr cw = code + 4u * (h0 >> 4);
+    uint32_t win = e1_funnel_l(e1_ld32(cw + 4u), e1_ld32(cw), 2u * (h0 & 15u));
+    win ^= j >= jw ? p->pat_b : p->pat_a;
+    if (j < jw && jw < j + R) {
+        int k0 = 2 * E1C_CODE_LEN - (int)h0; /* window position of half-chip 0 */
+        k0 = k0 < 0 ? 0 : (k0 > 16 ? 16 : k0);
+        const uint32_t keep = k0 >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * k0));
+        const uint32_t wb = (k0 >= 16 ? 0u : (e1_ld32(code) >> (2 * k0))) ^ p->pat_b;
+        win = (win & keep) | (wb & ~keep);
+    }
+    return win & ((win << 1) | 0x55555555u); /* fields are now y - x in two's complement */
+}
+
+template <int R>
+E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *acc,
+                           uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
+{
+    const int jw = p->j_w;
+    const uint32_t misc = p->misc;
+    if (misc & E1_PAR_FORCE)
+        return 2u;
+    const int after = j0 >= jw;
+    const uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * p->dH;
+    const uint32_t F = (uint32_t)(H >> 19);
+    const uint32_t win = e1_code_window(p, e1_sp(codes) + 4u * p->code_off, H, j0, R, jw);
+    uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU, dU = p->dU;
+    uint32_t neg = misc & E1_PAR_NEG;
+    if (misc & E1_PAR_HASZ) { /* rare: the phase changes sign inside this tile */
+        const int jz = (int)(misc >> 16);
+        /* the run that contains the crossing, and the one that ends on the last sample before it
+           (the magnitude there can be smaller than the stepping error below): generic form */
+        if (j0 < jz && jz <= j0 + R)
+            return 2u;
+        if (j0 >= jz) {
+            U = 0ull - U;
+            dU = 0ull - dU;
+            neg ^= E1_PAR_NEG;
+        }
+    }
+    int64_t D;
+    const uint64_t y = e1_carrier_start(U, dU, neg, tc_carr, lim_carr, &D);
+    return e1_sample_loop<R>(y, D, e1_sp(lut_lane), F, p->dF, win, acc, lim_carr, lim_code);
+}
+
+/* Two consecutive runs of E1C_MAX_RUN samples (tile samples j0 .. j0 + 2 E1C_MAX_RUN - 1) of one channel,
+ * with everything that does not depend on the half done once: parameter loads, the 64-bit products
+ * j0 * dH and j0 * dU (the second half adds 16 steps), the carrier step.  What is added to acc and
+ * what is flagged is, half by half, exactly what e1_run_fast<E1C_MAX_RUN> at j0 and at
+ * j0 + E1C_MAX_RUN adds and flags (same integers), so the caller repairs a flagged half with the
+ * single-run machinery.  Irregular channels -- generic form forced, a zero crossing in this tile --
+ * simply take the two single runs (the condition is the same for every thread of the tile).
+ * Returns the two halves' return codes, first half in bits 0-1, second in bits 2-3. */
+E1_HD uint32_t e1_run_fast_pair(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *acc,
+                                uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
+{
+    const int R = E1C_MAX_RUN;
+    const int jw = p->j_w;
+    const uint32_t misc = p->misc;
+    if (misc & (E1_PAR_FORCE | E1_PAR_HASZ)) {
+        const uint32_t a = e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0, acc, tc_carr, lim_carr, lim_code);
+        const uint32_t b = e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0 + R, acc + R, tc_carr, lim_carr, lim_code);
+        return a | (b << 2);
+    }
+    const uint64_t dH = p->dH, dU = p->dU;
+    const int after0 = j0 >= jw, after1 = j0 + R >= jw;
+    uint64_t H = (after0 ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * dH;
+    uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * dU;
+    const uint32_t dF = p->dF;
+    const uint32_t neg = misc & E1_PAR_NEG;
+    const e1_sptr code = e1_sp(codes) + 4u * p->code_off, lut = e1_sp(lut_lane);
+    uint32_t rc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int h = 0; h < 2; h++) {
+        const int jh = j0 + h * R;
+        if (h == 1) {
+            U += (uint64_t)R * dU;
+            /* the second half continues the first one's code phase unless the code wrapped in between */
+            H = after1 != after0 ? p->HB + (uint64_t)(uint32_t)jh * dH : H + (uint64_t)R * dH;
+        }
+        const uint32_t win = e1_code_window(p, code, H, jh, R, jw);
+        int64_t D;
+        const uint64_t y = e1_carrier_start(U, dU, neg, tc_carr, lim_carr, &D);
+        rc |= e1_sample_loop<E1C_MAX_RUN>(y, D, lut, (uint32_t)(H >> 19), dF, win, acc + h * R, lim_carr, lim_code) << (2 * h);
+    }
+    return rc;
 }
 
 /* acc = I + 65536*Q  ->  the sink's little-endian (int16 I, int16 Q) pair (:536-537) */

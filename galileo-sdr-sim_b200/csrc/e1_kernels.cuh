@@ -605,4 +605,135 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
         atomicAdd(&A.counters[0], s_cnt);
 }
 
+/* ------------------------------------------------------------------ synthesis, paired runs
+ * Same work as e1_synth_kernel<16> with 32 consecutive samples per thread (e1_run_fast_pair: the
+ * per-(thread, channel) set-up -- a third of the instructions of the 16-sample kernel -- is paid once
+ * per 32 samples).  A tile is still 8192 samples (one code wrap per tile at most), so a tile needs
+ * 256 threads: the CTA's 512 threads are two TEAMS of 256 that walk their own tiles independently --
+ * own parameter buffers, own mbarriers, own named barrier -- and share the code and carrier tables. */
+#define E1_TEAM_THREADS 256
+#define E1_PAIR_RUN (2 * E1C_MAX_RUN)
+
+__device__ __forceinline__ void e1_team_sync(int team)
+{
+    asm volatile("bar.sync %0, %1;" : : "r"(1 + team), "n"(E1_TEAM_THREADS) : "memory");
+}
+
+__global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_pair_kernel(const e1_synth_args A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *s_lut = smem_raw + E1_CODES_BYTES;
+    const uint32_t blk_bytes = (uint32_t)e1_blk_bytes(A.max_chan);
+    __shared__ __align__(8) uint64_t s_bar[5]; /* [0] tables, [1 + 2 team + b] parameter buffer b of a team */
+    __shared__ unsigned long long s_cnt;
+    __shared__ long s_tile[2][2]; /* [team][b]: tile number whose block is (being) loaded into that buffer */
+
+    const int tid = threadIdx.x, team = tid >> 8, t = tid & (E1_TEAM_THREADS - 1);
+    unsigned char *s_blk0 = smem_raw + E1_CODES_BYTES + E1_LUT_BYTES + (size_t)team * 2 * blk_bytes;
+    uint64_t *bar = &s_bar[1 + 2 * team];
+    const long total_tiles = (long)A.n_epochs * A.tiles_per_epoch;
+    const long first_wave = 2l * gridDim.x;
+    long next_id = 0; /* team leader: the tile after the one in s_tile[team][...] */
+    if (tid == 0) {
+        s_cnt = 0;
+        for (int i = 0; i < 5; i++)
+            e1_mbar_init(&s_bar[i], 1);
+        e1_mbar_init_fence();
+        if (A.use_bulk) {
+            e1_mbar_expect(&s_bar[0], E1_CODES_BYTES + E1_LUT_BYTES);
+            e1_bulk_g2s(s_codes, A.codes, E1_CODES_BYTES, &s_bar[0]);
+            e1_bulk_g2s(s_lut, A.lut, E1_LUT_BYTES, &s_bar[0]);
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        const long first = 2l * blockIdx.x + team;
+        s_tile[team][0] = first;
+        if (first < total_tiles) {
+            e1_mbar_expect(&bar[0], blk_bytes);
+            e1_bulk_g2s(s_blk0, A.blk + (size_t)first * blk_bytes, blk_bytes, &bar[0]);
+        }
+        next_id = first_wave + atomicAdd(A.next_tile, 1u);
+    }
+    __syncthreads();
+    if (A.use_bulk) {
+        e1_mbar_wait(&s_bar[0], 0);
+    } else {
+        for (int i = tid; i < E1_CODES_BYTES / 4; i += E1_SYNTH_THREADS)
+            s_codes[i] = A.codes[i];
+        for (int i = tid; i < E1_LUT_ENTRIES; i += E1_SYNTH_THREADS)
+            reinterpret_cast<int32_t *>(s_lut)[i] = A.lut[i];
+        __syncthreads();
+    }
+
+    const unsigned char *lut_lane = s_lut + 4 * (tid & (E1C_LUT_REP - 1)); /* this lane's copy of every entry */
+    const uint32_t lim_carr = e1_lim_carr(A.tc_carr, A.thr_carr), lim_code = e1_lim_code(A.tc_code, A.thr_code);
+    const int j0 = t * E1_PAIR_RUN;
+    unsigned long long n_exact = 0;
+    for (int it = 0;; it++) {
+        const int b = it & 1;
+        const long tile_id = s_tile[team][b];
+        if (tile_id >= total_tiles)
+            break;
+        /* the whole team is past the previous tile (barrier at the end of the loop body), so the other
+           buffer is free: start the next tile's block now, then draw the tile after it */
+        if (t == 0) {
+            s_tile[team][1 - b] = next_id;
+            if (next_id < total_tiles) {
+                e1_mbar_expect(&bar[1 - b], blk_bytes);
+                e1_bulk_g2s(s_blk0 + (size_t)(1 - b) * blk_bytes, A.blk + (size_t)next_id * blk_bytes, blk_bytes, &bar[1 - b]);
+                next_id = first_wave + atomicAdd(A.next_tile, 1u);
+            }
+        }
+        e1_mbar_wait(&bar[b], (uint32_t)(it >> 1) & 1u);
+        const unsigned char *blk = s_blk0 + (size_t)b * blk_bytes;
+        const int nact = *reinterpret_cast<const int *>(blk);
+        const e1_chan_par *par = reinterpret_cast<const e1_chan_par *>(blk + E1C_BLK_HEADER);
+        const int e = (int)(tile_id / A.tiles_per_epoch), tt = (int)(tile_id - (long)e * A.tiles_per_epoch);
+        const int n_valid = min(A.tile, A.n_samp - tt * A.tile);
+
+        if (j0 < n_valid) {
+            int acc[E1_PAIR_RUN];
+#pragma unroll
+            for (int i = 0; i < E1_PAIR_RUN; i++)
+                acc[i] = 0;
+            for (int a = 0; a < nact; a++) {
+                const uint32_t rc = e1_run_fast_pair(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code);
+                if (rc) { /* rare: a half of this (thread, channel) goes through the generic form */
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        if ((rc >> (2 * h)) & 3u) {
+                            int d[E1C_MAX_RUN];
+                            e1_fix_run<E1C_MAX_RUN>(&par[a], s_codes, lut_lane, j0 + h * E1C_MAX_RUN, d, A.thr_carr, A.thr_code, A.tc_carr,
+                                                    A.tc_code, &n_exact);
+#pragma unroll
+                            for (int i = 0; i < E1C_MAX_RUN; i++)
+                                acc[h * E1C_MAX_RUN + i] += d[i];
+                        }
+                }
+            }
+            /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
+            int16_t *dst = A.out + ((size_t)e * A.n_samp + (size_t)tt * A.tile + j0) * 2;
+            if (A.vec_ok && j0 + E1_PAIR_RUN <= n_valid) {
+#pragma unroll
+                for (int i = 0; i < E1_PAIR_RUN; i += 4)
+                    *reinterpret_cast<uint4 *>(dst + 2 * i) =
+                        make_uint4(e1_pack_iq(acc[i]), e1_pack_iq(acc[i + 1]), e1_pack_iq(acc[i + 2]), e1_pack_iq(acc[i + 3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < E1_PAIR_RUN; i++)
+                    if (j0 + i < n_valid)
+                        *reinterpret_cast<uint32_t *>(dst + 2 * i) = e1_pack_iq(acc[i]);
+            }
+        }
+        e1_team_sync(team); /* all reads of this tile's block (and of s_tile[team][b]) are done */
+    }
+    if (n_exact)
+        atomicAdd(&s_cnt, n_exact);
+    __syncthreads();
+    if (tid == 0 && A.counters && s_cnt)
+        atomicAdd(&A.counters[0], s_cnt);
+}
+
 #endif /* E1_KERNELS_CUH */

@@ -24,6 +24,7 @@ struct e1b200_ctx {
     double delt;        /* 1/fs, as the reference computes it (src/galileo-sdr.cpp:162) */
     int tile;           /* samples per planner checkpoint / synthesis tile              */
     int run;            /* consecutive samples per thread: tile = 512 * run             */
+    int pair;           /* run == 16: two runs per thread, two 256-thread teams per CTA (e1_synth_pair_kernel) */
     int tiles_per_epoch;
     int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
     int plan_epochs;    /* epochs per planner pass (bounds scratch)                     */
@@ -104,8 +105,10 @@ static int env_int(const char *name, int dflt)
 }
 
 typedef void (*synth_fn)(const e1_synth_args);
-static synth_fn synth_for(int run)
+static synth_fn synth_for(int run, int pair = 0)
 {
+    if (pair)
+        return e1_synth_pair_kernel;
     switch (run) {
     case 4: return e1_synth_kernel<4>;
     case 8: return e1_synth_kernel<8>;
@@ -152,6 +155,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
         ctx->cfg.dt_epoch = 0.10000002314200000; /* src/galileo-sdr.cpp:347 */
     ctx->delt = 1.0 / cfg->fs_hz;
     ctx->run = run;
+    ctx->pair = (run == E1C_MAX_RUN) && !env_int("E1B200_NO_PAIR", 0);
     ctx->tile = run * E1_SYNTH_THREADS;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
     ctx->geo = e1_span_geometry(ctx->tiles_per_epoch);
@@ -167,11 +171,11 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     long pe = (long)(((size_t)env_int("E1B200_PLAN_MB", 2048) << 20) / ck_epoch_bytes);
     ctx->plan_epochs = pe < 1 ? 1 : (pe > 4096 ? 4096 : (int)pe);
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + 2 * (int)e1_blk_bytes(cfg->max_chan);
+    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + (ctx->pair ? 4 : 2) * (int)e1_blk_bytes(cfg->max_chan);
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    synth_fn fn = synth_for(run);
+    synth_fn fn = synth_for(run, ctx->pair);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, E1_SYNTH_THREADS, ctx->smem_bytes));
@@ -410,13 +414,14 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     A.use_bulk = ctx->use_bulk;
     long total_tiles = (long)n * ctx->tiles_per_epoch;
     long grid = (long)ctx->sm_count * ctx->ctas_per_sm;
-    if (grid > total_tiles)
-        grid = total_tiles;
+    const long cta_tiles = ctx->pair ? (total_tiles + 1) / 2 : total_tiles; /* a paired-run CTA starts on two tiles */
+    if (grid > cta_tiles)
+        grid = cta_tiles;
     CK(cudaMemsetAsync(ctx->d_next_tile, 0, sizeof(unsigned int), ctx->stream));
     int rc = mark(ctx, 1, 0);
     if (rc)
         return rc;
-    synth_for(ctx->run)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
+    synth_for(ctx->run, ctx->pair)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     ctx->timing.synth_launches += 1;

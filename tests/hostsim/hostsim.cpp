@@ -160,6 +160,35 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
             int16_t *o = out + ((size_t)e * n_samp + (size_t)t * tile) * 2;
+            if (run == E1C_MAX_RUN) { // e1_synth_pair_kernel: 256 threads per tile, two runs of 16 samples each
+                for (int tid = 0; tid < threads / 2; tid++) {
+                    const int j0 = tid * 2 * run;
+                    if (j0 >= n_valid)
+                        continue;
+                    const unsigned char *lut_lane = (const unsigned char *)lut + 4 * (tid & (E1C_LUT_REP - 1));
+                    int acc[2 * E1C_MAX_RUN] = {0};
+                    for (int a = 0; a < nact; a++) {
+                        const uint32_t rc = e1_run_fast_pair(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code);
+                        for (int h = 0; h < 2; h++) {
+                            if (!((rc >> (2 * h)) & 3u))
+                                continue;
+                            stats[2]++; // e1_fix_run
+                            int tt[E1C_MAX_RUN] = {0}, g[E1C_MAX_RUN];
+                            e1_run_fast<16>(&par[a], codes.data(), lut_lane, j0 + h * run, tt, tc_carr, lim_carr, lim_code);
+                            e1_channel_run(&par[a], codes.data(), lut_lane, j0 + h * run, run, g, thr_carr, thr_code, e1_bias_h(tc_code), &stats[0]);
+                            for (int i = 0; i < run; i++)
+                                acc[h * run + i] += g[i] - tt[i];
+                        }
+                    }
+                    for (int i = 0; i < 2 * run; i++)
+                        if (j0 + i < n_valid) {
+                            uint32_t w = e1_pack_iq(acc[i]);
+                            o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
+                            o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
+                        }
+                }
+                continue;
+            }
             for (int tid = 0; tid < threads; tid++) { // e1_synth_kernel, one thread
                 const int j0 = tid * run;
                 if (j0 >= n_valid)

@@ -2,10 +2,10 @@
 # One GPU round trip: parity tests, bench cfg2 + cfg3s, optional ncu capture.  Usage (under gpurun):
 #   tools/gpu_check.sh <tag> [ncu]
 tag=$1
-python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_gpu_tests.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_gpu_tests.log 2>&1
 tail -3 gpurun_out/${tag}_gpu_tests.log
-python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_cfg2.json 2> gpurun_out/${tag}_bench_cfg2.err
-python bench.py --no-cpu-baseline --workload cfg3s > gpurun_out/${tag}_bench_cfg3s.json 2> gpurun_out/${tag}_bench_cfg3s.err
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_cfg2.json 2> gpurun_out/${tag}_bench_cfg2.err
+timeout 300 python bench.py --no-cpu-baseline --workload cfg3s > gpurun_out/${tag}_bench_cfg3s.json 2> gpurun_out/${tag}_bench_cfg3s.err
 python - <<PY
 import json
 for w in ("cfg2", "cfg3s"):
@@ -16,6 +16,6 @@ for w in ("cfg2", "cfg3s"):
         print(w, "failed", e)
 PY
 if [ "$2" = "ncu" ]; then
-    ncu --set full --clock-control none --import-source on -k regex:e1_synth -c 1 -o gpurun_out/${tag}_synth_full python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:e1_synth -c 1 -o gpurun_out/${tag}_synth_full python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1
     tail -1 gpurun_out/${tag}_ncu.log
 fi
