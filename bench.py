@@ -77,6 +77,51 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+try:
+    ALL_CPUS = os.sched_getaffinity(0)
+except Exception:
+    ALL_CPUS = None
+
+
+def unbind_cpus():
+    """The CPU baseline uses every host core again."""
+    if ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, ALL_CPUS)
+        except Exception:
+            pass
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs
+    off: D2H into memory of the other socket costs PCIe bandwidth (the e2e arm is a 3 GB copy per step)
+    and with 8 ranks everybody would otherwise crowd node 0.  Returns the node number or None."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bdf = out.splitlines()[0].strip()
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -260,6 +305,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
 
     fs_nom, n_samp, n_chan, n_epochs, desc = wl
     fs = U.fs_as_reference(fs_nom)
@@ -373,7 +419,8 @@ def main():
             "config": {"workload": desc, "fs_hz": fs_nom, "channels": n_chan, "blocks_per_step": n_epochs,
                        "samples_per_step_per_gpu": samples_per_step, "tile": st.tile, "ctas_per_sm": st.ctas_per_sm,
                        "l2": f"each step writes {out_bytes / 1e9:.2f} GB per GPU (> 126 MB L2), no flush needed",
-                       "shard": "time axis, one contiguous segment per rank, no data-path collective"},
+                       "shard": "time axis, one contiguous segment per rank, no data-path collective",
+                       "host_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "kernel": "e1_synth_kernel", "peak_source": peak_src,
@@ -391,6 +438,7 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
+            unbind_cpus()
             ref = reference_binary_cfg1() if args.workload == "cfg1" else None
             line["cpu_baseline"] = ref or cpu_baseline(fs, n_samp, n_chan)
             if args.workload != "cfg1":
