@@ -98,14 +98,17 @@ def bind_to_gpu_numa_node(local_rank):
     and with 8 ranks everybody would otherwise crowd node 0.  Returns the node number or None."""
     try:
         import torch
-        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bdf is None:
-            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+        pr = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
+        else:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = vis.split(",")[local_rank] if vis else str(local_rank)
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx],
                                  capture_output=True, text=True, timeout=20).stdout.strip()
-            bdf = out.splitlines()[0].strip()
-        bdf = bdf.lower()
-        if len(bdf.split(":")[0]) == 8:          # nvidia-smi prints an 8-digit domain, sysfs uses 4
-            bdf = bdf[4:]
+            bdf = out.splitlines()[0].strip().lower()
+            if len(bdf.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+                bdf = bdf[4:]
         node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
         if node < 0:
             return None
@@ -291,6 +294,12 @@ def main():
         run_reference(args, wl)
         return
 
+    # stdout carries exactly one JSON line: anything a library prints there while we run (NCCL's version
+    # banner does, whatever NCCL_DEBUG_FILE says) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import e1b200 as E
     import e1util as U
@@ -445,7 +454,8 @@ def main():
                 rb = reference_binary_cfg1()
                 if rb:
                     line["reference_binary_configs0"] = rb      # the real executable on its own runnable case, for scale
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     synth.close()
     if dist is not None:
         dist.barrier()
