@@ -83,6 +83,19 @@ E1_HD double e1_from_bits(int64_t b)
 }
 E1_HD double e1_fabs(double x) { return e1_from_bits(e1_bits(x) & 0x7fffffffffffffffLL); }
 
+/* floor(num / d) for 0 <= num < 2^53, 1 <= d < 2^53 (mantissa distances inside one binade).  On the
+ * device a 64-bit integer division is a ~100-instruction subroutine and was half of the planner's
+ * instructions; both operands are exact as doubles, and a quotient rounded DOWN has the same integer
+ * part as the true one (every integer below 2^53 is representable, rounding down is monotone). */
+E1_HD int64_t e1_div_binade(int64_t num, int64_t d)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2ll_rz(__ddiv_rd(__ll2double_rn(num), __ll2double_rn(d)));
+#else
+    return num / d;
+#endif
+}
+
 /* One literal reference step of the carrier recurrence (src/galileo-sdr.cpp:531-532). */
 E1_HD double e1_carr_step(double phi, double sp)
 {
@@ -143,7 +156,7 @@ E1_HD double e1_walk_up(double x, double s, double limit, int64_t *k, int64_t k_
         if (lim_bits < end)
             end = lim_bits;
         kk++;                           /* now at x2 */
-        int64_t n = (end - 1 - b2) / d; /* >= 1 because x3 qualified */
+        int64_t n = e1_div_binade(end - 1 - b2, d); /* >= 1 because x3 qualified */
         int64_t room = k_target - kk;
         if (n > room)
             n = room;
@@ -185,7 +198,7 @@ E1_HD double e1_walk_down(double x, double s, int64_t *k, int64_t k_target, int 
         }
         int64_t floor_bits = (b1 >> 52) << 52; /* 2^e: still inside the binade */
         kk++;                                  /* now at x2 */
-        int64_t n = (b2 - floor_bits) / d;     /* >= 1 */
+        int64_t n = e1_div_binade(b2 - floor_bits, d); /* >= 1 */
         int64_t room = k_target - kk;
         if (n > room)
             n = room;
@@ -610,7 +623,7 @@ E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile
         if (d == 0)
             n = k_end - k; /* stuck for good */
         else {
-            n = (end - 1 - b2) / d;
+            n = e1_div_binade(end - 1 - b2, d);
             if (n > k_end - k)
                 n = k_end - k;
         }
