@@ -42,9 +42,34 @@ WORKLOADS = {
     "cfg2": (2.6e6, 260000, 36, 2999, "BASELINE configs[1]: static, 2.6 MS/s, 36 ch, 300 s (2999 blocks)"),
     "cfg3": (25e6, 2500000, 36, 2999, "BASELINE configs[2]: static, 25 MS/s, 36 ch, 300 s (2999 blocks)"),
     "cfg3s": (25e6, 2500000, 36, 300, "BASELINE configs[2] slice: 25 MS/s, 36 ch, 30 s (300 blocks)"),
+    "cfg4s": (25e6, 2500000, 36, 300, "BASELINE configs[3] slice: dynamic receiver, 25 MS/s, 36 ch, 30 s (300 blocks), per-block "
+                                      "Doppler/code-phase restate on the device from pseudorange records"),
 }
 METRIC = "E1B/C IQ Msamples/sec"
 UNIT = "Msamples/s"
+
+
+def synthetic_range_records(n_epochs, n_chan, dtype, seed=0, dt=0.100000023142, grx0=43200.0):
+    """Pseudorange-level inputs for the device-side restate (e1_range_rec): per channel a range of
+    2.2-2.6e7 m, a range rate of +-760 m/s (+-4 kHz of Doppler) and an acceleration of +-0.5 m/s^2 (a
+    moving receiver), random pages."""
+    rng = np.random.default_rng(seed)
+    rr = np.zeros((n_epochs, n_chan), dtype)
+    t0 = (np.arange(n_epochs) * dt)[:, None]
+    t1 = t0 + dt
+    rho0, v, a = rng.uniform(2.2e7, 2.6e7, n_chan)[None, :], rng.uniform(-760, 760, n_chan)[None, :], rng.uniform(-0.5, 0.5, n_chan)[None, :]
+    rr["prn"] = (np.arange(n_chan) % 50 + 1)[None, :]
+    rr["rho_prev"] = rho0 + v * t0 + 0.5 * a * t0 * t0
+    rr["rho_cur"] = rho0 + v * t1 + 0.5 * a * t1 * t1
+    rr["grx_sec"] = grx0 + t1
+    rr["flags"][0] = 1                                            # E1_REC_SET_PHASE
+    rr["carr_phase_init"][0] = rng.uniform(0, 1, n_chan)
+    pages = rng.integers(0, 256, (n_chan, 64), dtype=np.uint8)
+    pages[:, 62] &= 0x0F                                           # 500 symbols: bits 500..511 stay zero
+    pages[:, 63] = 0
+    rr["page_cur"] = pages[None, :, :]
+    rr["page_next"] = pages[None, :, :]
+    return rr
 
 
 def ncu_summary_numbers():
@@ -332,6 +357,10 @@ def main():
         except Exception as ex:
             print(f"bench: host records unavailable ({ex}); synthetic records instead", file=sys.stderr)
             recs = None
+    use_ranges = args.workload.startswith("cfg4")
+    rec_dtype = E.RANGE_DTYPE if use_ranges else U.REC_DTYPE
+    if use_ranges:
+        recs = synthetic_range_records(n_epochs, n_chan, E.RANGE_DTYPE, seed=1000 + rank)
     if recs is None:
         recs = U.synthetic_recs_fast(n_epochs, n_chan, fs, seed=1000 + rank)     # each rank: its own time shard
     rec_bytes = recs.nbytes
@@ -358,8 +387,10 @@ def main():
         return float(t.item())
 
     # ---- device-resident arm -------------------------------------------------------------
+    dev_call = synth.synth_ranges_device if use_ranges else synth.synth_epochs_device
+    host_call = synth.synth_ranges if use_ranges else synth.synth_epochs
     for _ in range(args.warmup):
-        synth.synth_epochs_device(n_epochs, d_recs.data_ptr(), d_out.data_ptr())
+        dev_call(n_epochs, d_recs.data_ptr(), d_out.data_ptr())
         synth.sync()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -369,7 +400,7 @@ def main():
     synth_ms, plan_ms, launches, synth_launches = 0.0, 0.0, 0, 0
     ev0.record(ext)
     for _ in range(args.steps):
-        synth.synth_epochs_device(n_epochs, d_recs.data_ptr(), d_out.data_ptr())
+        dev_call(n_epochs, d_recs.data_ptr(), d_out.data_ptr())
         synth.sync()                      # also collects the per-kernel CUDA-event times of this step
         t = synth.timing()
         synth_ms += t.synth_ms
@@ -388,20 +419,20 @@ def main():
         h_recs = E.PinnedBuffer(rec_bytes)
         h_recs.u8[:] = recs.view(np.uint8).reshape(-1)
         h_out = E.PinnedBuffer(out_bytes)
-        recs_view = h_recs.view(U.REC_DTYPE).reshape(n_epochs, n_chan)
+        recs_view = h_recs.view(rec_dtype).reshape(n_epochs, n_chan)
         out_view = h_out.view(np.int16)
         for _ in range(max(1, min(args.warmup, 2))):
-            synth.synth_epochs(recs_view, out_view)
+            host_call(recs_view, out_view)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            synth.synth_epochs(recs_view, out_view)       # returns after the last D2H completed
+            host_call(recs_view, out_view)                # returns after the last D2H completed
         torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
         barrier()
         e2e = {"value": world * samples_per_step / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": rec_bytes, "d2h_bytes_per_step": out_bytes,
-               "api": "e1b200_synth_epochs (host buffers, pinned), timed on the host clock around the call"}
+               "api": ("e1b200_synth_ranges" if use_ranges else "e1b200_synth_epochs") + " (host buffers, pinned), timed on the host clock around the call"}
         h_recs.free(), h_out.free()
 
     if rank == 0:
