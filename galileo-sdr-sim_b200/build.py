@@ -32,7 +32,7 @@ def nvcc_path():
 
 
 def build_lib(force=False, verbose=False, defines=(), out=None):
-    """defines / out: tuning builds (e.g. defines=["E1_VARIANT=2"], out=lib/libe1b200_v2.so)."""
+    """defines / out: tuning builds (extra -D flags, alternative output path; select one at run time with E1B200_LIB=<path>)."""
     lib = Path(out) if out else LIB
     if not force and lib.exists() and all(lib.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return lib
