@@ -120,6 +120,11 @@ def test_internal_batching_and_no_tma_path(monkeypatch):
     s = E.Synth(fs, n_samp, nch)
     assert np.array_equal(s.synth_epochs(recs), ref)
     s.close()
+    monkeypatch.delenv("E1B200_NO_TMA")
+    monkeypatch.setenv("E1B200_NO_PAIR", "1")                # 16 samples per thread, one team (e1_synth_kernel<16>)
+    s = E.Synth(fs, n_samp, nch)
+    assert np.array_equal(s.synth_epochs(recs), ref)
+    s.close()
 
 
 def test_parallel_planner_equals_serial_planner(monkeypatch):
