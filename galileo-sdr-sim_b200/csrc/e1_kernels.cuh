@@ -164,6 +164,7 @@ __device__ __forceinline__ e1_tile_ck *e1_unit_ck(const e1_plan_args &P, int u, 
  * run from its true start. */
 #define E1_SERIAL_THREADS 128
 #define E1_SERIAL_CHUNK 128
+#define E1_CHAIN_THREADS 256 /* chain kernel: one span per thread per round, 256 spans per round */
 
 __device__ __forceinline__ double e1_fold1(double v) /* into (-1,1), sign kept (like :532) */
 {
@@ -294,13 +295,13 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
  * of the chunk is an ordinary accepted guess (HAT unit, anchored on its predecessor's last wrap, no
  * tie wrap, lo <= D < hi) the chunk is done; otherwise thread 0 walks that chunk with
  * e1_v2_chain_step exactly as the serial chain would. */
-__global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1_plan_args P)
+__global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_plan_args P)
 {
-    __shared__ __align__(16) e1_unit s_units[E1_SERIAL_CHUNK];
-    __shared__ double s_sp[E1_SERIAL_CHUNK];
-    __shared__ int s_n[E1_SERIAL_CHUNK];
-    __shared__ e1_trans s_delta[E1_SERIAL_CHUNK];
-    __shared__ double s_warp[E1_SERIAL_THREADS / 32];
+    __shared__ __align__(16) e1_unit s_units[E1_CHAIN_THREADS];
+    __shared__ double s_sp[E1_CHAIN_THREADS];
+    __shared__ int s_n[E1_CHAIN_THREADS];
+    __shared__ e1_trans s_delta[E1_CHAIN_THREADS];
+    __shared__ double s_warp[E1_CHAIN_THREADS / 32];
     __shared__ e1_chain_state s_cs;
     __shared__ int s_bad;
     const int ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -310,84 +311,130 @@ __global__ void __launch_bounds__(E1_SERIAL_THREADS) e1_v2_chain_kernel(const e1
     unsigned long long st[2] = {0, 0};
     if (tid == 0)
         e1_chain_init(&s_cs, P.phase[ch]);
-    for (int e0 = 0; e0 < P.n_units; e0 += E1_SERIAL_CHUNK) {
-        const int n = min(E1_SERIAL_CHUNK, P.n_units - e0);
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.units + o + e0);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_units);
-        for (int i = tid; i < n * (int)(sizeof(e1_unit) / 16); i += E1_SERIAL_THREADS)
-            dst[i] = src[i];
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS) {
-            s_sp[i] = P.prep[o + e0 + i].sp;
-            s_n[i] = P.prep[o + e0 + i].n;
+    /* The rounds are serial (each starts from the state the previous one leaves) and short, so the
+       global-memory latency of a round's inputs would be most of its time: every thread fetches ITS span
+       of the next round into registers before the current round's scan. */
+    uint4 pf[sizeof(e1_unit) / 16];
+    double pf_sp = 0.0;
+    int pf_n = 0;
+    auto fetch = [&](int e0) {
+        if (e0 + tid < P.n_units) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.units + o + e0 + tid);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(e1_unit) / 16); i++)
+                pf[i] = src[i];
+            pf_sp = P.prep[o + e0 + tid].sp;
+            pf_n = P.prep[o + e0 + tid].n;
         }
+    };
+    fetch(0);
+    for (int e0 = 0; e0 < P.n_units; e0 += E1_CHAIN_THREADS) {
+        const int n = min(E1_CHAIN_THREADS, P.n_units - e0);
+        if (tid < n) {
+            uint4 *dst = reinterpret_cast<uint4 *>(&s_units[tid]);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(e1_unit) / 16); i++)
+                dst[i] = pf[i];
+            s_sp[tid] = pf_sp;
+            s_n[tid] = pf_n;
+        }
+        fetch(e0 + E1_CHAIN_THREADS);
         if (tid == 0)
             s_bad = 0;
         __syncthreads();
-        /* optimistic pass: thread t owns span e0 + t */
-        double x = 0.0;
-        int ok = 1;
-        if (tid < n) {
-            const e1_unit *u = &s_units[tid];
-            int p_ok, p_neg, p_k;
-            double p_last;
-            if (tid == 0) {
-                p_ok = s_cs.prev_ok && s_cs.prev_u == e0 - 1, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_last = s_cs.prev_p;
-            } else {
-                const e1_unit *q = &s_units[tid - 1];
-                p_ok = q->last_k >= 1, p_neg = q->neg, p_k = q->last_k, p_last = q->last_p;
+        /* Optimistic pass over spans [start, n) of the round, thread t owns span e0 + t: assume every span
+           is a regular HAT span anchored in its predecessor, scan the translations, validate.  The prefix
+           up to the first span that is not (guess rejected, tie wrap, phase reset, idle slot, sign change,
+           no wrap to anchor on) is committed, thread 0 takes that ONE span through the serial chain step,
+           and the pass resumes behind it.  (A round that keeps failing -- a channel at very low Doppler has
+           no wrap in most spans -- goes to the serial chain for its remainder.) */
+        int start = 0, restarts = 0;
+        while (start < n) {
+            double x = 0.0;
+            int ok = 1;
+            if (tid >= start && tid < n) {
+                const e1_unit *u = &s_units[tid];
+                int p_ok, p_neg, p_k;
+                double p_last;
+                if (tid == start) {
+                    p_ok = s_cs.prev_ok && s_cs.prev_u == e0 + start - 1, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_last = s_cs.prev_p;
+                } else {
+                    const e1_unit *q = &s_units[tid - 1];
+                    p_ok = q->last_k >= 1, p_neg = q->neg, p_k = q->last_k, p_last = q->last_p;
+                }
+                ok = u->type == E1_UNIT_HAT && u->tie == 0 && u->anchor_back == 1 && p_ok && p_neg == u->neg && p_k == u->anchor_k;
+                x = ok ? __dadd_rn(p_last, -u->anchor_p) : 0.0;
             }
-            ok = u->type == E1_UNIT_HAT && u->tie == 0 && u->anchor_back == 1 && p_ok && p_neg == u->neg && p_k == u->anchor_k;
-            x = ok ? __dadd_rn(p_last, -u->anchor_p) : 0.0;
-        }
-        /* inclusive scan of x over the block (exact additions) */
-        double D = x;
+            /* inclusive scan of x over the block (exact additions: every term is a multiple of 2^-52) */
+            double D = x;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, D, d);
-            if (lane >= d)
-                D = __dadd_rn(D, y);
-        }
-        if (lane == 31)
-            s_warp[wid] = D;
-        __syncthreads();
-        for (int w = 0; w < wid; w++)
-            D = __dadd_rn(D, s_warp[w]);
-        if (tid < n) {
-            const e1_unit *u = &s_units[tid];
-            if (!(ok && D >= u->lo && D < u->hi))
-                atomicExch(&s_bad, 1);
-        }
-        __syncthreads();
-        if (!s_bad) {
-            if (tid < n) {
+            for (int d = 1; d < 32; d <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, D, d);
+                if (lane >= d)
+                    D = __dadd_rn(D, y);
+            }
+            if (lane == 31)
+                s_warp[wid] = D;
+            if (tid == 0)
+                s_bad = n; /* first span of [start, n) that fails */
+            __syncthreads();
+            for (int w = 0; w < wid; w++)
+                D = __dadd_rn(D, s_warp[w]);
+            if (tid >= start && tid < n) {
+                const e1_unit *u = &s_units[tid];
+                if (!(ok && D >= u->lo && D < u->hi))
+                    atomicMin(&s_bad, tid);
+            }
+            __syncthreads();
+            const int bad = s_bad;
+            if (tid >= start && tid < bad) {
                 const e1_unit *u = &s_units[tid];
                 e1_trans tr;
                 tr.a = tr.b = u->neg ? -D : D;
                 tr.k_split = 0;
                 tr.pad = 0;
                 s_delta[tid] = tr;
-                if (tid == n - 1) { /* the state the serial chain would carry out of this chunk */
+                /* the state the serial chain (e1_v2_chain_step) would carry out of this prefix: the phase after
+                   its last span, and the most recent wrap -- in the last span, or, when that one has none but
+                   stayed aligned (last_k == -1), still the one in the span before it */
+                if (tid == bad - 1) {
                     s_cs.phi = __dadd_rn(u->end_phi, tr.b);
-                    s_cs.prev_p = __dadd_rn(u->last_p, D);
-                    s_cs.prev_k = u->last_k; /* >= 1: every span of an accepted chunk but the last is an anchor, and
-                                                a last span without a wrap sends the next chunk to the serial path */
-                    s_cs.prev_u = e0 + n - 1;
-                    s_cs.prev_ok = u->last_k >= 1;
+                    if (u->last_k >= 1) {
+                        s_cs.prev_p = __dadd_rn(u->last_p, D);
+                        s_cs.prev_k = u->last_k;
+                        s_cs.prev_u = e0 + tid;
+                        s_cs.prev_ok = 1;
+                        s_cs.prev_neg = u->neg;
+                    } else if (u->last_k != -1) {
+                        s_cs.prev_ok = 0;
+                    }
+                } else if (tid == bad - 2 && s_units[bad - 1].last_k == -1) {
+                    s_cs.prev_p = __dadd_rn(u->last_p, D); /* u->last_k >= 1: span bad-1 passed the test on it */
+                    s_cs.prev_k = u->last_k;
+                    s_cs.prev_u = e0 + tid;
+                    s_cs.prev_ok = 1;
                     s_cs.prev_neg = u->neg;
                 }
             }
             if (tid == 0)
-                st[1] += (unsigned long long)n;
-        } else if (tid == 0) {
-            e1_chain_state cs = s_cs;
-            for (int i = 0; i < n; i++)
-                s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], e0 + i, s_sp[i], s_n[i], P.tile, (s_n[i] + P.tile - 1) / P.tile,
-                                              e1_unit_ck(P, e0 + i, ch), P.max_chan, st);
-            s_cs = cs;
+                st[1] += (unsigned long long)(bad - start);
+            __syncthreads();
+            if (bad >= n)
+                break;
+            const int upto = ++restarts > 8 ? n : bad + 1; /* the same in every thread */
+            if (tid == 0) {
+                e1_chain_state cs = s_cs;
+                for (int i = bad; i < upto; i++)
+                    s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], e0 + i, s_sp[i], s_n[i], P.tile, (s_n[i] + P.tile - 1) / P.tile,
+                                                  e1_unit_ck(P, e0 + i, ch), P.max_chan, st);
+                s_cs = cs;
+            }
+            start = upto;
+            __syncthreads();
         }
         __syncthreads();
-        for (int i = tid; i < n; i += E1_SERIAL_THREADS)
-            P.delta[o + e0 + i] = s_delta[i];
+        if (tid < n)
+            P.delta[o + e0 + tid] = s_delta[tid];
     }
     if (tid == 0) {
         P.phase[ch] = s_cs.phi;

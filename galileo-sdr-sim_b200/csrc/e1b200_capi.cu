@@ -31,6 +31,8 @@ struct e1b200_ctx {
     int sm_count, ctas_per_sm, smem_bytes;
     int use_bulk, amb_scale, serial_planner;
     cudaStream_t stream, copy_stream;
+    cudaStream_t side_stream;            /* planner: the code-phase pass runs here, beside the carrier chain */
+    cudaEvent_t ev_fork, ev_join;
     std::vector<cudaEvent_t> ev_buf, ev_copy; /* per staging slot: synthesis done / D2H done */
     std::vector<cudaEvent_t> ev;   /* pairs (start, end) of the current call */
     std::vector<int> ev_kind;      /* 0 = planner pass, 1 = synthesis launch */
@@ -175,6 +177,9 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     synth_fn fn = synth_for(run, ctx->pair);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
     int occ = 0;
@@ -236,6 +241,9 @@ int e1b200_destroy(e1b200_ctx *ctx)
         cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return E1B200_OK;
 }
@@ -327,7 +335,12 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
     const int nthr = n * cfg->max_chan;
     const int n_units = n * ctx->geo.spans_per_epoch, nuthr = n_units * cfg->max_chan;
     ctx->plan_n = n_units;
-    if (!carrier_only)
+    /* The code-phase pass writes the code fields of the tile checkpoints, the carrier passes only .phi:
+       the two are independent until finalize.  With the parallel planner it runs on a side stream,
+       released when the span pass is done, so that it fills the SMs the carrier chain (one block per
+       channel) leaves idle. */
+    const bool code_beside_chain = !carrier_only && !ctx->serial_planner;
+    if (!carrier_only && !code_beside_chain)
         e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
                                                                          ctx->tile, ctx->tiles_per_epoch, ctx->delt);
     if (ctx->serial_planner) {
@@ -363,7 +376,16 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         e1_v2_drift_kernel<<<(nuthr + 63) / 64, 64, 0, ctx->stream>>>(P);
         e1_v2_estimate_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         e1_v2_span_kernel<<<(nuthr + 63) / 64, 64, 0, ctx->stream>>>(P);
-        e1_v2_chain_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
+        if (code_beside_chain) {
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+            e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->side_stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
+                                                                                  ctx->tile, ctx->tiles_per_epoch, ctx->delt);
+            CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        }
+        e1_v2_chain_kernel<<<cb, E1_CHAIN_THREADS, 0, ctx->stream>>>(P);
+        if (code_beside_chain)
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         ctx->timing.kernel_launches += 7;
     }
     if (!carrier_only) {
