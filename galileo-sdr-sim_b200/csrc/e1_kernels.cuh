@@ -1,17 +1,22 @@
 /* e1_kernels.cuh -- sm_100a kernels of the Galileo E1B/C synthesiser.
  *
- *   e1_restate_kernel     computeCodePhase (src/gal-sig.cpp:308-347) per (epoch, channel)
- *   e1_plan_code_kernel   exact code-phase / symbol checkpoints per (epoch, tile, channel)
- *   e1_plan_carr_kernel   exact carrier-phase checkpoints per (epoch, tile, channel)
- *   e1_synth_kernel       the sample loop (src/galileo-sdr.cpp:481-539): per sample, all
- *                         channels, int32 accumulate, packed int16 I/Q, 128-bit stores
+ *   e1_restate_kernel        computeCodePhase (src/gal-sig.cpp:308-347) per (epoch, channel)
+ *   e1_plan_code_kernel      exact code-phase / symbol checkpoints per (epoch, tile, channel)
+ *   e1_v2_prep/ideal/drift/estimate/span/chain_kernel
+ *                            the parallel exact carrier planner (see "parallel carrier planner" in e1_core.h)
+ *   e1_plan_carr_kernel      the same checkpoints by one serial walk per channel (debug / comparison)
+ *   e1_finalize_kernel       checkpoints + translations -> one parameter block per tile
+ *   e1_synth_pair_kernel     the sample loop (src/galileo-sdr.cpp:481-539): per sample, all channels,
+ *                            int32 accumulate, packed int16 I/Q, 128-bit stores; 32 samples per thread
+ *   e1_synth_kernel<R>       the same with R = 4, 8 or 16 samples per thread (tiles shorter than 8192 samples)
  *
  * HBM layout
  *   recs   e1_epoch_rec[n_epochs][max_chan]                         176 B each (caller / H2D)
  *   ck     e1_tile_ck[n_epochs][tiles_per_epoch][max_chan]           32 B each (scratch)
+ *   blk    per tile: 16 B header + max_chan e1_chan_par (96 B), active channels first (scratch)
  *   out    int16 I,Q interleaved, sample (epoch*N + k) at byte 4*(epoch*N + k)
  *   codes  uint32[50][516]: one 2-bit field per BOC(1,1) half-chip (see e1_core.h)   103 200 B
- *   lut    int32[2][4][512]: carrier term by (phase regime, code/symbol field, index) 16 384 B
+ *   lut    int32[641][32]: carrier term by table position, one copy per lane         82 048 B
  *          both smem-resident, loaded once per persistent CTA with cp.async.bulk
  */
 #ifndef E1_KERNELS_CUH

@@ -136,7 +136,7 @@ def hostsim():
 
 
 def product_lut():
-    """int32[2][512][16] carrier table in the product's layout, built from the ORACLE's tables."""
+    """int32[641][32] carrier table in the product's layout (E1C_LUT_IDX x E1C_LUT_REP), built from the ORACLE's tables."""
     c, s = (C.c_int * 512)(), (C.c_int * 512)()
     oracle().e1o_carrier_lut(c, s)
     lut = np.zeros(hostsim().hs_lut_entries(), np.int32)

@@ -60,7 +60,7 @@ int hs_lut_entries(void) { return E1C_LUT_ENTRIES; }
 
 int hs_code_words_per_prn(void) { return E1C_CODE_WORDS_PER_PRN; }
 
-// Whole pipeline on the host.  lut: int32[2][512][16] in the product layout (passed in by the test
+// Whole pipeline on the host.  lut: int32[641][32] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
 // stats[0] = samples resolved by the literal fallback, stats[1] = planner errors,
 // stats[2] = threads that took the slow path.

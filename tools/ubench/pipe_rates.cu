@@ -64,7 +64,8 @@ PAIR(k_p_lop_shf, OP_LOP_X, OP_SHF_Y)
 PAIR(k_p_lop_add3, OP_LOP_X, OP_ADD3_Y)
 PAIR(k_p_add3_add3, OP_ADD3_X, OP_ADD3_Y)
 PAIR(k_p_lop_add2, OP_LOP_X, OP_ADD2_Y)
-/* shared-memory lookups like the carrier table's: 64-byte entries, one 4-byte copy per (lane & 15) */
+/* shared-memory lookups like the carrier table's FIRST layout (v4): 64-byte entries, one 4-byte copy per (lane & 15),
+ * random entries per lane -> lanes l and l+16 collide.  (The table now has one copy per lane.) */
 __global__ void __launch_bounds__(512, 1) k_lds(uint32_t *out, uint32_t a, uint32_t b, long long *clk)
 {
     extern __shared__ uint32_t sm[];
