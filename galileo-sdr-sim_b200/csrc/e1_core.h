@@ -294,7 +294,7 @@ E1_HD uint32_t e1_thr_code(int T, int scale)
  * 2*(cos + 65536*sin) of the reference's table index t(e) (include/constants.h:216-284):
  *     e in [0, 512]          t = e & 511
  *     e in [-EXT, -1]        t = 511 + e        (below: where a run that will wrap starts, phase >= 0)
- *     e in [513, 512 + EXT]  t = e - 511        (above: the same for phase < 0)
+ *     e in [513, 513 + EXT]  t = e - 511        (above: the same for phase < 0)
  * With i = trunc(511 |phi|) in [0, 510] the reference reads index i for phi >= 0 and (-i) & 511 for
  * phi < 0 (src/galileo-sdr.cpp:509-510).  The sample loop multiplies an UNWRAPPED magnitude across a
  * carrier wrap (phi -= (long)phi, :532): 511 (|phi| + 1) has the same fraction and an index exactly
@@ -306,7 +306,11 @@ E1_HD uint32_t e1_thr_code(int T, int scale)
  * are (with 16 copies lanes l and l+16 collided on almost every load).                           */
 #define E1C_LUT_REP 32
 #define E1C_LUT_EXT 64
-#define E1C_LUT_IDX (513 + 2 * E1C_LUT_EXT)
+/* 513 + 2 EXT positions are reachable by unambiguous samples; one more at the top because an AMBIGUOUS
+ * sample of a mirrored run reads one entry too high (see e1_carrier_start): the run is redone, but the
+ * fast form's terms are taken back out by recomputing them, so that read has to be inside the table
+ * (what lies behind it in shared memory -- a parameter buffer -- can change between the two reads). */
+#define E1C_LUT_IDX (514 + 2 * E1C_LUT_EXT)
 #define E1C_LUT_ENTRIES (E1C_LUT_IDX * E1C_LUT_REP)
 #define E1C_THREADS 512 /* synthesis CTA: thread t owns samples [t*R, (t+1)*R) of the tile */
 #define E1C_MAX_RUN 16
@@ -1153,6 +1157,9 @@ static __device__ __forceinline__ uint32_t e1_ld32(e1_sptr a)
     return v;
 }
 #else
+#if defined(E1_CHECK_LUT_BOUNDS)
+static unsigned long long e1_lut_oob = 0;
+#endif
 typedef const unsigned char *e1_sptr;
 static inline e1_sptr e1_sp(const void *p) { return (const unsigned char *)p; }
 static inline uint32_t e1_ld32(e1_sptr a) { return *(const uint32_t *)a; }
@@ -1199,6 +1206,10 @@ E1_HD uint32_t e1_sample_loop(uint64_t y, int64_t D, e1_sptr lut_lane, uint32_t 
 #if defined(__CUDA_ARCH__)
         const int w = (int)e1_ld32(e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, lut_lane));
 #else
+#if defined(E1_CHECK_LUT_BOUNDS) /* host test build: every lookup of the fast form must stay inside the table */
+        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT_IDX)
+            e1_lut_oob++;
+#endif
         const int w = (int)e1_ld32(lut_lane + (uint32_t)(y >> 32) * (4u * E1C_LUT_REP));
 #endif
         acc[i] += w * ((int)win >> 30);

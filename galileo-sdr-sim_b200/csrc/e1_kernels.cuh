@@ -16,7 +16,7 @@
  *   blk    per tile: 16 B header + max_chan e1_chan_par (96 B), active channels first (scratch)
  *   out    int16 I,Q interleaved, sample (epoch*N + k) at byte 4*(epoch*N + k)
  *   codes  uint32[50][516]: one 2-bit field per BOC(1,1) half-chip (see e1_core.h)   103 200 B
- *   lut    int32[641][32]: carrier term by table position, one copy per lane         82 048 B
+ *   lut    int32[642][32]: carrier term by table position, one copy per lane         82 176 B
  *          both smem-resident, loaded once per persistent CTA with cp.async.bulk
  */
 #ifndef E1_KERNELS_CUH

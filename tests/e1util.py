@@ -129,6 +129,7 @@ def hostsim():
         hs.hs_synth_epochs.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         hs.hs_synth_epochs_p.argtypes = hs.hs_synth_epochs.argtypes + [C.c_int]
+        hs.hs_lut_oob.restype = C.c_ulonglong
         hs.hs_plan_compare.restype = C.c_long
         hs.hs_plan_compare.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _hostsim = hs
@@ -136,7 +137,7 @@ def hostsim():
 
 
 def product_lut():
-    """int32[641][32] carrier table in the product's layout (E1C_LUT_IDX x E1C_LUT_REP), built from the ORACLE's tables."""
+    """int32[642][32] carrier table in the product's layout (E1C_LUT_IDX x E1C_LUT_REP), built from the ORACLE's tables."""
     c, s = (C.c_int * 512)(), (C.c_int * 512)()
     oracle().e1o_carrier_lut(c, s)
     lut = np.zeros(hostsim().hs_lut_entries(), np.int32)
@@ -158,6 +159,7 @@ def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1, p
     rc = hostsim().hs_synth_epochs_p(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, out.ctypes.data,
                                      groups, amb_scale, lut.ctypes.data, st.ctypes.data, planner)
     assert rc == 0, f"hostsim planner errors: {st}"
+    assert hostsim().hs_lut_oob() == 0, "a fast-form lookup left the carrier table"
     return out, ph, st
 
 

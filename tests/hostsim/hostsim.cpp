@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#define E1_CHECK_LUT_BOUNDS 1
 #include "../../galileo-sdr-sim_b200/csrc/e1_core.h"
 #include "../../galileo-sdr-sim_b200/data/e1_prn_codes.h"
 
@@ -57,10 +58,11 @@ void hs_build_codes(uint32_t *codes)
 
 void hs_build_lut(const int *cos512, const int *sin512, int32_t *lut) { e1_build_lut(cos512, sin512, lut); }
 int hs_lut_entries(void) { return E1C_LUT_ENTRIES; }
+unsigned long long hs_lut_oob(void) { return e1_lut_oob; } // fast-form lookups outside the carrier table since load (must stay 0)
 
 int hs_code_words_per_prn(void) { return E1C_CODE_WORDS_PER_PRN; }
 
-// Whole pipeline on the host.  lut: int32[641][32] in the product layout (passed in by the test
+// Whole pipeline on the host.  lut: int32[642][32] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
 // stats[0] = samples resolved by the literal fallback, stats[1] = planner errors,
 // stats[2] = threads that took the slow path.

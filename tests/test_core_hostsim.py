@@ -126,14 +126,14 @@ def test_code_table_matches_oracle_halfchips():
 
 
 def test_carrier_table_layout():
-    """int32[641][32]: 2*(cos + 65536*sin) of the reference's tables, 32 copies per entry (one per lane).
+    """int32[642][32]: 2*(cos + 65536*sin) of the reference's tables, 32 copies per entry (one per lane).
     Entry E = e + 64: e in [0, 512] -> table index e & 511; below 0 -> 511 + e; above 512 -> e - 511
     (where runs that are about to wrap start; see E1C_LUT_IDX in e1_core.h).  Checked against what the
     reference reads (src/galileo-sdr.cpp:509-510) for every index of a wrapped and an unwrapped phase."""
     c, s = (C.c_int * 512)(), (C.c_int * 512)()
     U.oracle().e1o_carrier_lut(c, s)
     c, s = np.array(c), np.array(s)
-    lut = U.product_lut().reshape(641, 32)
+    lut = U.product_lut().reshape(642, 32)
     w2 = 2 * (c + 65536 * s)
     assert (lut == lut[:, :1]).all()
     L, EXT = lut[:, 0], 64
@@ -229,6 +229,26 @@ def test_fast_path_edges_of_the_carrier_table():
     a, pa = U.oracle_synth(fs, N, recs)
     b, pb, st = U.hostsim_synth(fs, N, recs)
     assert np.array_equal(a, b) and np.array_equal(pa, pb), st
+
+
+def test_mirrored_run_that_starts_on_an_ambiguous_sample_stays_inside_the_table():
+    """Negative phase, first sample of a run with trunc(511 |phi|) = 447 (the lowest index from which a run
+    is started 511 entries up because it may wrap) and a fraction below the ambiguity limit: the bias
+    that marks the sample ambiguous carries into the entry word, one past the highest entry any
+    unambiguous sample reads.  The run is redone exactly, but the fast form's terms come back out by
+    recomputing them, so that read must be inside the table: on the GPU the bytes behind the table are
+    a parameter buffer that another team's bulk copy rewrites (one wrong sample per ~10 runs of 780 M
+    samples before the table got its extra entry).  hostsim_synth asserts that no lookup left the table."""
+    fs, N = FS26, 20000
+    for frac in (1e-9, 5e-8, 1.5e-6):
+        for i0 in (446, 447, 448, 510):
+            recs = U.synthetic_recs(1, 2, fs, seed=1)
+            recs[0, 0]["f_carr"] = -2500.0
+            recs[0, 0]["f_code"] = 1.023e6 - 2500.0 * 0.0006493506493506494
+            recs[0, 0]["carr_phase_init"] = -(i0 + frac) / 511.0
+            a, pa = U.oracle_synth(fs, N, recs)
+            b, pb, st = U.hostsim_synth(fs, N, recs)
+            assert np.array_equal(a, b) and np.array_equal(pa, pb), (frac, i0, st)
 
 
 # ------------------------------------------------------------------ parallel carrier planner
