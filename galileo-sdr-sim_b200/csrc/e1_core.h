@@ -343,12 +343,14 @@ typedef struct e1_chan_par { /* 96 bytes, one per active channel of a tile (HBM 
     uint32_t misc;          /* bits 0-1 symbol field (D<<1 | D^S) before the wrap, bits 2-3 after it,
                                bit 4 negative-phase regime, bit 5 force the generic path, bit 6: the
                                phase runs through zero at tile sample j_z = bits 16-30 (from there on
-                               the magnitude is the two's complement of U and the regime flips)       */
+                               the magnitude is the two's complement of U and the regime flips), bit 7:
+                               no sample of the tile is near an index boundary (e1_par_clean)          */
     double phi, sp, cp, sc; /* exact checkpoint for the exact fallback                                */
 } e1_chan_par;
 #define E1_PAR_NEG 16u
 #define E1_PAR_FORCE 32u
 #define E1_PAR_HASZ 64u
+#define E1_PAR_CLEAN 128u /* no run of this tile can be ambiguous (e1_par_clean): the sample loop skips its tracking */
 
 /* One tile's parameter block in HBM: header (16 bytes: n_active, 3 x pad) + max_chan e1_chan_par,
  * active channels first. */
@@ -1035,6 +1037,147 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     p->misc = misc;
 }
 
+/* ------------------------------------------------------------------ tile-level ambiguity test
+ * The sample loop's ambiguity tracking (two running minima, one instruction per channel-sample) asks,
+ * run by run, whether a biased index fraction comes closer to an integer than lim_*.  Both fractions
+ * are, up to the fast form's truncation slack, ARITHMETIC SEQUENCES modulo one over the whole tile:
+ *   carrier  frac(511 (U0 + j dU) / 2^64)      code  frac((H + j dH) / 2^51)
+ * so "does any of the tile's samples come that close" is the classic question about the first term of
+ * (a + j d) mod M that falls below L, answered in O(log) steps by a Euclid-like descent.  A tile whose
+ * widened test finds no such sample is marked E1_PAR_CLEAN and its runs go through the sample loop
+ * without the tracking; every other tile (about 3 % of the (tile, channel) pairs: lim_carr + slack is
+ * 4e-6 of an index and a tile has 8192 samples) keeps it.  The implication "clean => no run of the
+ * tile would have been flagged" is what has to hold; the host test build asserts it run by run
+ * (hs_clean_violations in tests/hostsim).
+ *
+ * e1_first_hit: smallest j in [0, n) with (a + j d) mod M < L, or -1.  0 <= a, d < M <= 2^40,
+ * 0 < L <= M, n <= 8192 keeps every intermediate below 2^53 (e1_div_binade).  One level: reflect the
+ * circle (x -> L-1-x keeps the zone, reverses the direction) so that the step goes up by d <= M/2;
+ * walking up from a >= L nothing can hit until the sequence wraps, and the landing points after the
+ * wraps are again an arithmetic sequence, modulo d, with step -(M mod d): recurse on those (at most
+ * n d / M of them), then turn the landing number back into a sample number. */
+#define E1_AMB_BITS 40
+/* floor(num / d) from a reciprocal of d computed once per level (a level divides twice by its step and
+ * once by its modulus, which is the previous level's step): 0 <= num < 2^53 and a quotient below 2^41
+ * put the product within 2^-11 of the true quotient, so its integer part is off by at most one. */
+E1_HD double e1_rcp(int64_t d)
+{
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(__ll2double_rn(d));
+#else
+    (void)d;
+    return 0.0;
+#endif
+}
+E1_HD int64_t e1_div_rcp(int64_t num, int64_t d, double rcp)
+{
+#if defined(__CUDA_ARCH__)
+    int64_t q = __double2ll_rz(__dmul_rn(__ll2double_rn(num), rcp));
+    const int64_t r = num - q * d;
+    if (r < 0)
+        q--;
+    else if (r >= d)
+        q++;
+    return q;
+#else
+    (void)rcp;
+    return num / d;
+#endif
+}
+template <bool INDEX>
+E1_HD int64_t e1_hit_descent(int64_t a, int64_t d, int64_t M, int64_t L, int64_t n)
+{
+    double rM = e1_rcp(M);
+    int64_t sa[INDEX ? 20 : 1], sd[INDEX ? 20 : 1], sM[INDEX ? 20 : 1]; /* INDEX = false: "is there one" only, no unwinding */
+    int depth = 0;
+    int64_t res = -1;
+    for (;;) {
+        if (n <= 0)
+            break;
+        if (a < L) {
+            res = 0;
+            break;
+        }
+        if (d == 0)
+            break;
+        if (2 * d > M) {
+            a = M - (a - L + 1);
+            d = M - d;
+        }
+        const double rd = e1_rcp(d);
+        const int64_t k0 = e1_div_rcp(M - a + d - 1, d, rd); /* steps to the first wrap */
+        if (k0 >= n)
+            break;
+        const int64_t a0 = a + k0 * d - M; /* first landing, in [0, d) */
+        if (a0 < L) {
+            res = k0;
+            break;
+        }
+        if (INDEX) {
+            if (depth == 20) /* cannot happen (n halves per level); "hit" is the safe answer */
+                return 0;
+            sa[depth] = a, sd[depth] = d, sM[depth] = M;
+            depth++;
+        }
+        const int64_t n1 = e1_div_rcp(a + (n - 1) * d, M, rM); /* landings within n samples */
+        const int64_t r = M - e1_div_rcp(M, d, rd) * d;
+        a = a0;
+        M = d;
+        rM = rd;
+        d = r ? M - r : 0;
+        n = n1;
+    }
+    if (res < 0)
+        return -1;
+    /* res is a sample number of the level it was found on: a landing number of the level above */
+    while (INDEX && depth > 0) { /* landing number res of a pushed level -> its sample number */
+        depth--;
+        res = e1_div_binade((res + 1) * sM[depth] - sa[depth] + sd[depth] - 1, sd[depth]);
+    }
+    return res;
+}
+E1_HD int64_t e1_first_hit(int64_t a, int64_t d, int64_t M, int64_t L, int64_t n) { return e1_hit_descent<true>(a, d, M, L, n); }
+E1_HD int e1_any_hit(int64_t a, int64_t d, int64_t M, int64_t L, int64_t n) { return e1_hit_descent<false>(a, d, M, L, n) >= 0; }
+
+/* 1 when no sample of the tile (T samples from the checkpoint in p) can make a run of R = E1C_MAX_RUN
+ * samples ambiguous in e1_sample_loop.  Slack, in units of 2^-32 of an index:
+ *   carrier  the loop's biased fraction f = low32(511 hi32(U_run) + tc_carr + i D) lies in
+ *            (r + tc_carr - 511 R, r + tc_carr] with r the exact 511 (U0 + j dU) / 2^32 (mod 2^32);
+ *   code     F = low32(H_run >> 19) + i dF lies in (r - R, r] with r = (H + j dH) / 2^19, H = HA for
+ *            runs that start before the code wrap, HB (= HA to within thr_code) after;
+ *   both     the 40-bit sequence used here is below the exact one by less than (T + 1) / 256 <= 33.
+ * FORCE / HASZ tiles are not examined (the kernel takes them through the single-run path anyway). */
+E1_HD int e1_par_clean(const e1_chan_par *p, int T, uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code, uint32_t thr_code)
+{
+    if ((p->misc & (E1_PAR_FORCE | E1_PAR_HASZ)) || T > 8192)
+        return 0;
+    const int64_t M = (int64_t)1 << E1_AMB_BITS;
+    const int R = E1C_MAX_RUN, sh = 64 - E1_AMB_BITS, slack = 33;
+    {
+        const uint64_t G0 = p->U0 * 511ull, GB = p->dU * 511ull; /* mod 2^64: the index fraction, 2^-64 */
+        const int64_t a = (int64_t)(((G0 >> sh) + (((uint64_t)tc_carr + slack) << (E1_AMB_BITS - 32))) & (uint64_t)(M - 1));
+        const int64_t L = ((int64_t)lim_carr + 511 * R + slack + 1) << (E1_AMB_BITS - 32);
+        if (L >= M / 2)
+            return 0;
+        if (e1_any_hit(a, (int64_t)(GB >> sh), M, L, T))
+            return 0;
+    }
+    {
+        /* one sequence for the whole tile, from HA: the runs after the code wrap step HB + j dH, which is
+           the pre-wrap closed form at the wrap to within thr_code (the serial recurrence restarts there,
+           e1_tc_code) and has the same step -- the zone grows by thr_code on either side */
+        const int hs = 51 - E1_AMB_BITS;
+        const uint64_t m51 = ((uint64_t)1 << 51) - 1ull;
+        const int64_t L = ((int64_t)lim_code + R + slack + 1 + 2 * (int64_t)thr_code) << (E1_AMB_BITS - 32);
+        const uint64_t bias = ((uint64_t)slack + thr_code) << (E1_AMB_BITS - 32);
+        if (L >= M / 2)
+            return 0;
+        if (e1_any_hit((int64_t)((((p->HA & m51) >> hs) + bias) & (uint64_t)(M - 1)), (int64_t)((p->dH & m51) >> hs), M, L, T))
+            return 0;
+    }
+    return 1;
+}
+
 /* Exact table indices of sample j of the tile by walking the reference recurrences exactly
  * from the tile checkpoint (only for samples the closed form flags as ambiguous). */
 E1_HD void e1_exact_indices_impl(const e1_chan_par *p, int j, uint32_t *h_out, uint32_t *it_out)
@@ -1192,7 +1335,7 @@ E1_HD uint64_t e1_carrier_start(uint64_t U, uint64_t dU, uint32_t neg, uint32_t 
 
 /* The sample loop proper: R samples from table position y (step D), code fraction F (step dF) and the
  * window of signed chip fields win.  Returns the ambiguity flag of the run. */
-template <int R>
+template <int R, bool CHECK = true>
 E1_HD uint32_t e1_sample_loop(uint64_t y, int64_t D, e1_sptr lut_lane, uint32_t F, uint32_t dF, uint32_t win, int *acc,
                               uint32_t lim_carr, uint32_t lim_code)
 {
@@ -1201,8 +1344,10 @@ E1_HD uint32_t e1_sample_loop(uint64_t y, int64_t D, e1_sptr lut_lane, uint32_t 
 #pragma unroll
 #endif
     for (int i = 0; i < R; i++) {
-        mY = (uint32_t)y < mY ? (uint32_t)y : mY;
-        mF = F < mF ? F : mF;
+        if (CHECK) { /* off for the runs of an E1_PAR_CLEAN tile: none of them can be ambiguous */
+            mY = (uint32_t)y < mY ? (uint32_t)y : mY;
+            mF = F < mF ? F : mF;
+        }
 #if defined(__CUDA_ARCH__)
         const int w = (int)e1_ld32(e1_mad_u32((uint32_t)(y >> 32), 4u * E1C_LUT_REP, lut_lane));
 #else
@@ -1229,7 +1374,7 @@ E1_HD uint32_t e1_sample_loop(uint64_t y, int64_t D, e1_sptr lut_lane, uint32_t 
         F = F2;
 #endif
     }
-    return (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code);
+    return CHECK ? (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code) : 0u;
 }
 
 /* The 16-field code window of the run that starts at tile sample j (code phase H, 2^-51 half-chip, bias
@@ -1291,7 +1436,10 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
  * j0 + E1C_MAX_RUN adds and flags (same integers), so the caller repairs a flagged half with the
  * single-run machinery.  Irregular channels -- generic form forced, a zero crossing in this tile --
  * simply take the two single runs (the condition is the same for every thread of the tile).
- * Returns the two halves' return codes, first half in bits 0-1, second in bits 2-3. */
+ * Returns the two halves' return codes, first half in bits 0-1, second in bits 2-3.
+ * CHECK = false is for the channels of a tile marked E1_PAR_CLEAN (e1_par_clean: no sample of the tile
+ * is near an index boundary, so no run can be flagged): the same sums without the ambiguity tracking. */
+template <bool CHECK>
 E1_HD uint32_t e1_run_fast_pair(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *acc,
                                 uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
 {
@@ -1324,7 +1472,7 @@ E1_HD uint32_t e1_run_fast_pair(const e1_chan_par *p, const uint32_t *codes, con
         const uint32_t win = e1_code_window(p, code, H, jh, R, jw);
         int64_t D;
         const uint64_t y = e1_carrier_start(U, dU, neg, tc_carr, lim_carr, &D);
-        rc |= e1_sample_loop<E1C_MAX_RUN>(y, D, lut, (uint32_t)(H >> 19), dF, win, acc + h * R, lim_carr, lim_code) << (2 * h);
+        rc |= e1_sample_loop<E1C_MAX_RUN, CHECK>(y, D, lut, (uint32_t)(H >> 19), dF, win, acc + h * R, lim_carr, lim_code) << (2 * h);
     }
     return rc;
 }

@@ -525,6 +525,31 @@ __device__ __forceinline__ void e1_mbar_wait(uint64_t *bar, uint32_t parity)
                  : "memory");
 }
 
+/* Marks the (tile, channel) parameter sets whose runs cannot be ambiguous (e1_par_clean): one thread per
+ * (tile, compacted slot), after e1_finalize_kernel, for the paired-run kernel. */
+struct e1_clean_args {
+    unsigned char *blk;
+    long n_tiles;
+    int max_chan, tile;
+    uint32_t tc_carr, lim_carr, lim_code, thr_code;
+};
+__global__ void __launch_bounds__(128) e1_clean_kernel(const e1_clean_args A)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long tile_id = i / A.max_chan;
+    const int slot = (int)(i - tile_id * A.max_chan);
+    if (tile_id >= A.n_tiles)
+        return;
+    unsigned char *blk = A.blk + (size_t)tile_id * e1_blk_bytes(A.max_chan);
+    if (slot >= *reinterpret_cast<const int *>(blk))
+        return;
+    e1_chan_par *p = reinterpret_cast<e1_chan_par *>(blk + E1C_BLK_HEADER) + slot;
+    e1_chan_par q;
+    q.U0 = p->U0, q.dU = p->dU, q.HA = p->HA, q.HB = p->HB, q.dH = p->dH, q.j_w = p->j_w, q.misc = p->misc;
+    if (e1_par_clean(&q, A.tile, A.tc_carr, A.lim_carr, A.lim_code, A.thr_code))
+        p->misc = q.misc | E1_PAR_CLEAN;
+}
+
 /* The rare path of one (thread, channel): the fast form flagged the run (rc 1: its terms are in the
  * accumulators and come back out) or did not handle it (rc 2).  d[i] receives the correction. */
 template <int R>
@@ -751,7 +776,9 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_pair_kernel(cons
             for (int i = 0; i < E1_PAIR_RUN; i++)
                 acc[i] = 0;
             for (int a = 0; a < nact; a++) {
-                const uint32_t rc = e1_run_fast_pair(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code);
+                const uint32_t rc = (par[a].misc & E1_PAR_CLEAN)
+                                        ? e1_run_fast_pair<false>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code)
+                                        : e1_run_fast_pair<true>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code);
                 if (rc) { /* rare: a half of this (thread, channel) goes through the generic form */
 #pragma unroll
                     for (int h = 0; h < 2; h++)

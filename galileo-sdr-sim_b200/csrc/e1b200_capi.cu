@@ -24,6 +24,7 @@ struct e1b200_ctx {
     double delt;        /* 1/fs, as the reference computes it (src/galileo-sdr.cpp:162) */
     int tile;           /* samples per planner checkpoint / synthesis tile              */
     int run;            /* consecutive samples per thread: tile = 512 * run             */
+    int elide;          /* mark tiles that cannot hold an ambiguous sample (e1_clean_kernel) so the sample loop skips its tracking */
     int pair;           /* run == 16: two runs per thread, two 256-thread teams per CTA (e1_synth_pair_kernel) */
     int tiles_per_epoch;
     int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
@@ -165,6 +166,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->amb_scale = env_int("E1B200_AMB_SCALE", 1);
     if (ctx->amb_scale < 1)
         ctx->amb_scale = 1;
+    ctx->elide = !env_int("E1B200_NO_ELIDE", 0);
     ctx->serial_planner = (cfg->flags & E1B200_CFG_SERIAL_PLANNER) || env_int("E1B200_SERIAL_PLANNER", 0);
     const size_t epoch_bytes = (size_t)cfg->samples_per_epoch * 4;
     long be = (long)(((size_t)env_int("E1B200_BATCH_MB", 128) << 20) / epoch_bytes);
@@ -406,6 +408,20 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         const long tiles = (long)n * ctx->tiles_per_epoch;
         e1_finalize_kernel<<<(unsigned)((tiles + 3) / 4), 128, 0, ctx->stream>>>(F);
         ctx->timing.kernel_launches += 1;
+        if (ctx->pair && ctx->elide) { /* tiles without a near-boundary sample: the sample loop drops its tracking */
+            e1_clean_args C;
+            C.blk = ctx->d_blk;
+            C.n_tiles = tiles;
+            C.max_chan = cfg->max_chan;
+            C.tile = ctx->tile;
+            const uint32_t thr_carr = e1_thr_carr(ctx->tile, ctx->amb_scale), thr_code = e1_thr_code(ctx->tile, ctx->amb_scale);
+            C.tc_carr = e1_tc_carr(thr_carr, ctx->run);
+            C.lim_carr = e1_lim_carr(C.tc_carr, thr_carr);
+            C.lim_code = e1_lim_code(F.tc_code, thr_code);
+            C.thr_code = thr_code;
+            e1_clean_kernel<<<(unsigned)((tiles * cfg->max_chan + 127) / 128), 128, 0, ctx->stream>>>(C);
+            ctx->timing.kernel_launches += 1;
+        }
     }
     CK(cudaGetLastError());
     return mark(ctx, 0, 1);
@@ -740,6 +756,33 @@ int e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out)
     out->ctas_per_sm = ctx->ctas_per_sm;
     out->smem_bytes = ctx->smem_bytes;
     return E1B200_OK;
+}
+
+__global__ void e1_selftest_any_hit_kernel(int n, const int64_t *cs, int32_t *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = e1_any_hit(cs[5 * i], cs[5 * i + 1], cs[5 * i + 2], cs[5 * i + 3], cs[5 * i + 4]);
+}
+
+int e1b200_selftest_any_hit(int device, int n_cases, const int64_t *cases, int32_t *out)
+{
+    if (n_cases <= 0 || !cases || !out)
+        return E1B200_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess)
+        return E1B200_ENODEV;
+    int64_t *d_c = nullptr;
+    int32_t *d_o = nullptr;
+    int rc = E1B200_ECUDA;
+    if (cudaMalloc(&d_c, sizeof(int64_t) * 5 * (size_t)n_cases) == cudaSuccess && cudaMalloc(&d_o, sizeof(int32_t) * (size_t)n_cases) == cudaSuccess &&
+        cudaMemcpy(d_c, cases, sizeof(int64_t) * 5 * (size_t)n_cases, cudaMemcpyHostToDevice) == cudaSuccess) {
+        e1_selftest_any_hit_kernel<<<(n_cases + 127) / 128, 128>>>(n_cases, d_c, d_o);
+        if (cudaMemcpy(out, d_o, sizeof(int32_t) * (size_t)n_cases, cudaMemcpyDeviceToHost) == cudaSuccess)
+            rc = E1B200_OK;
+    }
+    cudaFree(d_c);
+    cudaFree(d_o);
+    return rc;
 }
 
 void *e1b200_stream(e1b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

@@ -52,7 +52,7 @@ SYMBOLS = [
     "e1b200_get_carrier_phase", "e1b200_set_carrier_phase", "e1b200_synth_epochs",
     "e1b200_synth_epochs_device", "e1b200_sync", "e1b200_synth_ranges", "e1b200_synth_ranges_device", "e1b200_plan_phases",
     "e1b200_restate", "e1b200_get_timing", "e1b200_get_stats", "e1b200_stream", "e1b200_last_error",
-    "e1b200_version", "e1b200_host_alloc", "e1b200_host_free",
+    "e1b200_version", "e1b200_host_alloc", "e1b200_host_free", "e1b200_selftest_any_hit",
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def load():
     lib.e1b200_version.restype = C.c_char_p
     lib.e1b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.e1b200_host_free.argtypes = [vp]
+    lib.e1b200_selftest_any_hit.argtypes = [C.c_int, C.c_int, vp, vp]
     _lib = lib
     return lib
 

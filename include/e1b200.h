@@ -156,6 +156,12 @@ void *e1b200_stream(e1b200_ctx *ctx);          /* cudaStream_t the context launc
 const char *e1b200_last_error(e1b200_ctx *ctx);
 const char *e1b200_version(void);
 
+/* Diagnostics: the device build of the tile-level ambiguity search (e1_any_hit in csrc/e1_core.h, the
+ * arithmetic behind e1_clean_kernel) on caller-supplied cases, so a test can hold it against a literal
+ * loop: out[i] = 1 when some j in [0, n[i]) has (a[i] + j d[i]) mod M[i] < L[i].  Host pointers,
+ * 5 int64 per case in `cases` (a, d, M, L, n).  No counterpart in the reference. */
+int  e1b200_selftest_any_hit(int device, int n_cases, const int64_t *cases, int32_t *out);
+
 /* pinned host allocation helpers so the reference's fwrite/FIFO memcpy consumers
  * (src/galileo-sdr.cpp:542,588) can stay unchanged while D2H runs at full PCIe rate        */
 int  e1b200_host_alloc(void **p, size_t bytes);

@@ -130,6 +130,10 @@ def hostsim():
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         hs.hs_synth_epochs_p.argtypes = hs.hs_synth_epochs.argtypes + [C.c_int]
         hs.hs_lut_oob.restype = C.c_ulonglong
+        hs.hs_first_hit.restype = C.c_longlong
+        hs.hs_first_hit.argtypes = [C.c_longlong] * 5
+        for f in (hs.hs_clean_tiles, hs.hs_checked_tiles, hs.hs_clean_violations):
+            f.restype = C.c_ulonglong
         hs.hs_plan_compare.restype = C.c_long
         hs.hs_plan_compare.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _hostsim = hs
@@ -160,6 +164,7 @@ def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1, p
                                      groups, amb_scale, lut.ctypes.data, st.ctypes.data, planner)
     assert rc == 0, f"hostsim planner errors: {st}"
     assert hostsim().hs_lut_oob() == 0, "a fast-form lookup left the carrier table"
+    assert hostsim().hs_clean_violations() == 0, "a run of a tile marked E1_PAR_CLEAN was flagged by the tracking sample loop"
     return out, ph, st
 
 

@@ -62,6 +62,15 @@ unsigned long long hs_lut_oob(void) { return e1_lut_oob; } // fast-form lookups 
 
 int hs_code_words_per_prn(void) { return E1C_CODE_WORDS_PER_PRN; }
 
+// tile-level ambiguity test (e1_first_hit / e1_par_clean)
+long long hs_first_hit(long long a, long long d, long long M, long long L, long long n) { return e1_first_hit(a, d, M, L, n); }
+static unsigned long long g_clean_tiles = 0, g_checked_tiles = 0, g_clean_violations = 0;
+// (tile, channel) parameter sets marked clean / not marked since load, and runs of a clean tile that the
+// tracking sample loop flagged or summed differently (must stay 0)
+unsigned long long hs_clean_tiles(void) { return g_clean_tiles; }
+unsigned long long hs_checked_tiles(void) { return g_checked_tiles; }
+unsigned long long hs_clean_violations(void) { return g_clean_violations; }
+
 // Whole pipeline on the host.  lut: int32[642][32] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
 // stats[0] = samples resolved by the literal fallback, stats[1] = planner errors,
@@ -158,7 +167,15 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                 const int sp = t / geo.span_tiles;
                 e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile,
                             e1_trans_at(&delta[(size_t)ch * n_units + (size_t)e * S + sp], (t - sp * geo.span_tiles) * tile), tc_code,
-                            &par[nact++]);
+                            &par[nact]);
+                if (run == E1C_MAX_RUN) { // e1_clean_kernel
+                    if (e1_par_clean(&par[nact], tile, tc_carr, lim_carr, lim_code, thr_code)) {
+                        par[nact].misc |= E1_PAR_CLEAN;
+                        g_clean_tiles++;
+                    } else
+                        g_checked_tiles++;
+                }
+                nact++;
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
             int16_t *o = out + ((size_t)e * n_samp + (size_t)t * tile) * 2;
@@ -170,7 +187,19 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                     const unsigned char *lut_lane = (const unsigned char *)lut + 4 * (tid & (E1C_LUT_REP - 1));
                     int acc[2 * E1C_MAX_RUN] = {0};
                     for (int a = 0; a < nact; a++) {
-                        const uint32_t rc = e1_run_fast_pair(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code);
+                        uint32_t rc;
+                        if (par[a].misc & E1_PAR_CLEAN) {
+                            // what the kernel does, and beside it the tracking loop: it must not flag anything
+                            // and must add the same terms
+                            int a0[2 * E1C_MAX_RUN] = {0}, a1[2 * E1C_MAX_RUN] = {0};
+                            rc = e1_run_fast_pair<false>(&par[a], codes.data(), lut_lane, j0, a0, tc_carr, lim_carr, lim_code);
+                            const uint32_t rc1 = e1_run_fast_pair<true>(&par[a], codes.data(), lut_lane, j0, a1, tc_carr, lim_carr, lim_code);
+                            if (rc1 || rc || memcmp(a0, a1, sizeof a0))
+                                g_clean_violations++;
+                            for (int i = 0; i < 2 * run; i++)
+                                acc[i] += a0[i];
+                        } else
+                            rc = e1_run_fast_pair<true>(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code);
                         for (int h = 0; h < 2; h++) {
                             if (!((rc >> (2 * h)) & 3u))
                                 continue;

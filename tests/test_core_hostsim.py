@@ -332,3 +332,57 @@ def test_parallel_planner_ties_idle_gaps_resets_and_low_doppler():
     a, pa = U.oracle_synth(fs, 26000, recs[:14], np.linspace(-0.9, 0.9, 9))
     b, pb, st = U.hostsim_synth(fs, 26000, recs[:14], np.linspace(-0.9, 0.9, 9))
     assert np.array_equal(a, b) and np.array_equal(pa, pb)
+
+
+def _first_hit_brute(a, d, M, L, n):
+    x = a
+    for j in range(n):
+        if x < L:
+            return j
+        x = (x + d) % M
+    return -1
+
+
+def test_first_hit_equals_brute_force():
+    """e1_first_hit (the Euclid-like descent behind the tile-level ambiguity test) against the literal
+    loop: small moduli exhaustively-ish, the product's 2^40 modulus with steps near 0, near M, near
+    M/k and random, zones from one unit to M/16."""
+    import random
+    hs = U.hostsim()
+    rnd = random.Random(5)
+    for trial in range(6000):
+        kind = trial % 4
+        if kind == 0:
+            M = rnd.randrange(2, 120); L = rnd.randrange(1, M + 1); n = rnd.randrange(0, 50)
+        elif kind == 1:
+            M = 1 << 40; L = rnd.randrange(1, 1 << rnd.randrange(1, 37)); n = rnd.randrange(1, 8193)
+        elif kind == 2:
+            M = rnd.randrange(2, 1 << 40); L = rnd.randrange(1, min(M, 1 << 30) + 1); n = rnd.randrange(1, 8193)
+        else:
+            M = 1 << 40; L = rnd.randrange(1 << 20, 1 << 28); n = 8192
+        a = rnd.randrange(M)
+        d = [rnd.randrange(M), rnd.randrange(min(M, 1000)), M - 1 - rnd.randrange(min(M, 1000)),
+             (M // rnd.randrange(1, 50) + rnd.randrange(-3, 4)) % M,
+             (M * rnd.randrange(1, 30) // rnd.randrange(30, 60) + rnd.randrange(-2, 3)) % M][rnd.randrange(5)]
+        assert hs.hs_first_hit(a, d, M, L, n) == _first_hit_brute(a, d, M, L, n), (a, d, M, L, n)
+
+
+def test_tiles_marked_clean_never_hold_a_flagged_run():
+    """The paired-run kernel drops the per-sample ambiguity tracking for the channels of a tile that
+    e1_par_clean marks.  The host build runs the tracking loop beside the plain one on every run of
+    such a tile: it must flag nothing and add the same terms (hostsim_synth asserts the counter);
+    here, that the marking is neither vacuous nor universal, and that flagged runs do occur (in the
+    unmarked tiles) on the same input."""
+    hs = U.hostsim()
+    c0, k0 = hs.hs_clean_tiles(), hs.hs_checked_tiles()
+    slow = 0
+    for fs, n_samp, seed, kw in ((FS26, 260000, 41, {}), (FS26, 260000, 42, {"f_max": 60.0}), (FS25, 250000, 43, {})):
+        recs = U.synthetic_recs(3, 36, fs, seed=seed, max_chan=36, **kw)
+        a, pa = U.oracle_synth(fs, n_samp, recs, threads=8)
+        b, pb, st = U.hostsim_synth(fs, n_samp, recs)
+        assert np.array_equal(a, b) and np.array_equal(pa, pb)
+        slow += int(st[2])
+    clean, checked = hs.hs_clean_tiles() - c0, hs.hs_checked_tiles() - k0
+    assert hs.hs_clean_violations() == 0
+    assert clean > 0 and checked > 0 and slow > 0
+    assert 0.9 < clean / (clean + checked) < 0.995, (clean, checked)

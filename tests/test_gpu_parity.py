@@ -97,7 +97,7 @@ def test_device_entry_and_call_splitting():
     s.sync()
     assert np.array_equal(d_out.cpu().numpy().reshape(-1, 2), ref)
     t = s.timing()
-    assert t.synth_ms > 0 and t.plan_ms > 0 and t.kernel_launches == 9 and t.synth_launches == 1
+    assert t.synth_ms > 0 and t.plan_ms > 0 and t.kernel_launches == 10 and t.synth_launches == 1
     s2 = E.Synth(fs, n_samp, nch)
     a = s2.synth_epochs(recs[:2])
     b = s2.synth_epochs(recs[2:])
@@ -125,6 +125,27 @@ def test_internal_batching_and_no_tma_path(monkeypatch):
     s = E.Synth(fs, n_samp, nch)
     assert np.array_equal(s.synth_epochs(recs), ref)
     s.close()
+
+
+def test_clean_tile_marking_does_not_change_the_stream(monkeypatch):
+    """e1_clean_kernel marks the (tile, channel) sets without a sample near an index boundary and the
+    paired-run kernel drops the per-sample ambiguity tracking for them.  Same bytes with the marking
+    switched off (E1B200_NO_ELIDE: every run is tracked, as before), and both equal the oracle; the
+    exact-fallback count is the same too -- the flagged runs all live in unmarked tiles."""
+    fs, n_samp, nch = FS26, 260000, 36
+    recs = U.synthetic_recs(3, nch, fs, seed=77)
+    ref, _ = U.oracle_synth(fs, n_samp, recs, threads=8)
+    s = E.Synth(fs, n_samp, nch)
+    a = s.synth_epochs(recs)
+    na, la = s.stats().exact_samples, s.timing().kernel_launches
+    s.close()
+    monkeypatch.setenv("E1B200_NO_ELIDE", "1")
+    s = E.Synth(fs, n_samp, nch)
+    b = s.synth_epochs(recs)
+    nb, lb = s.stats().exact_samples, s.timing().kernel_launches
+    s.close()
+    assert np.array_equal(a, ref) and np.array_equal(b, ref)
+    assert na == nb and la == lb + 1
 
 
 def test_parallel_planner_equals_serial_planner(monkeypatch):
@@ -286,3 +307,34 @@ def test_full_size_linearity_config2():
     s.close()
     ref, _ = U.oracle_synth(fs, n_samp, recs[50:52], ph, threads=8)
     assert np.array_equal(full[50 * n_samp:52 * n_samp], ref)
+
+
+def test_device_ambiguity_search_equals_literal_loop():
+    """The device build of e1_any_hit (reciprocal-multiply divisions with one correction step) against the
+    literal loop, on the product's modulus with steps near 0, near M, near M/k and random, and on
+    small moduli; the host build of the same descent is held to the loop in test_core_hostsim.py."""
+    import random
+    rnd = random.Random(11)
+    cases = []
+    for trial in range(20000):
+        kind = trial % 4
+        if kind == 0:
+            M = rnd.randrange(2, 120); L = rnd.randrange(1, M + 1); n = rnd.randrange(0, 50)
+        elif kind == 1:
+            M = 1 << 40; L = rnd.randrange(1, 1 << rnd.randrange(1, 37)); n = rnd.randrange(1, 8193)
+        elif kind == 2:
+            M = rnd.randrange(2, 1 << 40); L = rnd.randrange(1, min(M, 1 << 30) + 1); n = rnd.randrange(1, 8193)
+        else:
+            M = 1 << 40; L = rnd.randrange(1 << 20, 1 << 28); n = 8192
+        a = rnd.randrange(M)
+        d = [rnd.randrange(M), rnd.randrange(min(M, 1000)), M - 1 - rnd.randrange(min(M, 1000)),
+             (M // rnd.randrange(1, 50) + rnd.randrange(-3, 4)) % M,
+             (M * rnd.randrange(1, 30) // rnd.randrange(30, 60) + rnd.randrange(-2, 3)) % M][rnd.randrange(5)]
+        cases.append((a, d, M, L, n))
+    cs = np.array(cases, dtype=np.int64)
+    out = np.zeros(len(cases), np.int32)
+    assert E.load().e1b200_selftest_any_hit(0, len(cases), cs.ctypes.data, out.ctypes.data) == 0
+    hs = U.hostsim()
+    want = np.array([hs.hs_first_hit(*c) >= 0 for c in cases], np.int32)   # == the literal loop (CPU test)
+    assert np.array_equal(out, want), np.nonzero(out != want)[0][:10]
+    assert 0.1 < want.mean() < 0.9
