@@ -732,12 +732,35 @@ E1_HD void e1_v2_ideal_prefix(const e1_prep *pp, int n_epochs, double phi0, doub
     }
 }
 
-/* drift pass: exact walk of one epoch from its ideal start; returns the end phase */
+/* drift pass: where the span ends when it starts at its ideal phase g, as an ESTIMATE (the chain
+ * validates every guess exactly; this only decides how many it accepts).  The rounding drift of the
+ * serial recurrence against the ideal line is systematic -- inside a binade every addition rounds the
+ * same way by the same amount, the step's bits below the binade's ulp -- so the first
+ * n / E1_DRIFT_DECIM samples are walked exactly and their drift is scaled to the span.  (With a Doppler
+ * that changes from epoch to epoch the accumulated drift is a random walk of a few 1e-10 cycles over
+ * 300 s and the pass hardly matters; with a constant Doppler it grows linearly to ~1e-8 and, left out,
+ * costs about one span in a hundred a serial walk.) */
+#define E1_DRIFT_DECIM 16
 E1_HD double e1_v2_drift_unit(const e1_prep *p, double g)
 {
     if (!(p->flags & E1_PREP_ACTIVE))
         return g;
-    return e1_carr_advance(g, p->sp, 0, p->n);
+    const int q = p->n / E1_DRIFT_DECIM;
+    if (q < 1024)
+        return e1_carr_advance(g, p->sp, 0, p->n);
+    double d = e1_carr_advance(g, p->sp, 0, q) - e1_ideal_next(g, p->sp, q);
+    if (d > 0.5)
+        d -= 1.0;
+    else if (d < -0.5)
+        d += 1.0;
+    if (!(d < 1e-6 && d > -1e-6)) /* not a drift: the two folded differently (sign change near zero) */
+        d = 0.0;
+    double v = e1_ideal_next(g, p->sp, p->n) + d * ((double)p->n / (double)q);
+    if (v >= 1.0)
+        v -= 1.0;
+    else if (v <= -1.0)
+        v += 1.0;
+    return v;
 }
 
 /* K1: refined start-phase estimates of one channel.  The drift pass walked epoch e exactly from

@@ -334,6 +334,25 @@ def test_parallel_planner_ties_idle_gaps_resets_and_low_doppler():
     assert np.array_equal(a, b) and np.array_equal(pa, pb)
 
 
+def test_planner_is_exact_whatever_the_drift_estimates(monkeypatch):
+    """The drift pass (e1_v2_drift_unit: the first 1/16 of each span walked exactly, its rounding drift
+    scaled to the span) only feeds the guesses; the chain validates every span exactly.  With a constant
+    Doppler the drift is systematic and grows linearly: with the estimates the chain accepts nearly
+    every span, without them (HS_NO_DRIFT: estimates = the ideal line) it walks more of them serially --
+    and the checkpoints equal the serial walk bit for bit either way."""
+    fs, n_ep = FS26, 1500
+    recs = U.synthetic_recs_fast(n_ep, 6, fs, seed=3)
+    for c in range(6):
+        recs[:, c]["f_carr"] = recs[0, c]["f_carr"]
+        recs[:, c]["f_code"] = recs[0, c]["f_code"]
+    bad, (serial, hat, active) = U.hostsim_plan_compare(fs, 260000, recs)
+    assert bad == 0 and serial <= 6
+    monkeypatch.setenv("HS_NO_DRIFT", "1")
+    bad2, (serial2, hat2, active2) = U.hostsim_plan_compare(fs, 260000, recs)
+    assert bad2 == 0 and active2 == active
+    assert serial2 > serial + 20 and serial2 < 0.02 * active
+
+
 def _first_hit_brute(a, d, M, L, n):
     x = a
     for j in range(n):
