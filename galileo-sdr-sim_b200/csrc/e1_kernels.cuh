@@ -169,7 +169,7 @@ __device__ __forceinline__ e1_tile_ck *e1_unit_ck(const e1_plan_args &P, int u, 
  * run from its true start. */
 #define E1_SERIAL_THREADS 128
 #define E1_SERIAL_CHUNK 128
-#define E1_CHAIN_THREADS 256 /* chain kernel: one span per thread per round, 256 spans per round */
+#define E1_CHAIN_THREADS 512 /* chain kernel: one span per thread per round, 512 spans per round */
 
 __device__ __forceinline__ double e1_fold1(double v) /* into (-1,1), sign kept (like :532) */
 {
@@ -295,7 +295,7 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
  *     D[u] = (true post-wrap value at its anchor) - (guessed one)
  *          = (last_p[u-1] + D[u-1]) - anchor_p[u]
  * where last_p / anchor_p are the span pass's hat values -- all multiples of 2^-52 below 1, so the sums
- * are exact in any order.  A chunk of 128 consecutive spans is therefore first tried as a parallel
+ * are exact in any order.  A round of E1_CHAIN_THREADS consecutive spans is therefore first tried as a parallel
  * inclusive scan of x[u] = last_p[u-1] - anchor_p[u] (x[first] uses the carried state); if every span
  * of the chunk is an ordinary accepted guess (HAT unit, anchored on its predecessor's last wrap, no
  * tie wrap, lo <= D < hi) the chunk is done; otherwise thread 0 walks that chunk with
@@ -303,8 +303,6 @@ __global__ void e1_v2_span_kernel(const e1_plan_args P)
 __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_plan_args P)
 {
     __shared__ __align__(16) e1_unit s_units[E1_CHAIN_THREADS];
-    __shared__ double s_sp[E1_CHAIN_THREADS];
-    __shared__ int s_n[E1_CHAIN_THREADS];
     __shared__ e1_trans s_delta[E1_CHAIN_THREADS];
     __shared__ double s_warp[E1_CHAIN_THREADS / 32];
     __shared__ e1_chain_state s_cs;
@@ -320,16 +318,12 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
        global-memory latency of a round's inputs would be most of its time: every thread fetches ITS span
        of the next round into registers before the current round's scan. */
     uint4 pf[sizeof(e1_unit) / 16];
-    double pf_sp = 0.0;
-    int pf_n = 0;
     auto fetch = [&](int e0) {
         if (e0 + tid < P.n_units) {
             const uint4 *src = reinterpret_cast<const uint4 *>(P.units + o + e0 + tid);
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(e1_unit) / 16); i++)
                 pf[i] = src[i];
-            pf_sp = P.prep[o + e0 + tid].sp;
-            pf_n = P.prep[o + e0 + tid].n;
         }
     };
     fetch(0);
@@ -340,8 +334,6 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(e1_unit) / 16); i++)
                 dst[i] = pf[i];
-            s_sp[tid] = pf_sp;
-            s_n[tid] = pf_n;
         }
         fetch(e0 + E1_CHAIN_THREADS);
         if (tid == 0)
@@ -429,9 +421,12 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
             const int upto = ++restarts > 8 ? n : bad + 1; /* the same in every thread */
             if (tid == 0) {
                 e1_chain_state cs = s_cs;
-                for (int i = bad; i < upto; i++)
-                    s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], e0 + i, s_sp[i], s_n[i], P.tile, (s_n[i] + P.tile - 1) / P.tile,
+                for (int i = bad; i < upto; i++) { /* rare: the span's step and length come straight from global memory */
+                    const double sp_i = P.prep[o + e0 + i].sp;
+                    const int n_i = P.prep[o + e0 + i].n;
+                    s_delta[i] = e1_v2_chain_step(&cs, &s_units[i], e0 + i, sp_i, n_i, P.tile, (n_i + P.tile - 1) / P.tile,
                                                   e1_unit_ck(P, e0 + i, ch), P.max_chan, st);
+                }
                 s_cs = cs;
             }
             start = upto;
