@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
     __shared__ __align__(16) e1_unit s_units[E1_CHAIN_THREADS];
     __shared__ e1_trans s_delta[E1_CHAIN_THREADS];
     __shared__ double s_warp[E1_CHAIN_THREADS / 32];
+    __shared__ int s_wmax[E1_CHAIN_THREADS / 32];
     __shared__ e1_chain_state s_cs;
     __shared__ int s_bad;
     const int ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -340,45 +341,68 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
             s_bad = 0;
         __syncthreads();
         /* Optimistic pass over spans [start, n) of the round, thread t owns span e0 + t: assume every span
-           is a regular HAT span anchored in its predecessor, scan the translations, validate.  The prefix
-           up to the first span that is not (guess rejected, tie wrap, phase reset, idle slot, sign change,
-           no wrap to anchor on) is committed, thread 0 takes that ONE span through the serial chain step,
-           and the pass resumes behind it.  (A round that keeps failing -- a channel at very low Doppler has
-           no wrap in most spans -- goes to the serial chain for its remainder.) */
+           is an accepted HAT span, scan the translations, validate.  The prefix up to the first span that
+           is not (guess rejected, tie wrap, phase reset, idle slot, sign change, no wrap within reach to
+           anchor on) is committed, thread 0 takes that ONE span through the serial chain step, and the
+           pass resumes behind it.  (A round that keeps failing goes to the serial chain for its remainder.) */
         int start = 0, restarts = 0;
         while (start < n) {
+            /* x = what span tid adds to T, the true |phase| right after the most recent wrap: a span with a
+               wrap moves it to last_p + D = last_p + (T_before - anchor_p), a span without one leaves it.
+               So T before span tid = T at `start` + the exclusive scan of x, and D = that - anchor_p -- whether
+               the anchor wrap lies in the span just before or (low Doppler) several spans back. */
             double x = 0.0;
-            int ok = 1;
+            int wrapidx = -1; /* this span if it holds a wrap: max-scanned into "the span with the most recent wrap" */
             if (tid >= start && tid < n) {
                 const e1_unit *u = &s_units[tid];
-                int p_ok, p_neg, p_k;
-                double p_last;
-                if (tid == start) {
-                    p_ok = s_cs.prev_ok && s_cs.prev_u == e0 + start - 1, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_last = s_cs.prev_p;
-                } else {
-                    const e1_unit *q = &s_units[tid - 1];
-                    p_ok = q->last_k >= 1, p_neg = q->neg, p_k = q->last_k, p_last = q->last_p;
+                if (u->type == E1_UNIT_HAT && u->last_k >= 1) {
+                    x = __dadd_rn(u->last_p, -u->anchor_p);
+                    wrapidx = tid;
                 }
-                ok = u->type == E1_UNIT_HAT && u->tie == 0 && u->anchor_back == 1 && p_ok && p_neg == u->neg && p_k == u->anchor_k;
-                x = ok ? __dadd_rn(p_last, -u->anchor_p) : 0.0;
             }
-            /* inclusive scan of x over the block (exact additions: every term is a multiple of 2^-52) */
-            double D = x;
+            double S = x; /* inclusive scans over the block (exact additions: every term is a multiple of 2^-52) */
+            int W = wrapidx;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const double y = __shfl_up_sync(0xffffffffu, D, d);
-                if (lane >= d)
-                    D = __dadd_rn(D, y);
+                const double y = __shfl_up_sync(0xffffffffu, S, d);
+                const int w = __shfl_up_sync(0xffffffffu, W, d);
+                if (lane >= d) {
+                    S = __dadd_rn(S, y);
+                    W = max(W, w);
+                }
             }
-            if (lane == 31)
-                s_warp[wid] = D;
+            if (lane == 31) {
+                s_warp[wid] = S;
+                s_wmax[wid] = W;
+            }
             if (tid == 0)
                 s_bad = n; /* first span of [start, n) that fails */
             __syncthreads();
-            for (int w = 0; w < wid; w++)
-                D = __dadd_rn(D, s_warp[w]);
+            for (int w = 0; w < wid; w++) {
+                S = __dadd_rn(S, s_warp[w]);
+                W = max(W, s_wmax[w]);
+            }
+            /* exclusive values: the state BEFORE span tid */
+            const double Tb = __dadd_rn(s_cs.prev_p, __dadd_rn(S, -x));
+            int Wb = __shfl_up_sync(0xffffffffu, W, 1);
+            if (lane == 0) {
+                Wb = -1;
+                for (int w = 0; w < wid; w++)
+                    Wb = max(Wb, s_wmax[w]);
+            }
+            double D = 0.0;
             if (tid >= start && tid < n) {
                 const e1_unit *u = &s_units[tid];
+                int p_ok, p_neg, p_k, p_u;
+                if (Wb >= start) { /* the most recent wrap is inside this pass: every span of the pass is taken to be an accepted guess */
+                    const e1_unit *q = &s_units[Wb];
+                    p_ok = 1, p_neg = q->neg, p_k = q->last_k, p_u = e0 + Wb;
+                } else {
+                    p_ok = s_cs.prev_ok, p_neg = s_cs.prev_neg, p_k = s_cs.prev_k, p_u = s_cs.prev_u;
+                }
+                D = __dadd_rn(Tb, -u->anchor_p);
+                const int ok = u->type == E1_UNIT_HAT && u->tie == 0 && p_ok && p_neg == u->neg && p_u == e0 + tid - u->anchor_back &&
+                               p_k == u->anchor_k;
                 if (!(ok && D >= u->lo && D < u->hi))
                     atomicMin(&s_bad, tid);
             }
@@ -391,26 +415,23 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
                 tr.k_split = 0;
                 tr.pad = 0;
                 s_delta[tid] = tr;
-                /* the state the serial chain (e1_v2_chain_step) would carry out of this prefix: the phase after
-                   its last span, and the most recent wrap -- in the last span, or, when that one has none but
-                   stayed aligned (last_k == -1), still the one in the span before it */
-                if (tid == bad - 1) {
-                    s_cs.phi = __dadd_rn(u->end_phi, tr.b);
-                    if (u->last_k >= 1) {
-                        s_cs.prev_p = __dadd_rn(u->last_p, D);
-                        s_cs.prev_k = u->last_k;
-                        s_cs.prev_u = e0 + tid;
-                        s_cs.prev_ok = 1;
-                        s_cs.prev_neg = u->neg;
-                    } else if (u->last_k != -1) {
-                        s_cs.prev_ok = 0;
-                    }
-                } else if (tid == bad - 2 && s_units[bad - 1].last_k == -1) {
-                    s_cs.prev_p = __dadd_rn(u->last_p, D); /* u->last_k >= 1: span bad-1 passed the test on it */
-                    s_cs.prev_k = u->last_k;
-                    s_cs.prev_u = e0 + tid;
+            }
+            __syncthreads(); /* every thread has read s_cs */
+            /* the state the serial chain (e1_v2_chain_step) would carry out of the accepted prefix: the phase
+               after its last span, and the most recent wrap -- the last one inside the prefix, or, when the
+               prefix has none (all its spans aligned and wrap-free), still the one carried in */
+            if (tid == bad - 1 && bad > start) {
+                const e1_unit *u = &s_units[tid];
+                s_cs.phi = __dadd_rn(u->end_phi, u->neg ? -D : D);
+                if (W >= start) {
+                    const e1_unit *q = &s_units[W];
+                    /* D of span W = T before W - anchor_p[W]; T after it = last_p[W] + that = T before tid + x terms:
+                       the inclusive sum S holds it */
+                    s_cs.prev_p = __dadd_rn(s_cs.prev_p, S);
+                    s_cs.prev_k = q->last_k;
+                    s_cs.prev_u = e0 + W;
                     s_cs.prev_ok = 1;
-                    s_cs.prev_neg = u->neg;
+                    s_cs.prev_neg = q->neg;
                 }
             }
             if (tid == 0)
@@ -418,7 +439,7 @@ __global__ void __launch_bounds__(E1_CHAIN_THREADS) e1_v2_chain_kernel(const e1_
             __syncthreads();
             if (bad >= n)
                 break;
-            const int upto = ++restarts > 8 ? n : bad + 1; /* the same in every thread */
+            const int upto = ++restarts > 16 ? n : bad + 1; /* the same in every thread */
             if (tid == 0) {
                 e1_chain_state cs = s_cs;
                 for (int i = bad; i < upto; i++) { /* rare: the span's step and length come straight from global memory */

@@ -130,6 +130,8 @@ def hostsim():
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         hs.hs_synth_epochs_p.argtypes = hs.hs_synth_epochs.argtypes + [C.c_int]
         hs.hs_lut_oob.restype = C.c_ulonglong
+        hs.hs_chain_scan_compare.restype = C.c_long
+        hs.hs_chain_scan_compare.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         hs.hs_first_hit.restype = C.c_longlong
         hs.hs_first_hit.argtypes = [C.c_longlong] * 5
         for f in (hs.hs_clean_tiles, hs.hs_checked_tiles, hs.hs_clean_violations):
@@ -348,3 +350,14 @@ class OracleEngine:
             out.reshape(-1)[: res.size] = res.reshape(-1)
             return out
         return res
+
+
+def hostsim_chain_scan_compare(fs_hz, n_samp, recs, carr_phase=None, round_spans=512):
+    """The chain kernel's rounds (optimistic scan + serial step) transcribed for the host against the serial
+    chain: (differing translations, [spans accepted by the scan, spans through the serial step])."""
+    recs = np.ascontiguousarray(recs)
+    n_epochs, max_chan = recs.shape
+    ph = np.zeros(max_chan) if carr_phase is None else np.array(carr_phase, dtype=np.float64)
+    st = np.zeros(2, np.uint64)
+    bad = hostsim().hs_chain_scan_compare(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, round_spans, st.ctypes.data)
+    return int(bad), [int(v) for v in st]

@@ -4,6 +4,7 @@
 // planner / closed-form / fallback logic can be checked against the oracle on a box without a
 // GPU.  It is built by tests/e1util.py into tests/hostsim/libe1hostsim.so and loaded only by
 // the tests; the product library (libe1b200.so) does not contain or call any of this.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -255,6 +256,145 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
             }
         }
     return stats[1] ? -1 : 0;
+}
+
+// The chain kernel's round structure on the host (e1_v2_chain_kernel in e1_kernels.cuh: rounds of
+// `round` spans, optimistic scan of T = true |phase| after the most recent wrap, prefix commit, one
+// serial step at the first span that fails, resume), statement for statement, against the serial chain
+// e1_v2_chain on the same span-pass output.  Returns the number of differing translations (+1 if the
+// final phase differs); stats[0] = spans accepted by the scan, stats[1] = spans through the serial step.
+long hs_chain_scan_compare(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs, const double *phase0,
+                           int round, unsigned long long *stats)
+{
+    const double delt = 1.0 / fs_hz;
+    const int tile = 4 * 4 * E1C_THREADS;
+    const int tpe = (n_samp + tile - 1) / tile;
+    const e1_span_geo geo = e1_span_geometry(tpe);
+    const int S_ = geo.spans_per_epoch, n_units = n_epochs * S_;
+    const size_t ne = (size_t)n_units * max_chan;
+    std::vector<e1_tile_ck> ck1((size_t)n_epochs * tpe * max_chan), ck2(ck1.size());
+    memset(ck1.data(), 0, ck1.size() * sizeof(e1_tile_ck));
+    memset(ck2.data(), 0, ck2.size() * sizeof(e1_tile_ck));
+    std::vector<double> g(ne), dend(ne), est(ne);
+    std::vector<e1_trans> d1(ne, e1_trans{0.0, 0.0, 0, 0}), d2(ne, e1_trans{0.0, 0.0, 0, 0});
+    std::vector<e1_unit> units(ne);
+    std::vector<e1_prep> prep(ne);
+    for (int e = 0; e < n_epochs; e++)
+        for (int ch = 0; ch < max_chan; ch++)
+            for (int sp = 0; sp < S_; sp++)
+                e1_v2_prep(&recs[(size_t)e * max_chan + ch], delt, sp, e1_span_samples(&geo, sp, n_samp, tile),
+                           &prep[(size_t)ch * n_units + (size_t)e * S_ + sp]);
+    for (int ch = 0; ch < max_chan; ch++)
+        e1_v2_ideal_prefix(&prep[(size_t)ch * n_units], n_units, phase0[ch], &g[(size_t)ch * n_units]);
+    for (size_t i = 0; i < ne; i++)
+        dend[i] = e1_v2_drift_unit(&prep[i], g[i]);
+    for (int ch = 0; ch < max_chan; ch++) {
+        const size_t o = (size_t)ch * n_units;
+        e1_v2_estimate_prefix(&prep[o], n_units, phase0[ch], &g[o], &dend[o], &est[o]);
+    }
+    for (int ch = 0; ch < max_chan; ch++)
+        for (int u = 0; u < n_units; u++) {
+            const size_t i = (size_t)ch * n_units + u;
+            const int e = u / S_, sp = u - e * S_;
+            e1_v2_span_unit(&prep[i], u, phase0[ch], &est[i], tile,
+                            &ck1[((size_t)e * tpe + (size_t)sp * geo.span_tiles) * max_chan + ch], max_chan, &units[i]);
+        }
+    ck2 = ck1;
+    long bad_total = 0;
+    stats[0] = stats[1] = 0;
+    for (int ch = 0; ch < max_chan; ch++) {
+        const size_t o = (size_t)ch * n_units;
+        unsigned long long st1[2] = {0, 0}, st2[2] = {0, 0};
+        std::vector<e1_unit> u1(units.begin() + o, units.begin() + o + n_units);
+        const double p1 = e1_v2_chain(&prep[o], n_units, phase0[ch], tile, u1.data(), &ck1[ch], max_chan, &d1[o], st1);
+        // ---- the kernel's rounds
+        e1_chain_state cs;
+        e1_chain_init(&cs, phase0[ch]);
+        std::vector<double> x(round), Sv(round), D(round);
+        std::vector<int> Wv(round);
+        for (int e0 = 0; e0 < n_units; e0 += round) {
+            const int n = std::min(round, n_units - e0);
+            const e1_unit *su = &units[o + e0];
+            e1_trans *sd = &d2[o + e0];
+            int start = 0, restarts = 0;
+            while (start < n) {
+                double run = 0.0;
+                int wmax = -1;
+                for (int tid = 0; tid < n; tid++) { // the two inclusive scans
+                    x[tid] = 0.0;
+                    int wi = -1;
+                    if (tid >= start && su[tid].type == E1_UNIT_HAT && su[tid].last_k >= 1) {
+                        x[tid] = e1_add(su[tid].last_p, -su[tid].anchor_p);
+                        wi = tid;
+                    }
+                    run = e1_add(run, x[tid]);
+                    wmax = std::max(wmax, wi);
+                    Sv[tid] = run;
+                    Wv[tid] = wmax;
+                }
+                int bad = n;
+                for (int tid = start; tid < n; tid++) {
+                    const e1_unit *u = &su[tid];
+                    const double Tb = e1_add(cs.prev_p, e1_add(Sv[tid], -x[tid]));
+                    const int Wb = tid > 0 ? Wv[tid - 1] : -1;
+                    int p_ok, p_neg, p_k, p_u;
+                    if (Wb >= start) {
+                        const e1_unit *q = &su[Wb];
+                        p_ok = 1, p_neg = q->neg, p_k = q->last_k, p_u = e0 + Wb;
+                    } else {
+                        p_ok = cs.prev_ok, p_neg = cs.prev_neg, p_k = cs.prev_k, p_u = cs.prev_u;
+                    }
+                    D[tid] = e1_add(Tb, -u->anchor_p);
+                    const int ok = u->type == E1_UNIT_HAT && u->tie == 0 && p_ok && p_neg == u->neg && p_u == e0 + tid - u->anchor_back &&
+                                   p_k == u->anchor_k;
+                    if (!(ok && D[tid] >= u->lo && D[tid] < u->hi) && tid < bad)
+                        bad = tid;
+                }
+                for (int tid = start; tid < bad; tid++) {
+                    e1_trans tr;
+                    tr.a = tr.b = su[tid].neg ? -D[tid] : D[tid];
+                    tr.k_split = 0;
+                    tr.pad = 0;
+                    sd[tid] = tr;
+                }
+                if (bad > start) {
+                    const int tid = bad - 1;
+                    const e1_unit *u = &su[tid];
+                    cs.phi = e1_add(u->end_phi, u->neg ? -D[tid] : D[tid]);
+                    if (Wv[tid] >= start) {
+                        const e1_unit *q = &su[Wv[tid]];
+                        cs.prev_p = e1_add(cs.prev_p, Sv[tid]);
+                        cs.prev_k = q->last_k;
+                        cs.prev_u = e0 + Wv[tid];
+                        cs.prev_ok = 1;
+                        cs.prev_neg = q->neg;
+                    }
+                }
+                st2[1] += (unsigned long long)(bad - start);
+                if (bad >= n)
+                    break;
+                const int upto = ++restarts > 16 ? n : bad + 1;
+                for (int i = bad; i < upto; i++) {
+                    const int u_abs = e0 + i, ep = u_abs / S_, sp = u_abs - ep * S_;
+                    sd[i] = e1_v2_chain_step(&cs, &su[i], u_abs, prep[o + u_abs].sp, prep[o + u_abs].n, tile,
+                                             (prep[o + u_abs].n + tile - 1) / tile,
+                                             &ck2[((size_t)ep * tpe + (size_t)sp * geo.span_tiles) * max_chan + ch], max_chan, st2);
+                    stats[1]++;
+                }
+                start = upto;
+            }
+        }
+        stats[0] += st2[1];
+        for (int u = 0; u < n_units; u++) {
+            const e1_trans &a = d1[o + u], &b = d2[o + u];
+            if (e1_bits(a.a) != e1_bits(b.a) || e1_bits(a.b) != e1_bits(b.b) || a.k_split != b.k_split)
+                if (!(a.a == b.a && a.b == b.b && a.k_split == b.k_split))
+                    bad_total++;
+        }
+        if (p1 != cs.phi)
+            bad_total++;
+    }
+    return bad_total;
 }
 
 // Carrier planners only: serial walk (planner 1) against the parallel passes (planner 2), every

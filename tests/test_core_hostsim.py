@@ -334,6 +334,35 @@ def test_parallel_planner_ties_idle_gaps_resets_and_low_doppler():
     assert np.array_equal(a, b) and np.array_equal(pa, pb)
 
 
+@pytest.mark.parametrize("round_spans", [512, 64, 7])
+def test_chain_kernel_rounds_equal_the_serial_chain(round_spans):
+    """e1_v2_chain_kernel's algorithm (rounds of spans: optimistic scan of T = the true value after the most
+    recent wrap, D = T - guess for anchors any number of spans back, prefix commit, one serial step at the
+    first span that fails) transcribed for the host: the translations and the carried phase equal the
+    serial chain's on ordinary, low-Doppler (anchors up to 64 spans back, spans without a wrap in reach),
+    sign-changing and tie inputs, whatever the round length."""
+    fs = FS26
+    cases = [(low_doppler_recs(300, fs), None),
+             (U.synthetic_recs_fast(200, 12, fs, seed=5), None),
+             (U.synthetic_recs_fast(300, 12, fs, seed=6, f_max=80.0), np.linspace(-0.9, 0.9, 12))]
+    recs = U.synthetic_recs_fast(24, 8, fs, seed=9, max_chan=9)
+    for e in range(24):
+        f = _step_multiple_of_2m53(fs, 2500.0 + e)
+        recs[e, 0]["f_carr"], recs[e, 0]["f_code"] = f, 1.023e6 + f * 0.0006493506493506494
+        f = (e - 11.5) * 300.0
+        recs[e, 2]["f_carr"], recs[e, 2]["f_code"] = f, 1.023e6 + f * 0.0006493506493506494
+    recs[6:9, 3]["prn"] = 0
+    recs[12, 4]["flags"] = U.E1_REC_SET_PHASE
+    recs[12, 4]["carr_phase_init"] = 0.4321
+    cases.append((recs, np.linspace(-0.9, 0.9, 9)))
+    scan = serial = 0
+    for r, ph in cases:
+        bad, (a, b) = U.hostsim_chain_scan_compare(fs, 260000, r, ph, round_spans)
+        assert bad == 0
+        scan, serial = scan + a, serial + b
+    assert scan > 4 * serial
+
+
 def test_planner_is_exact_whatever_the_drift_estimates(monkeypatch):
     """The drift pass (e1_v2_drift_unit: the first 1/16 of each span walked exactly, its rounding drift
     scaled to the span) only feeds the guesses; the chain validates every span exactly.  With a constant

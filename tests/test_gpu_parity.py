@@ -183,6 +183,32 @@ def test_low_doppler_and_zero_crossings():
     s.close()
 
 
+def test_chain_scan_with_anchors_several_spans_back_equals_serial_planner(monkeypatch):
+    """Long runs with channels at 2 - 100 Hz of Doppler beside ordinary ones: most spans of the slow
+    channels hold no carrier wrap and anchor on a wrap up to 64 spans back.  The chain kernel takes
+    them through its parallel scan (T = true value after the most recent wrap, D = T - guess); the
+    carried phases must equal the one-thread-per-channel exact walk bit for bit, at both rates, and
+    nearly every span has to be accepted by the scan rather than walked serially."""
+    for fs, n_samp, n_ep in ((FS26, 260000, 1500), (FS25, 2500000, 150)):
+        recs = U.synthetic_recs_fast(n_ep, 12, fs, seed=31)
+        e = np.arange(n_ep)
+        for c, (f0, rate) in enumerate([(30, -0.01), (-5, 0.002), (2.5, 0.0), (100, -0.05), (-45, 0.015), (75, 0.0)]):
+            f = f0 + rate * e
+            recs[:, c]["f_carr"] = f
+            recs[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+        s = E.Synth(fs, n_samp, 12)
+        pa = s.plan_phases(recs)
+        st = s.stats()
+        s.close()
+        monkeypatch.setenv("E1B200_SERIAL_PLANNER", "1")
+        s = E.Synth(fs, n_samp, 12)
+        pb = s.plan_phases(recs)
+        s.close()
+        monkeypatch.delenv("E1B200_SERIAL_PLANNER")
+        assert np.array_equal(pa, pb), (fs, pa - pb)
+        assert st.serial_epochs < 0.02 * (st.hat_epochs + st.serial_epochs), (st.serial_epochs, st.hat_epochs)
+
+
 def test_result_independent_of_ambiguity_threshold(monkeypatch):
     fs, n_samp, nch = FS25, 500000, 12
     recs = U.synthetic_recs(2, nch, fs, seed=21)
