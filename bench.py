@@ -23,6 +23,7 @@ fixed 16-channel / 2.6 MS/s build that needs its RINEX tree) on rank 0's host co
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -77,7 +78,12 @@ def ncu_summary_numbers():
     (profiles/*synth_ncu_summary.txt, one launch): DRAM traffic (dram__bytes_read.sum +
     dram__bytes_write.sum) and warp instructions executed (smsp__inst_executed.sum)."""
     best = None
-    for f in sorted((ROOT / "profiles").glob("*synth_ncu_summary.txt")):
+
+    def version(f):     # r<round>_v<build>_...: numeric order (v10 after v9)
+        m = re.match(r"r(\d+)_v(\d+)_", f.name)
+        return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+
+    for f in sorted((ROOT / "profiles").glob("*synth_ncu_summary.txt"), key=version):
         if "cfg3" in f.name:
             continue
         tot, inst, mult = 0.0, None, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -463,10 +469,10 @@ def main():
                        "host_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "kernel": "e1_synth_kernel", "peak_source": peak_src,
+                         "kernel": "e1_synth_pair_kernel", "peak_source": peak_src,
                          "ms_per_launch": per_launch_ms, "launches_per_step": synth_launches / args.steps,
                          "planner_ms_per_step": plan_ms / args.steps, "synth_ms_per_step": synth_ms / args.steps,
-                         "note": f"issue-bound, not HBM-bound: {n_chan} channel visits x ~14 integer instructions per 4-byte sample "
+                         "note": f"issue-bound, not HBM-bound: {n_chan} channel visits x ~{(issue or {}).get('inst_per_channel_sample', 12.3):.1f} integer instructions per 4-byte sample "
                                  "(see roofline_issue; ncu: profiles/*synth_ncu_summary.txt); HBM time of the same bytes "
                                  f"would be {bytes_per_launch / peak / 1e6:.2f} ms"},
             "roofline_issue": issue,
