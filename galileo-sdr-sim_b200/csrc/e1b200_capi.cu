@@ -169,7 +169,7 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->elide = !env_int("E1B200_NO_ELIDE", 0);
     ctx->serial_planner = (cfg->flags & E1B200_CFG_SERIAL_PLANNER) || env_int("E1B200_SERIAL_PLANNER", 0);
     const size_t epoch_bytes = (size_t)cfg->samples_per_epoch * 4;
-    long be = (long)(((size_t)env_int("E1B200_BATCH_MB", 64) << 20) / epoch_bytes);
+    long be = (long)(((size_t)env_int("E1B200_BATCH_MB", 96) << 20) / epoch_bytes);
     ctx->batch_epochs = be < 1 ? 1 : (be > 512 ? 512 : (int)be);
     const size_t ck_epoch_bytes = (sizeof(e1_tile_ck) * (size_t)cfg->max_chan + e1_blk_bytes(cfg->max_chan)) * (size_t)ctx->tiles_per_epoch;
     long pe = (long)(((size_t)env_int("E1B200_PLAN_MB", 2048) << 20) / ck_epoch_bytes);
