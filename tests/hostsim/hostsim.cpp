@@ -71,6 +71,11 @@ static unsigned long long g_clean_tiles = 0, g_checked_tiles = 0, g_clean_violat
 unsigned long long hs_clean_tiles(void) { return g_clean_tiles; }
 unsigned long long hs_checked_tiles(void) { return g_checked_tiles; }
 unsigned long long hs_clean_violations(void) { return g_clean_violations; }
+// largest distance seen, in units of 2^-32 half-chip, between the code fraction the runs before a tile's code
+// wrap step (HA + j dH) and the one the runs after it step (HB + j dH): e1_par_clean searches ONE sequence
+// for the whole tile and widens its zone by thr_code for this
+static double g_max_ab = 0.0;
+double hs_max_code_ab_units(void) { return g_max_ab; }
 
 // Whole pipeline on the host.  lut: int32[642][32] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
@@ -169,6 +174,12 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                 e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile,
                             e1_trans_at(&delta[(size_t)ch * n_units + (size_t)e * S + sp], (t - sp * geo.span_tiles) * tile), tc_code,
                             &par[nact]);
+                if (run == E1C_MAX_RUN && par[nact].j_w != E1C_NO_WRAP && !(par[nact].misc & E1_PAR_FORCE)) {
+                    const int64_t d51 = (int64_t)((par[nact].HA - par[nact].HB) << 13) >> 13; // mod 2^51, signed
+                    const double units = (double)(d51 < 0 ? -d51 : d51) / 524288.0;
+                    if (units > g_max_ab)
+                        g_max_ab = units;
+                }
                 if (run == E1C_MAX_RUN) { // e1_clean_kernel
                     if (e1_par_clean(&par[nact], tile, tc_carr, lim_carr, lim_code, thr_code)) {
                         par[nact].misc |= E1_PAR_CLEAN;

@@ -432,5 +432,8 @@ def test_tiles_marked_clean_never_hold_a_flagged_run():
         slow += int(st[2])
     clean, checked = hs.hs_clean_tiles() - c0, hs.hs_checked_tiles() - k0
     assert hs.hs_clean_violations() == 0
+    # one code sequence per tile: the fraction stepped after the tile's code wrap stays within thr_code of the
+    # one stepped before it (what e1_par_clean widens its zone by)
+    assert 0.0 < hs.hs_max_code_ab_units() <= 8192 / 512.0 * 1.001 + 3.0
     assert clean > 0 and checked > 0 and slow > 0
     assert 0.9 < clean / (clean + checked) < 0.995, (clean, checked)
