@@ -6,6 +6,8 @@
  *                            the parallel exact carrier planner (see "parallel carrier planner" in e1_core.h)
  *   e1_plan_carr_kernel      the same checkpoints by one serial walk per channel (debug / comparison)
  *   e1_finalize_kernel       checkpoints + translations -> one parameter block per tile
+ *   e1_clean_kernel          tile-level ambiguity test (e1_par_clean): marks the (tile, channel) sets whose runs
+ *                            cannot be ambiguous, so the sample loop skips its per-sample tracking for them
  *   e1_synth_pair_kernel     the sample loop (src/galileo-sdr.cpp:481-539): per sample, all channels,
  *                            int32 accumulate, packed int16 I/Q, 128-bit stores; 32 samples per thread
  *   e1_synth_kernel<R>       the same with R = 4, 8 or 16 samples per thread (tiles shorter than 8192 samples)
