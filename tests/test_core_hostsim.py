@@ -361,6 +361,15 @@ def test_chain_kernel_rounds_equal_the_serial_chain(round_spans):
         assert bad == 0
         scan, serial = scan + a, serial + b
     assert scan > 4 * serial
+    # 25 MS/s: 306 tiles per block, spans of 39 tiles, slow channels beside ordinary ones
+    r25 = U.synthetic_recs_fast(40, 10, FS25, seed=8)
+    e = np.arange(40)
+    for c, (f0, rate) in enumerate([(30, -0.01), (-5, 0.002), (2.5, 0.0), (100, -0.05)]):
+        f = f0 + rate * e
+        r25[:, c]["f_carr"] = f
+        r25[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+    bad, _ = U.hostsim_chain_scan_compare(FS25, 2500000, r25, None, round_spans)
+    assert bad == 0
 
 
 def test_planner_is_exact_whatever_the_drift_estimates(monkeypatch):
