@@ -18,6 +18,8 @@
  *     (src/galileo-sdr.cpp:481-539)
  *   chan[i].carr_phase carried across blocks               e1b200_get/set_carrier_phase
  *     (src/galileo-sdr.cpp:531-532)
+ *   (nothing: diagnostics of this library)                 e1b200_get_timing / get_stats / last_error,
+ *                                                          e1b200_selftest_any_hit
  *
  * Conventions: plain C linkage, no exceptions cross the boundary, every call returns 0 or a
  * negative E1B200_E* code, the opaque context owns all device memory, the caller owns every
