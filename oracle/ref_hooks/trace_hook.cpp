@@ -1,7 +1,10 @@
 // Trace dump for the reference oracle build (see trace_pre.h).  Test infrastructure.
 // One record per (epoch, active slot), written at the first sample of each 0.1 s block:
 // exactly the state the loop at src/galileo-sdr.cpp:481-539 consumes.
-#include "/root/reference/include/galileo-sdr.h"
+#ifndef E1_REF_HEADER
+#define E1_REF_HEADER "/root/reference/include/galileo-sdr.h" /* patched builds (make ref25 / ref36) point this at their scratch copy */
+#endif
+#include E1_REF_HEADER
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -10,7 +10,10 @@
 // struct the reference declares uninitialised on the stack (src/galileo-sdr.cpp:139,
 // `vflg` is read at src/iono.cpp:37 but never written) before readRinexV3 fills it.
 #pragma once
-#include "/root/reference/include/galileo-sdr.h"
+#ifndef E1_REF_HEADER
+#define E1_REF_HEADER "/root/reference/include/galileo-sdr.h" /* patched builds (make ref25 / ref36) point this at their scratch copy */
+#endif
+#include E1_REF_HEADER
 
 void e1_oracle_trace_hook(int line, int isamp, int iumd, const channel_t *chan, const galtime_t *grx);
 int e1_oracle_pinned_rinex(std::vector<ephem_t> eph_vector[MAX_SAT], ionoutc_t *ionoutc, char *fname);

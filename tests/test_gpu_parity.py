@@ -56,6 +56,31 @@ def test_paris45_all_blocks_match_reference_golden():
     s.close()
 
 
+@pytest.mark.parametrize("name,fs,n,md5", [
+    ("fs25", FS25, 2500000, "038c859da001e2cf45c0528f3864adc1"),
+    ("ch36", FS26, 260000, "09ea87819b295a90d2295b0554d7a5c2"),
+    ("fs25ch36", FS25, 2500000, "542bc0887b3f81897f2af436ac42ab89"),
+])
+def test_patched_reference_goldens(name, fs, n, md5):
+    """The rates and channel counts the BASELINE configs are quoted on, against bytes the reference itself
+    wrote when built with those constants (oracle/ref_patches/*.diff: SAMP_RATE 25e6; MAX_CHAN 36 with the
+    elevation mask off = all 24 satellites of the RINEX file, 35 s across the re-allocation and every
+    channel's page turns; both): every block's SHA-256 and the whole file's md5."""
+    recs, phase, header, sha = gold(name)
+    s = E.Synth(fs, n, recs.shape[1])
+    out = s.synth_epochs(recs)
+    blocks = out.reshape(recs.shape[0], n, 2)
+    bad = [e for e in range(recs.shape[0]) if hashlib.sha256(blocks[e].tobytes()).hexdigest() != sha[e]]
+    assert not bad, bad[:10]
+    assert hashlib.md5(out.tobytes()).hexdigest() == md5 == header.split()[2]
+    # the carried carrier phase after the run is the reference's: its trace holds the phase at the top of
+    # the last block, the oracle (pinned to the same bytes on CPU) carries it over that block
+    _, ph = U.oracle_synth(fs, n, recs[-1:], np.nan_to_num(phase[-1]), threads=8)
+    act = recs[-1]["prn"] > 0
+    assert np.array_equal(s.carrier_phases()[act], ph[act])
+    s.close()
+
+
 @pytest.mark.parametrize("fs,n_samp,n_chan,max_chan,n_epochs", [
     (FS26, 260000, 8, 16, 3),
     (FS26, 260000, 36, 36, 2),

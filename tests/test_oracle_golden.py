@@ -33,6 +33,35 @@ def test_oracle_matches_reference_blocks(name, epochs):
         assert hashlib.sha256(out[e].tobytes()).hexdigest() == sha[epochs.start + e], f"{name} block {e}"
 
 
+# Patched builds of the reference (oracle/ref_patches/*.diff applied by `make -C oracle refp`; fixtures by
+# tools/make_golden.py): the rates / channel counts of BASELINE configs[1]-[4].
+PATCHED = {  # name: (fs, samples per block, MAX_CHAN, satellites, blocks, md5 of the reference's file)
+    "fs25": (U.fs_as_reference(25e6), 2500000, 16, 8, 29, "038c859da001e2cf45c0528f3864adc1"),
+    "ch36": (FS, 260000, 36, 24, 349, "09ea87819b295a90d2295b0554d7a5c2"),
+    "fs25ch36": (U.fs_as_reference(25e6), 2500000, 36, 24, 29, "542bc0887b3f81897f2af436ac42ab89"),
+}
+
+
+@pytest.mark.parametrize("name,epochs", [("fs25", slice(0, 12)), ("ch36", slice(0, 349)), ("fs25ch36", slice(0, 10))])
+def test_oracle_matches_patched_reference_blocks(name, epochs):
+    """25 MS/s, 24 satellites in 36 slots with the elevation mask off (35 s: every channel turns its page,
+    the 30 s re-allocation runs), and both together: the oracle's blocks equal, hash for hash, the bytes the
+    reference ITSELF wrote when built with those constants.  The whole ch36 file (its md5) is checked here;
+    the 25 MS/s ones in full on the GPU side (tests/test_gpu_parity.py), a slice here to keep the CPU suite short."""
+    fs, n, max_chan, n_sat, n_blocks, md5 = PATCHED[name]
+    recs, phase, header, sha = load(name)
+    assert recs.shape == (n_blocks, max_chan) and header.split()[2] == md5
+    assert len(set(int(x) for x in recs["prn"].ravel()) - {0}) == n_sat
+    ph0 = None
+    r = recs[epochs]
+    out, _ = U.oracle_synth(fs, n, r, ph0, threads=8)
+    out = out.reshape(r.shape[0], n, 2)
+    for e in range(r.shape[0]):
+        assert hashlib.sha256(out[e].tobytes()).hexdigest() == sha[epochs.start + e], f"{name} block {e}"
+    if r.shape[0] == n_blocks:
+        assert hashlib.md5(out.tobytes()).hexdigest() == md5
+
+
 def test_oracle_cfg1_file_md5():
     recs, _, header, _ = load("cfg1")
     out, _ = U.oracle_synth(FS, N, recs)

@@ -25,13 +25,23 @@ import e1util as U  # noqa: E402
 
 REF = Path("/root/reference")
 BIN = ROOT / "oracle" / "_ref"
-N = 260000
 
+NAV = str(REF / "rinex_files/week171.rnx")
+# name: (binary suffix, samples per block, fs, MAX_CHAN of that build, args)
 SCENARIOS = {
     # BASELINE.json configs[0]
-    "cfg1": ["-l", "-6,51,100", "-e", str(REF / "rinex_files/week171.rnx"), "-d", "10"],
+    "cfg1": ("", 260000, 2.6e6, 16, ["-l", "-6,51,100", "-e", NAV, "-d", "10"]),
     # second pin: other site/time, grx ~ 43200 s, crosses the 30 s re-allocation check (:545-562)
-    "paris45": ["-l", "48.85,2.35,35", "-t", "2021/06/20,11:59:40", "-e", str(REF / "rinex_files/week171.rnx"), "-d", "45"],
+    "paris45": ("", 260000, 2.6e6, 16, ["-l", "48.85,2.35,35", "-t", "2021/06/20,11:59:40", "-e", NAV, "-d", "45"]),
+    # Patched builds of the reference (oracle/ref_patches/*.diff, `make -C oracle refp`): the rates and channel
+    # counts of BASELINE configs[1]-[4], which the as-shipped build cannot run.
+    #   fs25      SAMP_RATE 25e6, the 8 satellites of configs[0], 3 s
+    #   ch36      MAX_CHAN 36 + elevation mask off: all 24 satellites of the RINEX file, 35 s (crosses the
+    #             30 s re-allocation and every channel's page turns) -- the channel count configs[1] is quoted on
+    #   fs25ch36  both: 24 satellites at 25 MS/s, 3 s -- the shape of configs[2]
+    "fs25": ("_fs25", 2500000, 25e6, 16, ["-l", "-6,51,100", "-e", NAV, "-d", "3"]),
+    "ch36": ("_ch36", 260000, 2.6e6, 36, ["-l", "-6,51,100", "-e", NAV, "-d", "35"]),
+    "fs25ch36": ("_fs25ch36", 2500000, 25e6, 36, ["-l", "-6,51,100", "-e", NAV, "-d", "3"]),
 }
 
 
@@ -45,22 +55,25 @@ def run(binary, args, out, trace=None):
 
 
 def main():
-    subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "ref", "libe1oracle.so"])
+    subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "ref", "refp", "libe1oracle.so"])
     gold = ROOT / "tests" / "golden"
     gold.mkdir(exist_ok=True)
+    only = sys.argv[1:]
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
-        for name, args in SCENARIOS.items():
+        for name, (suffix, N, fs_nom, max_chan, args) in SCENARIOS.items():
+            if only and name not in only:
+                continue
             out, tr, plain = td / "o.ishort", td / "t.bin", td / "p.ishort"
-            run(BIN / "usrp_galileo_trace", args, out, tr)
-            run(BIN / "usrp_galileo", args, plain)
+            run(BIN / f"usrp_galileo{suffix}_trace", args, out, tr)
+            run(BIN / f"usrp_galileo{suffix}", args, plain)
             raw = out.read_bytes()
             assert raw == plain.read_bytes(), "trace hook changed the output"
             iq = np.frombuffer(raw, np.int16).reshape(-1, N, 2)
             trace = np.fromfile(tr, U.TRACE_DTYPE)
-            recs, phase = U.trace_to_recs(trace, 16)
+            recs, phase = U.trace_to_recs(trace, max_chan)
             assert recs.shape[0] == iq.shape[0]
-            mine, _ = U.oracle_synth(U.fs_as_reference(2.6e6), N, recs)
+            mine, _ = U.oracle_synth(U.fs_as_reference(fs_nom), N, recs, threads=8)
             assert np.array_equal(mine.reshape(iq.shape), iq), "oracle restatement differs from the reference"
             np.savez_compressed(gold / f"{name}_recs.npz", recs=recs, phase=phase,
                                 grx=np.array(sorted(set(trace["grx"]))))
@@ -72,7 +85,7 @@ def main():
             keep = sorted(set([0, iq.shape[0] - 1] + turn[:2]))
             np.savez_compressed(gold / f"{name}_samples.npz", epochs=np.array(keep),
                                 head=np.stack([iq[e, :4096] for e in keep]), tail=np.stack([iq[e, -4096:] for e in keep]))
-            print(name, iq.shape, "md5", hashlib.md5(raw).hexdigest(), "page-turn epochs", turn[:4])
+            print(name, iq.shape, "satellites", sorted(set(int(x) for x in recs["prn"].ravel()) - {0}), "md5", hashlib.md5(raw).hexdigest(), "page-turn epochs", turn[:4])
 
 
 if __name__ == "__main__":
