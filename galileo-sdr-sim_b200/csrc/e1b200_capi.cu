@@ -732,6 +732,37 @@ int e1b200_restate(double rho_prev, double rho_cur, double dt, double grx_sec, d
     return E1B200_OK;
 }
 
+/* How many times the reference's loop takes its code-wrap branch (src/galileo-sdr.cpp:491-494) inside one
+ * block that starts from code_phase0: the wrap test runs at the TOP of samples 0 .. n_samp-1, so a sum that
+ * reaches 4092 on the block's last addition is not counted (the next computeCodePhase absorbs it).  Exact:
+ * the same roundings as the loop's `code_phase += f_code * delt`, walked binade by binade (e1_walk_up).
+ * The caller adds it to ibit0 to know whether the loop would have called generateINavMsg (:497-506). */
+int e1b200_code_wraps(double fs_hz, int32_t n_samp, double code_phase0, double f_code, int32_t *n_wraps)
+{
+    if (!n_wraps || !(fs_hz > 0.0) || n_samp < 0 || !(code_phase0 >= 0.0) || !(f_code > 0.0))
+        return E1B200_EINVAL;
+    const double sc = (1.0 / fs_hz) * f_code; /* f_code * delt, delt = 1/fs (:162, :528); one rounding each, commutative */
+    if (!(sc < (double)E1C_CODE_LEN))
+        return E1B200_EINVAL;
+    double cp = code_phase0;
+    int wraps = 0;
+    if (n_samp > 0 && cp >= (double)E1C_CODE_LEN) { /* the test at sample 0 */
+        cp -= (double)E1C_CODE_LEN;
+        wraps++;
+        if (cp >= (double)E1C_CODE_LEN)
+            return E1B200_EINVAL;
+    }
+    int64_t k = 0;
+    while (k < n_samp) {
+        int w = 0;
+        cp = e1_walk_up(cp, sc, (double)E1C_CODE_LEN, &k, n_samp, &w);
+        if (w && k < n_samp)
+            wraps++;
+    }
+    *n_wraps = wraps;
+    return E1B200_OK;
+}
+
 int e1b200_get_timing(e1b200_ctx *ctx, e1b200_timing *out)
 {
     if (!ctx || !out)
@@ -795,5 +826,16 @@ int e1b200_host_alloc(void **p, size_t bytes)
 }
 
 int e1b200_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? E1B200_OK : E1B200_ECUDA; }
+
+/* Pin a buffer the caller allocated itself (the reference's calloc'd iq_buff, src/galileo-sdr.cpp:326, which
+ * it also frees itself at :655) so the D2H into it is a DMA at PCIe rate. */
+int e1b200_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes)
+        return E1B200_EINVAL;
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? E1B200_OK : E1B200_ECUDA;
+}
+
+int e1b200_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? E1B200_OK : E1B200_ECUDA; }
 
 } /* extern "C" */

@@ -53,6 +53,7 @@ SYMBOLS = [
     "e1b200_synth_epochs_device", "e1b200_sync", "e1b200_synth_ranges", "e1b200_synth_ranges_device", "e1b200_plan_phases",
     "e1b200_restate", "e1b200_get_timing", "e1b200_get_stats", "e1b200_stream", "e1b200_last_error",
     "e1b200_version", "e1b200_host_alloc", "e1b200_host_free", "e1b200_selftest_any_hit",
+    "e1b200_code_wraps", "e1b200_host_register", "e1b200_host_unregister",
 ]
 
 _lib = None
@@ -93,6 +94,9 @@ def load():
     lib.e1b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.e1b200_host_free.argtypes = [vp]
     lib.e1b200_selftest_any_hit.argtypes = [C.c_int, C.c_int, vp, vp]
+    lib.e1b200_code_wraps.argtypes = [C.c_double, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32)]
+    lib.e1b200_host_register.argtypes = [vp, C.c_size_t]
+    lib.e1b200_host_unregister.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -106,6 +110,15 @@ def restate(rho_prev, rho_cur, dt, grx_sec):
     if rc:
         raise E1B200Error(f"e1b200_restate: {rc}")
     return f[0].value, f[1].value, f[2].value, ib.value, ip.value
+
+
+def code_wraps(fs_hz, n_samp, code_phase0, f_code):
+    """How often the reference's loop wraps the code phase inside one block (src/galileo-sdr.cpp:491-494), exactly."""
+    n = C.c_int32()
+    rc = load().e1b200_code_wraps(fs_hz, n_samp, code_phase0, f_code, n)
+    if rc:
+        raise E1B200Error(f"e1b200_code_wraps: {rc}")
+    return n.value
 
 
 class PinnedBuffer:

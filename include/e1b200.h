@@ -18,6 +18,9 @@
  *     (src/galileo-sdr.cpp:481-539)
  *   chan[i].carr_phase carried across blocks               e1b200_get/set_carrier_phase
  *     (src/galileo-sdr.cpp:531-532)
+ *   `code_phase -= 4092; ibit++` count of a block, i.e.     e1b200_code_wraps
+ *     whether the in-loop generateINavMsg ran (:491-506)
+ *   calloc'd iq_buff (:326)                                 e1b200_host_register / host_alloc
  *   (nothing: diagnostics of this library)                 e1b200_get_timing / get_stats / last_error,
  *                                                          e1b200_selftest_any_hit
  *
@@ -138,6 +141,14 @@ int  e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_re
 int  e1b200_restate(double rho_prev, double rho_cur, double dt, double grx_sec,
                     double *f_carr, double *f_code, double *code_phase0, int32_t *ibit0, int32_t *ipage);
 
+/* Number of times the reference's loop takes its code-wrap branch (`code_phase -= 4092; ibit++`,
+ * src/galileo-sdr.cpp:491-494) inside one block of n_samp samples that starts from code_phase0 -- exact, same
+ * roundings as the loop.  ibit0 + *n_wraps >= 500 is the loop's condition for calling generateINavMsg
+ * in-loop (:497-506): the caller uses it to decide whether chan[i].page is replaced by page_next after
+ * the block (a wrap that falls exactly on the block's end is NOT counted: the next computeCodePhase absorbs
+ * it and the reference keeps the stale page).  Host arithmetic, needs no device or context.              */
+int  e1b200_code_wraps(double fs_hz, int32_t n_samp, double code_phase0, double f_code, int32_t *n_wraps);
+
 int  e1b200_get_timing(e1b200_ctx *ctx, e1b200_timing *out);
 
 /* Exactness bookkeeping and launch geometry (for tests, bench and profiles).                */
@@ -168,6 +179,9 @@ int  e1b200_selftest_any_hit(int device, int n_cases, const int64_t *cases, int3
  * (src/galileo-sdr.cpp:542,588) can stay unchanged while D2H runs at full PCIe rate        */
 int  e1b200_host_alloc(void **p, size_t bytes);
 int  e1b200_host_free(void *p);
+/* ... or pin the buffer the reference calloc()s and free()s itself (:326, :655) in place               */
+int  e1b200_host_register(void *p, size_t bytes);
+int  e1b200_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

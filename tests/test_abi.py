@@ -96,3 +96,39 @@ def test_bench_reads_the_newest_ncu_summary():
                     if "cfg3" not in f.name)
     assert name == f"r1_v{builds[-1]}_synth_ncu_summary.txt" and (root / "profiles" / name).exists()
     assert 3.0e9 < traffic < 4.0e9 and 5.0e9 < inst < 2.0e10
+
+
+def test_code_wraps_equals_the_literal_loop(lib):
+    """e1b200_code_wraps against the reference's own statements (src/galileo-sdr.cpp:491-494, :528) run
+    sample by sample, including starts at or above 4092 (wrap at sample 0) and blocks whose last addition
+    reaches 4092 (not counted: the wrap test of that value belongs to the next block)."""
+    rng = np.random.default_rng(11)
+    for fs_nom, n in ((2.6e6, 260000), (25e6, 250000), (4e6, 1000)):
+        fs = U.fs_as_reference(fs_nom)
+        delt = 1.0 / fs
+        for trial in range(6):
+            f_code = 1.023e6 + rng.uniform(-3, 3)
+            cp0 = float(rng.uniform(0, 4092)) if trial else 4092.0 + 1e-9
+            sc = np.float64(f_code) * np.float64(delt)
+            cp, wraps = np.float64(cp0), 0
+            for _ in range(n):
+                if cp >= 4092.0:
+                    cp -= 4092.0
+                    wraps += 1
+                cp = cp + sc
+            assert E.code_wraps(fs, n, cp0, f_code) == wraps, (fs_nom, trial)
+    # a block that ends exactly on a wrap: the start is chosen so that the last addition lands on >= 4092
+    fs, n, f_code = U.fs_as_reference(2.6e6), 10400, 1.023e6
+    sc = np.float64(f_code) * np.float64(1.0 / fs)
+    cp = np.float64(0.0)
+    for _ in range(n):
+        cp = cp + sc
+    start = float(4092.0 - cp + 1e-9)          # after n additions the sum is just above 4092, never tested in this block
+    lit, c = 0, np.float64(start)
+    for _ in range(n):
+        if c >= 4092.0:
+            c -= 4092.0
+            lit += 1
+        c = c + sc
+    assert c >= 4092.0 and lit == 0 and E.code_wraps(fs, n, start, f_code) == 0
+    assert E.code_wraps(fs, n + 1, start, f_code) == 1
