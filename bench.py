@@ -222,6 +222,53 @@ def cpu_baseline(fs, n_samp, n_chan, seconds_target=15.0):
                       f"oracle/e1_oracle.c (channels split over {threads} threads)"}
 
 
+def parity_check(d_out, recs, fs, n_samp, n_chan, world, use_ranges, dt_epoch=0.100000023142):
+    """The bytes the timed loop left in d_out against the CPU oracle (oracle/e1_oracle.c, checker only, after the
+    timed regions).  All blocks when the host has the cores for it (~15 s budget), else a spread: first, last,
+    blocks that turn a page, and evenly spaced ones -- each started from the phase the LITERAL carrier recurrence
+    (e1o_carrier_phases, no planner involved) reaches at the top of that block.  Returns the dict for the JSON line."""
+    import e1util as U
+    t0 = time.perf_counter()
+    n_epochs = recs.shape[0]
+    if use_ranges:                       # pseudorange records: computeCodePhase by the oracle's restatement
+        er = np.zeros(recs.shape, U.REC_DTYPE)
+        for k in ("prn", "flags", "carr_phase_init", "page_cur", "page_next"):
+            er[k] = recs[k]
+        for e in range(n_epochs):
+            for c in range(recs.shape[1]):
+                r = recs[e, c]
+                if r["prn"] > 0:
+                    fc, fcode, cp, ib, _ = U.oracle_restate(float(r["rho_prev"]), float(r["rho_cur"]), dt_epoch, float(r["grx_sec"]))
+                    er[e, c]["f_carr"], er[e, c]["f_code"], er[e, c]["code_phase0"], er[e, c]["ibit0"] = fc, fcode, cp, ib
+        recs = er
+    threads = max(1, min((os.cpu_count() or 1) // world, n_chan))
+    budget = int(15.0 * 69e6 * threads / (n_samp * n_chan))          # blocks the oracle does in ~15 s (69 M channel-samples/s/thread)
+    out_blocks = d_out.view(n_epochs, n_samp * 2)
+    differing = 0
+    if budget >= n_epochs:
+        blocks, how = list(range(n_epochs)), "all blocks"
+        ph, step = None, 256
+        for a in range(0, n_epochs, step):
+            ref, ph = U.oracle_synth(fs, n_samp, recs[a:a + step], ph, threads=threads)
+            got = out_blocks[a:a + step].cpu().numpy().reshape(-1, 2)
+            differing += int(np.count_nonzero((got != ref).any(axis=1)))
+    else:
+        act = recs["prn"] > 0
+        turns = np.nonzero((act & (recs["ibit0"] + 26 >= 500)).any(axis=1))[0]
+        n = max(min(budget * 2 // 3, n_epochs), 3)                     # a third of the budget goes to the carrier-only walk
+        pick = set(np.linspace(0, n_epochs - 1, max(n - min(len(turns), n // 3), 2)).astype(int).tolist())
+        pick |= set(turns[np.linspace(0, len(turns) - 1, min(len(turns), n // 3)).astype(int)].tolist()) if len(turns) else set()
+        blocks, how = sorted(pick), "first, last, page-turn and evenly spaced blocks; start phases from the literal carrier recurrence"
+        phases, _ = U.oracle_carrier_phases(fs, n_samp, recs, threads=threads)
+        for b in blocks:
+            ref, _ = U.oracle_synth(fs, n_samp, recs[b:b + 1], phases[b], threads=threads)
+            got = out_blocks[b].cpu().numpy().reshape(-1, 2)
+            differing += int(np.count_nonzero((got != ref).any(axis=1)))
+    return {"blocks": len(blocks), "of": n_epochs, "samples_compared": len(blocks) * n_samp, "differing_samples": differing,
+            "what": f"d_out of the last timed step vs oracle/e1_oracle.c ({how})", "threads": threads,
+            "seconds": round(time.perf_counter() - t0, 1)}
+
+
 REF_BIN = ROOT / "oracle" / "_ref" / "usrp_galileo"
 NAV_SUBSET = ROOT / "tests" / "golden" / "week171_subset.rnx"
 
@@ -319,6 +366,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed output (profiling runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -441,6 +489,17 @@ def main():
                "api": ("e1b200_synth_ranges" if use_ranges else "e1b200_synth_epochs") + " (host buffers, pinned), timed on the host clock around the call"}
         h_recs.free(), h_out.free()
 
+    # ---- the timed bytes against the oracle (after both timed regions) ---------------------
+    parity = None
+    if not args.no_parity:
+        unbind_cpus()
+        parity = parity_check(d_out, recs, fs, n_samp, n_chan, world, use_ranges)
+        if dist is not None:                                            # every rank checked its own segment
+            t = torch.tensor([parity["blocks"], parity["samples_compared"], parity["differing_samples"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            parity.update(blocks=int(t[0].item()), samples_compared=int(t[1].item()), differing_samples=int(t[2].item()),
+                          of=n_epochs * world, what=parity["what"] + f", summed over {world} ranks")
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         per_launch_ms = synth_ms / max(synth_launches, 1)
@@ -483,6 +542,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        line["parity_check"] = parity
         if not args.no_cpu_baseline and world == 1:
             unbind_cpus()
             ref = reference_binary_cfg1() if args.workload == "cfg1" else None

@@ -228,3 +228,62 @@ void e1o_synth_epochs_mt(double fs_hz, int n_samp, int max_chan, int n_epochs,
         free(acc[t]);
     free(acc); free(jobs); free(th);
 }
+
+/* ---- carrier recurrence alone (src/galileo-sdr.cpp:531-532, src/channel.cpp:98-99) -----------------
+ * The literal `phi += f_carr * delt; phi -= (long)phi` of every sample of every block, nothing else:
+ * phases[e][ch] receives the phase each channel holds at the top of block e.  Lets a checker start the
+ * full loop at any block of a long run from a phase that no planner had a hand in.  Channels split
+ * over threads (each channel's walk is independent). */
+typedef struct {
+    double delt;
+    int n_samp, max_chan, n_epochs, c0, c1;
+    const e1_epoch_rec *recs;
+    double *carr_phase, *phases;
+} ph_job;
+
+static void *ph_worker(void *arg)
+{
+    ph_job *j = (ph_job *)arg;
+    for (int ch = j->c0; ch < j->c1; ch++) {
+        double phi = j->carr_phase[ch];
+        for (int e = 0; e < j->n_epochs; e++) {
+            const e1_epoch_rec *r = &j->recs[(size_t)e * j->max_chan + ch];
+            if (r->prn > 0) {
+                if (r->flags & E1_REC_SET_PHASE)
+                    phi = r->carr_phase_init;
+                j->phases[(size_t)e * j->max_chan + ch] = phi;
+                const double f_carr = r->f_carr, delt = j->delt;
+                for (int k = 0; k < j->n_samp; k++) {
+                    phi += f_carr * delt; /* :531 */
+                    phi -= (long)phi;     /* :532 */
+                }
+            } else {
+                j->phases[(size_t)e * j->max_chan + ch] = phi;
+            }
+        }
+        j->carr_phase[ch] = phi;
+    }
+    return NULL;
+}
+
+void e1o_carrier_phases(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs,
+                        double *carr_phase, double *phases, int n_threads)
+{
+    if (max_chan < 1)
+        return;
+    if (n_threads > max_chan) n_threads = max_chan;
+    if (n_threads < 1) n_threads = 1;
+    ph_job *jobs = (ph_job *)calloc((size_t)n_threads, sizeof *jobs);
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof *th);
+    for (int t = 0; t < n_threads; t++) {
+        ph_job *j = &jobs[t];
+        j->delt = 1.0 / fs_hz; j->n_samp = n_samp; j->max_chan = max_chan; j->n_epochs = n_epochs;
+        j->c0 = (int)((long)max_chan * t / n_threads);
+        j->c1 = (int)((long)max_chan * (t + 1) / n_threads);
+        j->recs = recs; j->carr_phase = carr_phase; j->phases = phases;
+        pthread_create(&th[t], NULL, ph_worker, j);
+    }
+    for (int t = 0; t < n_threads; t++)
+        pthread_join(th[t], NULL);
+    free(jobs); free(th);
+}

@@ -37,6 +37,12 @@ void e1o_synth_epochs(double fs_hz, int n_samp, int max_chan, int n_epochs,
 void e1o_synth_epochs_mt(double fs_hz, int n_samp, int max_chan, int n_epochs,
                          const e1_epoch_rec *recs, double *carr_phase, int16_t *out, int n_threads);
 
+/* The carrier recurrence alone (:531-532), literally, over n_epochs blocks: phases[n_epochs][max_chan] =
+ * chan[i].carr_phase at the top of every block; carr_phase[max_chan] is read and updated.  For checkers
+ * that want to start the full loop in the middle of a long run.                              */
+void e1o_carrier_phases(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs,
+                        double *carr_phase, double *phases, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

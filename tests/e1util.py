@@ -72,6 +72,7 @@ def oracle():
         lib.e1o_restate.argtypes = [C.c_double] * 4 + [dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.e1o_synth_epochs.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, dp, C.c_void_p]
         lib.e1o_synth_epochs_mt.argtypes = lib.e1o_synth_epochs.argtypes + [C.c_int]
+        lib.e1o_carrier_phases.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, dp, dp, C.c_int]
         _oracle = lib
     return _oracle
 
@@ -88,6 +89,17 @@ def oracle_synth(fs_hz, n_samp, recs, carr_phase=None, threads=1):
         lib.e1o_synth_epochs_mt(*args, threads)
     else:
         lib.e1o_synth_epochs(*args)
+    return out, ph
+
+
+def oracle_carrier_phases(fs_hz, n_samp, recs, carr_phase=None, threads=1):
+    """The literal carrier recurrence alone: (phase at the top of every block [n_epochs, max_chan], final phases)."""
+    recs = np.ascontiguousarray(recs)
+    n_epochs, max_chan = recs.shape
+    ph = np.zeros(max_chan) if carr_phase is None else np.array(carr_phase, dtype=np.float64)
+    out = np.zeros((n_epochs, max_chan))
+    dp = C.POINTER(C.c_double)
+    oracle().e1o_carrier_phases(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data_as(dp), out.ctypes.data_as(dp), threads)
     return out, ph
 
 
