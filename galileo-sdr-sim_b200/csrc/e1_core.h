@@ -382,6 +382,17 @@ E1_HD uint32_t e1_sym_bits(const e1_epoch_rec *r, int ibit, int page_sel)
     return d | (s << 1);
 }
 
+/* Carrier fields of a record inside the contract (include/e1b200.h): the walkers and the closed form take
+ * ONE wrap per step (x1 - 1.0), which equals the reference's `phi -= (long)phi` (:532) only while the
+ * phase stays inside (-1, 1) and the step is below one cycle per sample; anything else (NaN included) is
+ * rejected like a bad code phase, instead of silently giving other samples than the reference would. */
+E1_HD int e1_rec_carrier_ok(const e1_epoch_rec *r, double delt)
+{
+    if ((r->flags & E1_REC_SET_PHASE) && !(e1_fabs(r->carr_phase_init) < 1.0))
+        return 0;
+    return e1_fabs(e1_mul(r->f_carr, delt)) < 1.0;
+}
+
 /* Code-phase plan of one (epoch, channel): the code phase restarts every epoch
  * (computeCodePhase, src/gal-sig.cpp:308-347), so epochs are independent.  Walks the
  * recurrence (:491-507, :528) exactly and leaves one checkpoint per tile in o[t*stride]. */
@@ -398,7 +409,7 @@ E1_HD void e1_plan_code_epoch(const e1_epoch_rec *r, e1_tile_ck *o, int stride, 
     double cp = r->code_phase0;
     int ibit = r->ibit0, page_sel = 0;
     uint32_t err = 0;
-    if (!(cp >= 0.0) || !(sc > 0.0) || !(sc < 2048.0) || ibit < 0 || ibit >= E1C_SYM_PER_PAGE) {
+    if (!(cp >= 0.0) || !(sc > 0.0) || !(sc < 2048.0) || ibit < 0 || ibit >= E1C_SYM_PER_PAGE || !e1_rec_carrier_ok(r, delt)) {
         err = E1_CK_ERROR;
         ibit = 0;
     }

@@ -111,6 +111,15 @@ __global__ void e1_plan_code_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, in
                        tiles_per_epoch, delt);
 }
 
+/* carrier-only passes (e1b200_plan_phases) do not run the code planner, which is where a record is
+   validated: the carrier fields alone, one thread per (epoch, channel) */
+__global__ void e1_validate_carrier_kernel(const e1_epoch_rec *recs, int n, double delt, unsigned long long *counters)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && e1_rec_active(&recs[i]) && !e1_rec_carrier_ok(&recs[i], delt))
+        atomicAdd(&counters[1], 1ull);
+}
+
 /* serial reference planner (E1B200_CFG_SERIAL_PLANNER): one thread per channel, one exact walk */
 __global__ void e1_plan_carr_kernel(const e1_epoch_rec *recs, e1_tile_ck *ck, double *phase, int n_epochs,
                                     int max_chan, int n_samp, int tile, int tiles_per_epoch, double delt)
@@ -587,7 +596,7 @@ __device__ __noinline__ void e1_fix_run(const e1_chan_par *p, const uint32_t *co
 }
 
 /* Persistent CTA, one per SM.  Shared memory: code words of all PRNs (103 200 B) and the replicated
- * carrier table (65 536 B), both loaded once by bulk copy; two parameter-block buffers, the next
+ * carrier table (82 176 B), both loaded once by bulk copy; two parameter-block buffers, the next
  * tile's block in flight (bulk copy + mbarrier) while the current tile is computed.  The first wave of
  * tiles is blockIdx.x; after that CTAs draw tile numbers from an atomic counter (one draw ahead, so
  * the atomic's latency hides behind a tile), which keeps the SMs level when some tiles are slow.

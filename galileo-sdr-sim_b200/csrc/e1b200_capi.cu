@@ -190,10 +190,10 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
         return fail(ctx, E1B200_ECUDA, "synthesis kernel does not fit on this device", cudaSuccess);
     ctx->ctas_per_sm = env_int("E1B200_CTAS_PER_SM", occ);
 
-    uint32_t *h_codes = (uint32_t *)malloc(E1_CODES_BYTES);
-    int32_t *h_lut = (int32_t *)malloc(E1_LUT_BYTES);
-    if (!h_codes || !h_lut)
-        return fail(ctx, E1B200_ENOMEM, "host alloc", cudaSuccess);
+    std::vector<uint32_t> codes_v(E1_CODES_BYTES / 4);
+    std::vector<int32_t> lut_v(E1_LUT_ENTRIES);
+    uint32_t *h_codes = codes_v.data();
+    int32_t *h_lut = lut_v.data();
     build_codes(h_codes);
     build_lut(h_lut);
     CK(cudaMalloc(&ctx->d_codes, E1_CODES_BYTES));
@@ -203,8 +203,6 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     CK(cudaMalloc(&ctx->d_next_tile, sizeof(unsigned int)));
     CK(cudaMemcpy(ctx->d_codes, h_codes, E1_CODES_BYTES, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_lut, h_lut, E1_LUT_BYTES, cudaMemcpyHostToDevice));
-    free(h_codes);
-    free(h_lut);
     CK(cudaMemset(ctx->d_phase, 0, sizeof(double) * E1B200_MAX_CHAN));
     CK(cudaMemset(ctx->d_counters, 0, sizeof ctx->counters));
     return E1B200_OK;
@@ -342,6 +340,10 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
        released when the span pass is done, so that it fills the SMs the carrier chain (one block per
        channel) leaves idle. */
     const bool code_beside_chain = !carrier_only && !ctx->serial_planner;
+    if (carrier_only) {
+        e1_validate_carrier_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, nthr, ctx->delt, ctx->d_counters);
+        ctx->timing.kernel_launches += 1;
+    }
     if (!carrier_only && !code_beside_chain)
         e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
                                                                          ctx->tile, ctx->tiles_per_epoch, ctx->delt);
@@ -349,7 +351,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         e1_plan_carr_kernel<<<(cfg->max_chan + 31) / 32, 32, 0, ctx->stream>>>(d_recs, ctx->d_ck, ctx->d_phase, n, cfg->max_chan,
                                                                              cfg->samples_per_epoch, ctx->tile,
                                                                              ctx->tiles_per_epoch, ctx->delt);
-        ctx->timing.kernel_launches += 2;
+        ctx->timing.kernel_launches += carrier_only ? 1 : 2;
         /* the serial planner writes final checkpoints: translations are zero */
         CK(cudaMemsetAsync(ctx->d_delta, 0, sizeof(e1_trans) * (size_t)nuthr, ctx->stream));
     } else {
@@ -482,7 +484,7 @@ static int finish_timing(e1b200_ctx *ctx)
     unsigned long long before = ctx->counters[1];
     CK(cudaMemcpy(ctx->counters, ctx->d_counters, sizeof ctx->counters, cudaMemcpyDeviceToHost));
     if (ctx->counters[1] != before)
-        return fail(ctx, E1B200_EINVAL, "planner rejected a record (code phase / f_code / ibit out of range, or fs too low for the tile)",
+        return fail(ctx, E1B200_EINVAL, "planner rejected a record (code phase / f_code / ibit out of range, |carr_phase_init| >= 1, |f_carr / fs| >= 1, or fs too low for the tile)",
                     cudaSuccess);
     return E1B200_OK;
 }

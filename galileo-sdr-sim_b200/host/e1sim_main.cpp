@@ -216,19 +216,37 @@ int main(int argc, char **argv)
     const int total = e1h_total_epochs(scn);
     const size_t block_i16 = (size_t)opt.samples_per_epoch * 2;
     int16_t *iq = nullptr;
-    if (e1b200_host_alloc((void **)&iq, (size_t)batch * block_i16 * sizeof(int16_t)) != E1B200_OK) {
-        fprintf(stderr, "ERROR: pinned allocation failed\n");
-        return 1;
-    }
-    /* -r: FIFO of two batches + the consumer ("TX") thread: radio-sized reads, paced to the sample rate */
     e1_fifo *fifo = nullptr;
     std::thread consumer;
+    /* every exit from here on goes through this: a joinable std::thread must be joined before it is destroyed
+       (the reference's own exit aborts on exactly that), and the pinned buffer, the context and
+       the scenario are released */
+    auto cleanup = [&](int rc) {
+        if (fifo)
+            e1_fifo_finish(fifo);
+        if (consumer.joinable())
+            consumer.join();
+        if (fifo)
+            e1_fifo_destroy(fifo);
+        if (fd >= 0)
+            close(fd);
+        if (iq)
+            e1b200_host_free(iq);
+        e1b200_destroy(gpu);
+        e1h_close(scn);
+        return rc;
+    };
+    if (e1b200_host_alloc((void **)&iq, (size_t)batch * block_i16 * sizeof(int16_t)) != E1B200_OK) {
+        fprintf(stderr, "ERROR: pinned allocation failed\n");
+        return cleanup(1);
+    }
+    /* -r: FIFO of two batches + the consumer ("TX") thread: radio-sized reads, paced to the sample rate */
     bool consumer_ok = true;
     if (realtime) {
         fifo = e1_fifo_create((size_t)2 * batch * opt.samples_per_epoch, nullptr);
         if (!fifo) {
             fprintf(stderr, "ERROR: FIFO allocation failed\n");
-            return 1;
+            return cleanup(1);
         }
         consumer = std::thread([&] {
             const size_t chunk = 32 * 1024; /* SAMPLES_PER_BUFFER, include/constants.h:78 */
@@ -273,7 +291,7 @@ int main(int argc, char **argv)
         clock_gettime(CLOCK_MONOTONIC, &b);
         if ((device_restate ? e1b200_synth_ranges(gpu, n, ranges.data(), iq) : e1b200_synth_epochs(gpu, n, recs.data(), iq)) != E1B200_OK) {
             fprintf(stderr, "ERROR: %s\n", e1b200_last_error(gpu));
-            return 1;
+            return cleanup(1);
         }
         clock_gettime(CLOCK_MONOTONIC, &d);
         const size_t bytes = (size_t)n * block_i16 * sizeof(int16_t);
@@ -286,7 +304,7 @@ int main(int argc, char **argv)
         }
         if (!wrote) {
             fprintf(stderr, "ERROR: short write\n");
-            return 1;
+            return cleanup(1);
         }
         file_off += (off_t)bytes;
         clock_gettime(CLOCK_MONOTONIC, &e);
@@ -299,20 +317,14 @@ int main(int argc, char **argv)
     if (fifo) {
         e1_fifo_finish(fifo);
         consumer.join();
-        e1_fifo_destroy(fifo);
         if (!consumer_ok) {
             fprintf(stderr, "ERROR: short write\n");
-            return 1;
+            return cleanup(1);
         }
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    if (fd >= 0)
-        close(fd);
     const double wall = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     fprintf(stderr, "\nDone!\nProcess time = %.3f [sec]  (records %.3f, synthesis incl. copies %.3f, file %.3f)  %.1f Msamples/s\n", wall, t_host,
             t_gpu, t_io, (double)done * opt.samples_per_epoch / wall / 1e6);
-    e1b200_host_free(iq);
-    e1b200_destroy(gpu);
-    e1h_close(scn);
-    return 0;
+    return cleanup(0);
 }

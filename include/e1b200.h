@@ -69,8 +69,9 @@ typedef struct e1_epoch_rec {
     uint32_t reserved;
     double   code_phase0;      /* chips, [0,4092)                            (channel_t.code_phase)*/
     double   f_code;           /* chips/s                                    (channel_t.f_code)   */
-    double   f_carr;           /* Hz                                         (channel_t.f_carr)   */
-    double   carr_phase_init;  /* cycles, used iff E1_REC_SET_PHASE                               */
+    double   f_carr;           /* Hz, |f_carr| < fs_hz                       (channel_t.f_carr)   */
+    double   carr_phase_init;  /* cycles in (-1, 1), used iff E1_REC_SET_PHASE (allocateChannel
+                                  stores a fraction in [0,1), src/channel.cpp:98-99)              */
     uint8_t  page_cur[E1_PAGE_BYTES];   /* symbols in force at sample 0      (channel_t.page)     */
     uint8_t  page_next[E1_PAGE_BYTES];  /* symbols after ibit passes 499 inside this epoch        */
 } e1_epoch_rec;                /* 176 bytes */
@@ -123,7 +124,10 @@ int  e1b200_set_carrier_phase(e1b200_ctx *ctx, int slot, double phase);
 int  e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, int16_t *out);
 
 /* Device-resident variant: d_recs and d_out are device pointers on cfg.device.  Runs on the
- * context's stream; returns after the work is enqueued and e1b200_sync() waits for it.     */
+ * context's stream; returns after the work is enqueued and e1b200_sync() waits for it.
+ * A record outside its documented range (code phase, f_code, ibit0, carrier phase / step) makes
+ * e1b200_sync() -- for the host entry points the call itself -- return E1B200_EINVAL; with the device
+ * entry points the samples of that call have been written by then and must be discarded.     */
 int  e1b200_synth_epochs_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *d_recs, int16_t *d_out);
 int  e1b200_sync(e1b200_ctx *ctx);
 

@@ -446,3 +446,23 @@ def test_tiles_marked_clean_never_hold_a_flagged_run():
     assert 0.0 < hs.hs_max_code_ab_units() <= 8192 / 512.0 * 1.001 + 3.0
     assert clean > 0 and checked > 0 and slow > 0
     assert 0.9 < clean / (clean + checked) < 0.995, (clean, checked)
+
+
+def test_records_with_carrier_fields_outside_the_contract_are_rejected():
+    """A carr_phase_init outside (-1, 1) or a carrier step of a cycle or more per sample (or NaN) would be
+    walked with ONE wrap per step where the reference does `phi -= (long)phi`: the planner rejects the record
+    (E1_CK_ERROR -> E1B200_EINVAL) instead of producing other samples than the reference."""
+    fs, n = U.fs_as_reference(2.6e6), 26000
+    good = U.synthetic_recs(2, 3, fs, seed=4)
+    U.hostsim_synth(fs, n, good)                                   # in contract: fine
+    for field, val, e in (("carr_phase_init", 1.5, 0), ("carr_phase_init", -1.0, 0), ("carr_phase_init", float("nan"), 0),
+                          ("f_carr", 1.5 * fs, 1), ("f_carr", -fs, 1), ("f_carr", float("nan"), 0)):
+        bad = good.copy()
+        bad[e, 1][field] = val
+        if field == "carr_phase_init":
+            bad[e, 1]["flags"] = U.E1_REC_SET_PHASE
+        with pytest.raises(AssertionError, match="planner errors"):
+            U.hostsim_synth(fs, n, bad)
+    ok = good.copy()                                               # an out-of-range init without the flag is never read
+    ok[1, 1]["carr_phase_init"] = 7.0
+    U.hostsim_synth(fs, n, ok)

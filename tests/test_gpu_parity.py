@@ -314,6 +314,16 @@ def test_bad_records_are_rejected():
     with pytest.raises(E.E1B200Error):
         s.synth_epochs(recs)
     s.close()
+    # carrier fields outside the contract (one wrap per step is only the reference's `phi -= (long)phi` inside it)
+    for field, val in (("carr_phase_init", 1.5), ("f_carr", 1.5 * FS26), ("f_carr", float("nan"))):
+        s = E.Synth(FS26, 26000, 2)
+        recs = U.synthetic_recs(2, 2, FS26, seed=1)
+        recs[0, 1][field] = val
+        with pytest.raises(E.E1B200Error):
+            s.synth_epochs(recs)
+        with pytest.raises(E.E1B200Error):
+            s.plan_phases(recs)                     # the carrier-only pass validates too
+        s.close()
 
 
 def test_device_side_restate_matches_oracle():
