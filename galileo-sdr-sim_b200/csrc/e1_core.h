@@ -338,7 +338,9 @@ typedef struct e1_chan_par { /* 96 bytes, one per active channel of a tile (HBM 
     uint64_t dH;            /* code phase step per sample, 2^-51 half-chip                            */
     uint32_t dF;            /* dH >> 19: step of the fast path's 32-bit half-chip fraction            */
     int32_t j_w;
-    uint32_t pat_a, pat_b;  /* symbol XOR pattern for the code words before / after the code wrap     */
+    uint32_t pat_a, pat_b;  /* symbol XOR pattern for the code words before / after the code wrap;
+                               FLOAT path (E1B200_CFG_CBOC / _GAIN): pat_a = the channel's linear gain as
+                               IEEE float bits, pat_b unused (the symbols are in misc)                */
     uint32_t code_off;      /* word offset of this PRN's code words                                   */
     uint32_t misc;          /* bits 0-1 symbol field (D<<1 | D^S) before the wrap, bits 2-3 after it,
                                bit 4 negative-phase regime, bit 5 force the generic path, bit 6: the
@@ -1027,8 +1029,29 @@ E1_HD uint32_t e1_lim_code(uint32_t tc_code, uint32_t thr_code) { return tc_code
 E1_HD double e1_trans_at(const e1_trans *t, int k0) { return k0 >= t->k_split ? t->b : t->a; }
 
 /* Tile checkpoint + epoch record -> the per-channel parameters the sample loop reads. */
+E1_HD uint32_t e1_float_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+E1_HD float e1_bits_float(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
 E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, int tile, double delta, uint32_t tc_code,
-                       e1_chan_par *p)
+                       e1_chan_par *p, uint32_t cfg_flags = 0u)
 {
     p->phi = e1_add(c->phi, delta); /* planner translation of this epoch (exact, see e1_v2_chain) */
     p->cp = c->cp;
@@ -1069,6 +1092,11 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     p->pat_b = ((db & 2u) ? 0xAAAAAAAAu : 0u) | ((db & 1u) ? 0x55555555u : 0u);
     p->code_off = (uint32_t)(r->prn - 1) * E1C_CODE_WORDS_PER_PRN;
     p->misc = misc;
+    if (cfg_flags & (E1B200_CFG_CBOC | E1B200_CFG_GAIN)) { /* float path: gain[i] / 2^7 (src/galileo-sdr.cpp:477), exact in float below 2^24 */
+        const int32_t g = ((cfg_flags & E1B200_CFG_GAIN) && r->gain_q7 != 0) ? r->gain_q7 : 128;
+        p->pat_a = e1_float_bits((float)g * 0.0078125f);
+        p->pat_b = 0u;
+    }
 }
 
 /* ------------------------------------------------------------------ tile-level ambiguity test
@@ -1214,7 +1242,7 @@ E1_HD int e1_par_clean(const e1_chan_par *p, int T, uint32_t tc_carr, uint32_t l
 
 /* Exact table indices of sample j of the tile by walking the reference recurrences exactly
  * from the tile checkpoint (only for samples the closed form flags as ambiguous). */
-E1_HD void e1_exact_indices_impl(const e1_chan_par *p, int j, uint32_t *h_out, uint32_t *it_out)
+E1_HD void e1_exact_indices_impl(const e1_chan_par *p, int j, uint32_t *h_out, uint32_t *it_out, double per_chip = 2.0)
 {
     /* same values as j literal e1_carr_step / e1_code_step calls, in O(binades) steps */
     const double phi = e1_carr_advance(p->phi, p->sp, 0, j);
@@ -1225,15 +1253,20 @@ E1_HD void e1_exact_indices_impl(const e1_chan_par *p, int j, uint32_t *h_out, u
         cp = e1_walk_up(cp, p->sc, (double)E1C_CODE_LEN, &k, j, &w);
     }
     *it_out = (uint32_t)(e1_d2i_rz(e1_mul(511.0, phi)) & 511); /* src/galileo-sdr.cpp:509-510 */
-    *h_out = (uint32_t)e1_d2i_rz(e1_mul(cp, 2.0));             /* :512 */
+    *h_out = (uint32_t)e1_d2i_rz(e1_mul(cp, per_chip));        /* :512 (per_chip = 2; 12 = CBOC sub-chips) */
 }
 #if defined(__CUDA_ARCH__)
 static __device__ __noinline__ void e1_exact_indices(const e1_chan_par *p, int j, uint32_t *h_out, uint32_t *it_out)
 {
     e1_exact_indices_impl(p, j, h_out, it_out);
 }
+static __device__ __noinline__ void e1_exact_indices12(const e1_chan_par *p, int j, uint32_t *s_out, uint32_t *it_out)
+{
+    e1_exact_indices_impl(p, j, s_out, it_out, 12.0);
+}
 #else
 #define e1_exact_indices e1_exact_indices_impl
+E1_HD void e1_exact_indices12(const e1_chan_par *p, int j, uint32_t *s_out, uint32_t *it_out) { e1_exact_indices_impl(p, j, s_out, it_out, 12.0); }
 #endif
 
 E1_HD uint32_t e1_funnel_l(uint32_t lo, uint32_t hi, uint32_t n) /* high word of (hi:lo) << (n & 31) */
@@ -1303,6 +1336,79 @@ E1_HD void e1_channel_run(const e1_chan_par *p, const uint32_t *codes, const uns
         Ua += dU;
     }
 }
+
+/* FLOAT path (E1B200_CFG_CBOC / E1B200_CFG_GAIN, see include/e1b200.h): one channel's contribution to the R
+ * consecutive samples from tile-relative j0, added to the FP32 sums fi / fq.  Same exact phases as e1_channel_run
+ * (full-precision closed form, ambiguity test, exact fallback), with the code phase resolved to the SUB-CHIP
+ * s = trunc(12 code_phase) (the reference's `(int)(code_phase * 2)`, :512, at CBOC's resolution):
+ *     chip = s / 12, k = s % 12, a = (k < 6 ? -1 : +1), b = (k odd ? +1 : -1)          (sboc's sign convention)
+ *     Bd = B d, Cs = C s in {-1,+1};  m = eB - eC = alpha a (Bd - Cs) + beta b (Bd + Cs)
+ *       = 2 alpha a Bd  when Bd != Cs,   2 beta b Bd  when Bd == Cs                      (one of the two vanishes)
+ * so a sample adds  +-(g alpha) or +-(g beta)  times the table's 2 cos / 2 sin.  wa = g alpha, wb = g beta.
+ * Closed form vs serial recurrence in sub-chip units: six times the half-chip bound, plus the 2^-44 truncation
+ * below and the rounding of fl(12 code_phase) (< 1 unit of 2^-32 together). */
+E1_HD void e1_channel_run_float(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int R, float *fi,
+                                float *fq, float wa, float wb, uint32_t thr_carr, uint32_t thr_code, uint64_t bias_h,
+                                unsigned long long *n_exact)
+{
+    const uint64_t U0 = p->U0, dU = p->dU, HA = p->HA, dH = p->dH, HB = p->HB;
+    const int jw = p->j_w;
+    const uint32_t misc = p->misc;
+    const int jz = (misc & E1_PAR_HASZ) ? (int)(misc >> 16) : E1C_NO_WRAP;
+    const uint32_t *code = codes + p->code_off;
+    const uint32_t force = (misc >> 5) & 1u;
+    const uint32_t thr12 = 6u * thr_code + 2u;
+    uint64_t Ua = U0 + (uint64_t)(uint32_t)j0 * dU;
+    for (int i = 0; i < R; i++) {
+        const int j = j0 + i;
+        const int after = j >= jw;
+        const uint64_t H = (after ? HB : HA) + (uint64_t)(uint32_t)j * dH - bias_h; /* code phase, 2^-52 chip */
+        const uint32_t ds = after ? (misc >> 2) & 3u : misc & 3u;                     /* (D << 1) | (D ^ S) */
+        const uint64_t U = j >= jz ? 0ull - Ua : Ua;
+        const uint32_t neg = ((misc & E1_PAR_NEG) ? 1u : 0u) ^ (j >= jz ? 1u : 0u);
+        const uint32_t lo511 = e1_umulhi((uint32_t)U, 511u);
+        const uint64_t y = (uint64_t)(uint32_t)(U >> 32) * 511u + lo511;
+        uint32_t it = (uint32_t)(y >> 32);
+        const uint32_t yf = (uint32_t)y;
+        const uint64_t P = (H >> 8) * 12ull; /* 12 code_phase, 2^-44 sub-chip; < 49104 * 2^44 */
+        uint32_t s = (uint32_t)(P >> 44);
+        const uint32_t sf = (uint32_t)(P >> 12);
+        const uint32_t amb = (uint32_t)((yf + thr_carr) < 2u * thr_carr + 1u) | (uint32_t)((sf + thr12) < 2u * thr12 + 1u) | force;
+        if (neg)
+            it = (0u - it) & 511u;
+        if (amb) {
+            e1_exact_indices12(p, j, &s, &it);
+            (*n_exact)++;
+        }
+        const uint32_t chip = (s * 43691u) >> 19; /* s / 12 for s < 98304 */
+        const uint32_t k = s - 12u * chip;
+        const uint32_t hh = 2u * chip + 1u;                                        /* the odd half-chip carries +chip */
+        const uint32_t f = (code[hh >> 4] >> (30u - 2u * (hh & 15u))) & 3u;        /* (bneg, bneg ^ cneg) */
+        const uint32_t bd = (f >> 1) ^ (ds >> 1);                                  /* 1: B d = -1 */
+        const uint32_t differ = (f ^ ds) & 1u;                                     /* (bneg ^ cneg) ^ (D ^ S): B d != C s */
+        const uint32_t aneg = k < 6u ? 1u : 0u, bneg = (k & 1u) ^ 1u;
+        const uint32_t sneg = bd ^ (differ ? aneg : bneg);
+        const float w = differ ? wa : wb;
+        const int32_t t = *(const int32_t *)(lut_lane + (it + E1C_LUT_EXT) * (4u * E1C_LUT_REP)); /* 2 (cos + 65536 sin) */
+        const int32_t c2 = (int32_t)(int16_t)(uint16_t)t, s2 = (t - c2) >> 16;
+        const float ws = sneg ? -w : w;
+        fi[i] += ws * (float)c2;
+        fq[i] += ws * (float)s2;
+        Ua += dU;
+    }
+}
+/* FP32 sum -> the sink's int16: round to nearest even, saturate (the float->int16 store of the north star) */
+E1_HD int32_t e1_f2i16(float v)
+{
+#if defined(__CUDA_ARCH__)
+    int32_t r = __float2int_rn(v);
+#else
+    int32_t r = (int32_t)__builtin_rintf(v);
+#endif
+    return r > 32767 ? 32767 : (r < -32768 ? -32768 : r);
+}
+#define E1C_ALPHA_CBOC 0.95346258924559231545 /* sqrt(10/11) */
+#define E1C_BETA_CBOC 0.30151134457776362265  /* sqrt(1/11)  */
 
 /* Fast form for the common run: the channel is inside the closed form's domain.  Per sample it costs
  * one 32x32+64 multiply-add (carrier index and its fraction, straight from the run's start value),

@@ -62,6 +62,7 @@ struct e1_finalize_args {
     double delt;
     int n_epochs, max_chan, tile, tiles_per_epoch;
     uint32_t tc_code;
+    uint32_t cfg_flags; /* E1B200_CFG_CBOC / _GAIN: the parameter blocks carry the channel gain (float path) */
 };
 
 /* ------------------------------------------------------------------ restate (a8) */
@@ -73,8 +74,8 @@ __global__ void e1_restate_kernel(const e1_range_rec *rr, e1_epoch_rec *recs, in
     const e1_range_rec r = rr[i];
     e1_epoch_rec o;
     o.prn = r.prn;
-    o.flags = r.flags;
-    o.reserved = 0;
+    o.flags = r.flags & 0xffu;
+    o.gain_q7 = (int32_t)(r.flags >> 8); /* e1_range_rec carries gain[i] in the upper flag bits */
     o.carr_phase_init = r.carr_phase_init;
     const double lambda_e1 = 0.1902936727983649;       /* constants.h:119 */
     const double carr_to_code = 0.0006493506493506494; /* constants.h:125 */
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(128) e1_finalize_kernel(const e1_finalize_args
             e1_make_par(&c, &A.recs[(size_t)e * A.max_chan + ch], A.delt, A.tile,
                         e1_trans_at(&A.delta[(size_t)ch * A.delta_stride + (size_t)e * A.geo.spans_per_epoch + sp],
                                     (t - sp * A.geo.span_tiles) * A.tile),
-                        A.tc_code, &p);
+                        A.tc_code, &p, A.cfg_flags);
             if (c.sym & E1_CK_ERROR)
                 errs++;
             par[base + __popc(m & ((1u << lane) - 1u))] = p;
@@ -701,6 +702,102 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_kernel(const e1_
             }
         }
         __syncthreads(); /* all reads of this tile's block (and of s_tile[b]) are done */
+    }
+    if (n_exact)
+        atomicAdd(&s_cnt, n_exact);
+    __syncthreads();
+    if (tid == 0 && A.counters && s_cnt)
+        atomicAdd(&A.counters[0], s_cnt);
+}
+
+/* ------------------------------------------------------------------ synthesis, FLOAT path
+ * E1B200_CFG_CBOC / E1B200_CFG_GAIN (include/e1b200.h): CBOC(6,1,1/11) sub-carrier and the
+ * reference's computed-but-unused per-satellite gain.  Same persistent-CTA frame, same parameter blocks and
+ * tables as e1_synth_kernel<16>; per (thread, channel) e1_channel_run_float evaluates the exact closed form per
+ * sample at sub-chip resolution and adds +-(g alpha | g beta) x (2 cos, 2 sin) into 2 x 16 FP32 sums; the store is
+ * the fused float -> int16 (round to nearest even, saturating) interleaved I/Q, 128 bits at a time. */
+#define E1_FLOAT_RUN 16
+__global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_float_kernel(const e1_synth_args A, const float alpha, const float beta)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *s_lut = smem_raw + E1_CODES_BYTES;
+    const uint32_t blk_bytes = (uint32_t)e1_blk_bytes(A.max_chan);
+    unsigned char *s_blk0 = smem_raw + E1_CODES_BYTES + E1_LUT_BYTES;
+    __shared__ __align__(8) uint64_t s_bar[3];
+    __shared__ unsigned long long s_cnt;
+    __shared__ long s_tile[2];
+    const int R = E1_FLOAT_RUN;
+    const int tid = threadIdx.x;
+    const long total_tiles = (long)A.n_epochs * A.tiles_per_epoch;
+    long next_id = 0;
+    if (tid == 0) {
+        s_cnt = 0;
+        e1_mbar_init(&s_bar[0], 1);
+        e1_mbar_init(&s_bar[1], 1);
+        e1_mbar_init(&s_bar[2], 1);
+        e1_mbar_init_fence();
+        e1_mbar_expect(&s_bar[0], E1_CODES_BYTES + E1_LUT_BYTES);
+        e1_bulk_g2s(s_codes, A.codes, E1_CODES_BYTES, &s_bar[0]);
+        e1_bulk_g2s(s_lut, A.lut, E1_LUT_BYTES, &s_bar[0]);
+        s_tile[0] = blockIdx.x;
+        if ((long)blockIdx.x < total_tiles) {
+            e1_mbar_expect(&s_bar[1], blk_bytes);
+            e1_bulk_g2s(s_blk0, A.blk + (size_t)blockIdx.x * blk_bytes, blk_bytes, &s_bar[1]);
+        }
+        next_id = (long)gridDim.x + atomicAdd(A.next_tile, 1u);
+    }
+    __syncthreads();
+    e1_mbar_wait(&s_bar[0], 0);
+    const unsigned char *lut_lane = s_lut + 4 * (tid & (E1C_LUT_REP - 1));
+    const uint64_t bias_h = e1_bias_h(A.tc_code);
+    const int j0 = tid * R;
+    unsigned long long n_exact = 0;
+    for (int it = 0;; it++) {
+        const int b = it & 1;
+        const long tile_id = s_tile[b];
+        if (tile_id >= total_tiles)
+            break;
+        if (tid == 0) {
+            s_tile[1 - b] = next_id;
+            if (next_id < total_tiles) {
+                e1_mbar_expect(&s_bar[2 - b], blk_bytes);
+                e1_bulk_g2s(s_blk0 + (size_t)(1 - b) * blk_bytes, A.blk + (size_t)next_id * blk_bytes, blk_bytes, &s_bar[2 - b]);
+                next_id = (long)gridDim.x + atomicAdd(A.next_tile, 1u);
+            }
+        }
+        e1_mbar_wait(&s_bar[1 + b], (uint32_t)(it >> 1) & 1u);
+        const unsigned char *blk = s_blk0 + (size_t)b * blk_bytes;
+        const int nact = *reinterpret_cast<const int *>(blk);
+        const e1_chan_par *par = reinterpret_cast<const e1_chan_par *>(blk + E1C_BLK_HEADER);
+        const int e = (int)(tile_id / A.tiles_per_epoch), t = (int)(tile_id - (long)e * A.tiles_per_epoch);
+        const int n_valid = min(A.tile, A.n_samp - t * A.tile);
+        if (j0 < n_valid) {
+            float fi[R], fq[R];
+#pragma unroll
+            for (int i = 0; i < R; i++)
+                fi[i] = fq[i] = 0.0f;
+            for (int a = 0; a < nact; a++) {
+                const float g = __uint_as_float(par[a].pat_a);
+                e1_channel_run_float(&par[a], s_codes, lut_lane, j0, R, fi, fq, g * alpha, g * beta, A.thr_carr, A.thr_code, bias_h, &n_exact);
+            }
+            int16_t *dst = A.out + ((size_t)e * A.n_samp + (size_t)t * A.tile + j0) * 2;
+            uint32_t w[R];
+#pragma unroll
+            for (int i = 0; i < R; i++) /* the sink's little-endian (int16 I, int16 Q) pair (:536-537) */
+                w[i] = ((uint32_t)e1_f2i16(fi[i]) & 0xffffu) | ((uint32_t)e1_f2i16(fq[i]) << 16);
+            if (A.vec_ok && j0 + R <= n_valid) {
+#pragma unroll
+                for (int i = 0; i < R; i += 4)
+                    *reinterpret_cast<uint4 *>(dst + 2 * i) = make_uint4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; i++)
+                    if (j0 + i < n_valid)
+                        *reinterpret_cast<uint32_t *>(dst + 2 * i) = w[i];
+            }
+        }
+        __syncthreads();
     }
     if (n_exact)
         atomicAdd(&s_cnt, n_exact);

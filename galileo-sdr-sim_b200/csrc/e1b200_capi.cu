@@ -31,6 +31,8 @@ struct e1b200_ctx {
     int plan_epochs;    /* epochs per planner pass (bounds scratch)                     */
     int sm_count, ctas_per_sm, smem_bytes;
     int use_bulk, amb_scale, serial_planner;
+    int float_path;     /* E1B200_CFG_CBOC / _GAIN: e1_synth_float_kernel (FP32 accumulate, float -> int16 store) */
+    float alpha, beta;  /* sub-carrier weights of the float path: (1, 0) BOC(1,1), (sqrt(10/11), sqrt(1/11)) CBOC */
     cudaStream_t stream, copy_stream;
     cudaStream_t side_stream;            /* planner: the code-phase pass runs here, beside the carrier chain */
     cudaEvent_t ev_fork, ev_join;
@@ -158,7 +160,14 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
         ctx->cfg.dt_epoch = 0.10000002314200000; /* src/galileo-sdr.cpp:347 */
     ctx->delt = 1.0 / cfg->fs_hz;
     ctx->run = run;
-    ctx->pair = (run == E1C_MAX_RUN) && !env_int("E1B200_NO_PAIR", 0);
+    ctx->float_path = (cfg->flags & (E1B200_CFG_CBOC | E1B200_CFG_GAIN)) != 0;
+    ctx->alpha = (cfg->flags & E1B200_CFG_CBOC) ? (float)E1C_ALPHA_CBOC : 1.0f;
+    ctx->beta = (cfg->flags & E1B200_CFG_CBOC) ? (float)E1C_BETA_CBOC : 0.0f;
+    if (ctx->float_path && run != E1C_MAX_RUN) { /* the float kernel owns 16 samples per thread: 8192-sample tiles */
+        delete ctx;
+        return E1B200_EINVAL;
+    }
+    ctx->pair = (run == E1C_MAX_RUN) && !env_int("E1B200_NO_PAIR", 0) && !ctx->float_path;
     ctx->tile = run * E1_SYNTH_THREADS;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
     ctx->geo = e1_span_geometry(ctx->tiles_per_epoch);
@@ -183,9 +192,14 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     synth_fn fn = synth_for(run, ctx->pair);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, E1_SYNTH_THREADS, ctx->smem_bytes));
+    if (ctx->float_path) {
+        CK(cudaFuncSetAttribute(e1_synth_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e1_synth_float_kernel, E1_SYNTH_THREADS, ctx->smem_bytes));
+    } else {
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, E1_SYNTH_THREADS, ctx->smem_bytes));
+    }
     if (occ < 1)
         return fail(ctx, E1B200_ECUDA, "synthesis kernel does not fit on this device", cudaSuccess);
     ctx->ctas_per_sm = env_int("E1B200_CTAS_PER_SM", occ);
@@ -407,6 +421,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         F.tile = ctx->tile;
         F.tiles_per_epoch = ctx->tiles_per_epoch;
         F.tc_code = e1_tc_code(e1_thr_code(ctx->tile, ctx->amb_scale), ctx->run);
+        F.cfg_flags = ctx->cfg.flags;
         const long tiles = (long)n * ctx->tiles_per_epoch;
         e1_finalize_kernel<<<(unsigned)((tiles + 3) / 4), 128, 0, ctx->stream>>>(F);
         ctx->timing.kernel_launches += 1;
@@ -461,7 +476,10 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     int rc = mark(ctx, 1, 0);
     if (rc)
         return rc;
-    synth_for(ctx->run, ctx->pair)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
+    if (ctx->float_path)
+        e1_synth_float_kernel<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A, ctx->alpha, ctx->beta);
+    else
+        synth_for(ctx->run, ctx->pair)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     ctx->timing.synth_launches += 1;

@@ -18,7 +18,7 @@ PAGE_BYTES = 64
 REF_DT = 0.10000002314200000  # src/galileo-sdr.cpp:347
 
 REC_DTYPE = np.dtype([
-    ("prn", "<i4"), ("ibit0", "<i4"), ("flags", "<u4"), ("reserved", "<u4"),
+    ("prn", "<i4"), ("ibit0", "<i4"), ("flags", "<u4"), ("gain_q7", "<i4"),
     ("code_phase0", "<f8"), ("f_code", "<f8"), ("f_carr", "<f8"), ("carr_phase_init", "<f8"),
     ("page_cur", "u1", PAGE_BYTES), ("page_next", "u1", PAGE_BYTES),
 ])

@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "lib" / "libe1host.so"
 
 REC_DTYPE = np.dtype([
-    ("prn", "<i4"), ("ibit0", "<i4"), ("flags", "<u4"), ("reserved", "<u4"),
+    ("prn", "<i4"), ("ibit0", "<i4"), ("flags", "<u4"), ("gain_q7", "<i4"),
     ("code_phase0", "<f8"), ("f_code", "<f8"), ("f_carr", "<f8"), ("carr_phase_init", "<f8"),
     ("page_cur", "u1", 64), ("page_next", "u1", 64),
 ])
@@ -25,7 +25,7 @@ class Options(C.Structure):
     _fields_ = [("navfile", C.c_char * 512), ("llh", C.c_double * 3), ("have_start", C.c_int32),
                 ("y", C.c_int32), ("m", C.c_int32), ("d", C.c_int32), ("hh", C.c_int32), ("mm", C.c_int32),
                 ("sec", C.c_double), ("iduration", C.c_int32), ("iono_enable", C.c_int32), ("max_chan", C.c_int32),
-                ("fs_hz", C.c_double), ("samples_per_epoch", C.c_int32), ("verbose", C.c_int32)]
+                ("fs_hz", C.c_double), ("samples_per_epoch", C.c_int32), ("verbose", C.c_int32), ("elev_mask_deg", C.c_double)]
 
 
 _lib = None
@@ -58,7 +58,8 @@ class Scenario:
     """navfile + receiver position (+ start time) -> records, exactly as the reference's galileo_task()
     derives its channel state for every 0.1 s block."""
 
-    def __init__(self, navfile, llh=None, start=None, duration_s=300.0, iono=True, max_chan=16, verbose=False):
+    def __init__(self, navfile, llh=None, start=None, duration_s=300.0, iono=True, max_chan=16, verbose=False, fs_hz=None,
+                 elev_mask_deg=0.0):
         lib = load()
         o = Options()
         lib.e1h_default_options(C.byref(o))
@@ -73,6 +74,10 @@ class Scenario:
         o.iono_enable = 1 if iono else 0
         o.max_chan = max_chan
         o.verbose = 1 if verbose else 0
+        if fs_hz is not None:                  # a build of the reference with another SAMP_RATE (oracle/ref_patches/fs25.diff)
+            o.fs_hz = float(np.float32(fs_hz))
+            o.samples_per_epoch = int(np.float32(fs_hz) / 10)      # NUM_IQ_SAMPLES = TX_SAMPLERATE / 10
+        o.elev_mask_deg = float(elev_mask_deg)  # 0 = the reference's 10 degrees
         err = C.create_string_buffer(256)
         self._h = lib.e1h_open(C.byref(o), err, 256)
         if not self._h:

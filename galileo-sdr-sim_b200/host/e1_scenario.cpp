@@ -601,6 +601,8 @@ struct e1h_scenario {
     double delt;
     int numd = 0, iumd = 1;
     std::vector<double> motion; /* optional: lat, lon [deg], height [m] per block index (e1h_set_motion) */
+    double ant_pat[37];         /* receiver antenna pattern, linear, boresight angle 0:5:180 deg (src/galileo-sdr.cpp:50-54,365) */
+    double elev_mask_deg = 10.0; /* allocateChannel's mask: the reference hard-codes 10 (src/channel.cpp:60) */
 
     /* allocateChannel (src/channel.cpp:21-122): runs on a COPY of the current-ephemeris indices */
     void allocate(const GalTime &g, const double *pos)
@@ -613,7 +615,7 @@ struct e1h_scenario {
                 continue;
             const Ephemeris &e = eph[sv][idx];
             double azel[2];
-            if (visible(e, g, pos, 10.0, azel)) {
+            if (visible(e, g, pos, elev_mask_deg, azel)) {
                 if (slot_of_sv[sv] != -1)
                     continue;
                 int i;
@@ -667,6 +669,17 @@ e1h_scenario *e1h_open(const e1h_options *o, char *err, int err_len)
     if (!o || o->max_chan < 1 || o->max_chan > E1B200_MAX_CHAN || o->iduration < 1)
         return fail("bad options");
     e1h_scenario *s = new e1h_scenario();
+    {
+        /* attenuation in dB per 5 degrees off boresight: the pattern table gps-sdr-sim and this reference ship
+           (src/galileo-sdr.cpp:50-54), turned into amplitude factors as at :365 */
+        static const double ant_pat_db[37] = {0.00, 0.00, 0.22, 0.44, 0.67, 1.11, 1.56, 2.00, 2.44, 2.89, 3.56, 4.22, 4.89,
+                                              5.56, 6.22, 6.89, 7.56, 8.22, 8.89, 9.78, 10.67, 11.56, 12.44, 13.33, 14.44, 15.56,
+                                              16.67, 17.78, 18.89, 20.00, 21.33, 22.67, 24.00, 25.56, 27.33, 29.33, 31.56};
+        for (int i = 0; i < 37; i++)
+            s->ant_pat[i] = pow(10.0, -ant_pat_db[i] / 20.0);
+        if (o->elev_mask_deg != 0.0)
+            s->elev_mask_deg = o->elev_mask_deg;
+    }
     s->opt = *o;
     s->iono.enable = o->iono_enable;
     if (!read_rinex(o->navfile, s->eph, s->iono)) {
@@ -814,6 +827,14 @@ int e1h_next_ex(e1h_scenario *s, int n, e1_epoch_rec *recs, e1_range_rec *ranges
 
             e1_epoch_rec &r = out[i];
             r.prn = c.prn;
+            /* gain[i] (src/galileo-sdr.cpp:469-477): free-space loss relative to 20 200 km times the receiver
+               antenna pattern at the boresight angle, scaled by 2^7.  The reference computes it every block and
+               never applies it (:520-521); the record carries it for E1B200_CFG_GAIN. */
+            {
+                const double path_loss = 20200000.0 / rho.d;
+                const int ibs = (int)((90.0 - rho.azel[1] * kRadToDeg) / 5.0);
+                r.gain_q7 = (int)(path_loss * s->ant_pat[ibs < 0 ? 0 : (ibs > 36 ? 36 : ibs)] * 128.0);
+            }
             r.ibit0 = ibit;
             r.code_phase0 = code_phase;
             r.f_code = f_code;
@@ -824,7 +845,7 @@ int e1h_next_ex(e1h_scenario *s, int n, e1_epoch_rec *recs, e1_range_rec *ranges
                 c.fresh = false;
             }
             if (rout) {
-                rout[i].flags = r.flags;
+                rout[i].flags = r.flags | ((uint32_t)r.gain_q7 << 8); /* e1_range_rec: gain in the upper flag bits */
                 rout[i].carr_phase_init = r.carr_phase_init;
             }
             pack_symbols(c.page, r.page_cur);

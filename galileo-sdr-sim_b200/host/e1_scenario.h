@@ -33,6 +33,8 @@ typedef struct e1h_options {
     double fs_hz;         /* sample rate the records are for (reference: (float)2.6e6)            */
     int32_t samples_per_epoch;
     int32_t verbose;      /* print the reference's allocation lines to stderr                      */
+    double elev_mask_deg; /* 0 = the reference's hard-coded 10 degrees (src/channel.cpp:60); e.g. -90 =
+                             every satellite of the file (the patched `ch36` reference build)          */
 } e1h_options;
 
 typedef struct e1h_scenario e1h_scenario;

@@ -81,7 +81,12 @@ static void usage(const char *prog)
             "  -u <motion>      Receiver motion file, one line per 0.1 s: t,x,y,z (ECEF) or lat,lon,hgt\n"
             "  -R               Evaluate the per-block code-phase/Doppler restate on the GPU\n"
             "  -r               Pace the output to real time (FIFO / radio style consumer)\n"
-            "  -B <blocks>      0.1 s blocks per GPU call (default 512)\n",
+            "  -B <blocks>      0.1 s blocks per GPU call (default 512)\n"
+            "  -f <rate>        Sample rate [Hz] (default 2.6e6, the reference's SAMP_RATE)\n"
+            "  -c <channels>    Channel slots (default 16, the reference's MAX_CHAN; up to 64)\n"
+            "  -m <degrees>     Elevation mask (default 10, hard-coded in the reference)\n"
+            "  -C               CBOC(6,1,1/11) sub-carrier instead of the reference's BOC(1,1) (float path)\n"
+            "  -A               Apply the per-satellite gain the reference computes and leaves unused (float path)\n",
             prog);
 }
 
@@ -93,10 +98,29 @@ int main(int argc, char **argv)
     int batch = 512;
     bool device_restate = false, realtime = false, have_duration = false, have_batch = false;
     char motion_file[512] = "";
+    uint32_t cfg_flags = 0;
     opt.verbose = 1; /* the reference always prints its allocation lines */
     int c;
-    while ((c = getopt(argc, argv, "e:n:o:u:g:l:T:t:d:G:a:p:iI:U:b:vB:Rr")) != -1) {
+    while ((c = getopt(argc, argv, "e:n:o:u:g:l:T:t:d:G:a:p:iI:U:b:vB:Rrf:c:m:CA")) != -1) {
         switch (c) {
+        case 'f': { /* like the reference's `const float SAMP_RATE` (include/constants.h:96): rounded to float */
+            const float fs = (float)atof(optarg);
+            opt.fs_hz = (double)fs;
+            opt.samples_per_epoch = (int)(fs / 10);
+            break;
+        }
+        case 'c':
+            opt.max_chan = atoi(optarg);
+            break;
+        case 'm':
+            opt.elev_mask_deg = atof(optarg);
+            break;
+        case 'C':
+            cfg_flags |= E1B200_CFG_CBOC;
+            break;
+        case 'A':
+            cfg_flags |= E1B200_CFG_GAIN;
+            break;
         case 'u':
             snprintf(motion_file, sizeof motion_file, "%s", optarg);
             break;
@@ -194,6 +218,7 @@ int main(int argc, char **argv)
     cfg.fs_hz = opt.fs_hz;
     cfg.samples_per_epoch = opt.samples_per_epoch;
     cfg.max_chan = opt.max_chan;
+    cfg.flags = cfg_flags;
     e1b200_ctx *gpu = nullptr;
     if (e1b200_create(&cfg, &gpu) != E1B200_OK) {
         fprintf(stderr, "ERROR: no usable CUDA device (%s)\n", e1b200_last_error(gpu));

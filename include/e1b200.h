@@ -66,7 +66,10 @@ typedef struct e1_epoch_rec {
     int32_t  prn;              /* 1..50, 0 = slot idle this epoch            (channel_t.prn)      */
     int32_t  ibit0;            /* nav symbol index at sample 0, 0..499       (channel_t.ibit)     */
     uint32_t flags;            /* E1_REC_*                                                        */
-    uint32_t reserved;
+    int32_t  gain_q7;          /* the reference's gain[i] (path loss x antenna pattern, scaled by 2^7,
+                                  src/galileo-sdr.cpp:469-477): applied only with E1B200_CFG_GAIN
+                                  (the reference computes it and leaves it unused, :520-521);
+                                  0 = unit gain (128)                                             */
     double   code_phase0;      /* chips, [0,4092)                            (channel_t.code_phase)*/
     double   f_code;           /* chips/s                                    (channel_t.f_code)   */
     double   f_carr;           /* Hz, |f_carr| < fs_hz                       (channel_t.f_carr)   */
@@ -80,7 +83,7 @@ typedef struct e1_epoch_rec {
  * evaluates computeCodePhase (src/gal-sig.cpp:308-347) itself.                              */
 typedef struct e1_range_rec {
     int32_t  prn;
-    uint32_t flags;
+    uint32_t flags;            /* bits 0-7 E1_REC_*, bits 8-31 gain_q7 (see e1_epoch_rec)          */
     double   rho_prev;         /* chan->rho0.range  [m]                                           */
     double   rho_cur;          /* rho1.range        [m]                                           */
     double   grx_sec;          /* receiver time of this epoch [s of week]                         */
@@ -99,6 +102,17 @@ typedef struct e1b200_config {
 } e1b200_config;
 
 #define E1B200_CFG_SERIAL_PLANNER 1u  /* carrier planner: single chain per channel (debug/compare) */
+/* Signal options beyond what the reference transmits.  The reference modulates BOC(1,1) at unit
+ * gain into exact integers (sboc(.., 1, 1), src/gal-sig.cpp:224,232; gain[i] unused, :520-521) -- that stays
+ * the default and stays bit-exact.  Either flag below selects the FLOAT path: per sample
+ *     I = sum_c g_c * m_c * cos_c,   m_c = eB_c - eC_c,
+ *     eB = B d (alpha a + beta b),   eC = C s (alpha a - beta b)            (Galileo OS SIS ICD 2.1.2, eq. 7-9)
+ * with a / b the BOC(1,1) / BOC(6,1) sub-carrier signs at sub-chip trunc(12 code_phase) (first half of the
+ * chip / every even sub-chip negative, the convention of the reference's sboc), accumulated in FP32 and
+ * stored as int16 by round-to-nearest-even with saturation.  Phases and table indices are the same exact
+ * ones as in the integer path; the accumulate is float, so the criterion against the oracle is +-1 LSB.   */
+#define E1B200_CFG_CBOC 2u  /* alpha = sqrt(10/11), beta = sqrt(1/11) instead of BOC(1,1)'s (1, 0)          */
+#define E1B200_CFG_GAIN 4u  /* g_c = gain_q7 / 128 of the record instead of 1                               */
 
 typedef struct e1b200_ctx e1b200_ctx;
 

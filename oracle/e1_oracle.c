@@ -287,3 +287,99 @@ void e1o_carrier_phases(double fs_hz, int n_samp, int max_chan, int n_epochs, co
         pthread_join(th[t], NULL);
     free(jobs); free(th);
 }
+
+/* ---- CBOC(6,1,1/11) sub-carrier and per-satellite gain --------------------------------
+ * PARITY UNPINNED for alpha/beta != (1, 0) and for gains: the reference transmits BOC(1,1) at unit gain
+ * (sboc(.., 1, 1), src/gal-sig.cpp:224,232; `* gain[i]` commented out, src/galileo-sdr.cpp:520-521), so there
+ * are no reference bytes to hold this mode to.  Written from the Galileo OS SIS ICD (2.1.2, E1 CBOC):
+ *     e_B(t) = c_B d (alpha sc_a + beta sc_b),   e_C(t) = c_C s (alpha sc_a - beta sc_b),   s = e_B - e_C
+ * with the reference's own loop around it (code wrap / symbol advance :491-507, table index :509-510, phase
+ * advance :528-532) and its sign convention for a sub-carrier (sboc negates the FIRST half period): sc_a < 0 on
+ * the first half of a chip, sc_b < 0 on every even twelfth.  The sub-chip is (int)(code_phase * 12), the
+ * resolution-12 analogue of :512.  Accumulated in double, stored as the nearest int16 (ties to even,
+ * saturating).  With (alpha, beta) = (1, 0) and unit gains it writes the reference's bytes (tested).
+ * Deterministic whatever the thread count: threads take whole blocks, each block sums its channels in slot
+ * order from the phase the literal carrier recurrence (e1o_carrier_phases) reaches at its top. */
+typedef struct {
+    double delt, alpha, beta;
+    int n_samp, max_chan, n_epochs, use_gain, tid, n_threads;
+    const e1_epoch_rec *recs;
+    const double *phases;
+    int16_t *out;
+} fl_job;
+
+static void *fl_worker(void *arg)
+{
+    fl_job *j = (fl_job *)arg;
+    double *acc = (double *)malloc(sizeof(double) * 2 * (size_t)j->n_samp);
+    for (int e = j->tid; e < j->n_epochs; e += j->n_threads) {
+        memset(acc, 0, sizeof(double) * 2 * (size_t)j->n_samp);
+        for (int ch = 0; ch < j->max_chan; ch++) {
+            const e1_epoch_rec *r = &j->recs[(size_t)e * j->max_chan + ch];
+            if (r->prn <= 0)
+                continue;
+            const code_pair *cp = codes_for(r->prn);
+            const double g = (j->use_gain && r->gain_q7 != 0) ? (double)r->gain_q7 / 128.0 : 1.0; /* gain[i] is scaled by 2^7 (:477) */
+            double code_phase = r->code_phase0, phi = j->phases[(size_t)e * j->max_chan + ch];
+            int ibit = r->ibit0;
+            const uint8_t *page = r->page_cur;
+            for (int k = 0; k < j->n_samp; k++) {
+                if (code_phase >= E1_CODE_LEN) {
+                    code_phase -= E1_CODE_LEN;
+                    if (++ibit >= E1_SYM_PER_PAGE) {
+                        ibit = 0;
+                        page = r->page_next;
+                    }
+                }
+                int it = ((int)(511 * phi)) & 511;
+                int sub = (int)(code_phase * 12);
+                int chip = sub / 12, tw = sub % 12;
+                double sc_a = tw < 6 ? -1.0 : 1.0, sc_b = (tw & 1) ? 1.0 : -1.0;
+                double c_b = cp->b[2 * chip + 1], c_c = cp->c[2 * chip + 1]; /* +chip sits on the odd half-chip */
+                double d = page_bit(page, ibit) ? -1.0 : 1.0, sec = SEC25[ibit % E1_SEC_CODE_LEN] ? -1.0 : 1.0;
+                double e_b = c_b * d * (j->alpha * sc_a + j->beta * sc_b);
+                double e_c = c_c * sec * (j->alpha * sc_a - j->beta * sc_b);
+                double m = g * (e_b - e_c);
+                acc[2 * k] += m * g_cos[it];
+                acc[2 * k + 1] += m * g_sin[it];
+                code_phase += r->f_code * j->delt;
+                phi += r->f_carr * j->delt;
+                phi -= (long)phi;
+            }
+        }
+        int16_t *o = j->out + (size_t)e * j->n_samp * 2;
+        for (int k = 0; k < 2 * j->n_samp; k++) {
+            double v = nearbyint(acc[k]); /* default rounding mode: to nearest, ties to even */
+            o[k] = (int16_t)(v > 32767.0 ? 32767.0 : (v < -32768.0 ? -32768.0 : v));
+        }
+    }
+    free(acc);
+    return NULL;
+}
+
+void e1o_synth_epochs_float(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs,
+                            double *carr_phase, int16_t *out, double alpha, double beta, int use_gain, int n_threads)
+{
+    if (max_chan < 1 || n_samp < 1 || n_epochs < 1)
+        return;
+    if (n_threads < 1) n_threads = 1;
+    for (int c = 0; c < max_chan; c++)
+        for (int e = 0; e < n_epochs; e++)
+            if (recs[(size_t)e * max_chan + c].prn > 0)
+                codes_for(recs[(size_t)e * max_chan + c].prn);
+    double *phases = (double *)malloc(sizeof(double) * (size_t)n_epochs * max_chan);
+    e1o_carrier_phases(fs_hz, n_samp, max_chan, n_epochs, recs, carr_phase, phases, n_threads);
+    if (n_threads > n_epochs) n_threads = n_epochs;
+    fl_job *jobs = (fl_job *)calloc((size_t)n_threads, sizeof *jobs);
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof *th);
+    for (int t = 0; t < n_threads; t++) {
+        fl_job *j = &jobs[t];
+        j->delt = 1.0 / fs_hz; j->alpha = alpha; j->beta = beta; j->n_samp = n_samp; j->max_chan = max_chan;
+        j->n_epochs = n_epochs; j->use_gain = use_gain; j->tid = t; j->n_threads = n_threads;
+        j->recs = recs; j->phases = phases; j->out = out;
+        pthread_create(&th[t], NULL, fl_worker, j);
+    }
+    for (int t = 0; t < n_threads; t++)
+        pthread_join(th[t], NULL);
+    free(phases); free(jobs); free(th);
+}

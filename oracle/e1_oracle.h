@@ -43,6 +43,13 @@ void e1o_synth_epochs_mt(double fs_hz, int n_samp, int max_chan, int n_epochs,
 void e1o_carrier_phases(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs,
                         double *carr_phase, double *phases, int n_threads);
 
+/* SURVEY 8 f4, PARITY UNPINNED (the reference has no such mode): the same loop with the E1 CBOC(6,1,1/11)
+ * sub-carrier of the Galileo OS SIS ICD (alpha = sqrt(10/11), beta = sqrt(1/11); (1, 0) is the reference's
+ * BOC(1,1)) at sub-chip (int)(code_phase * 12) and, with use_gain, the record's gain_q7 / 128; double
+ * accumulate, nearest-int16 store.  carr_phase is read and updated.                              */
+void e1o_synth_epochs_float(double fs_hz, int n_samp, int max_chan, int n_epochs, const e1_epoch_rec *recs,
+                            double *carr_phase, int16_t *out, double alpha, double beta, int use_gain, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

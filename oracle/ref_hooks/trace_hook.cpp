@@ -11,7 +11,7 @@
 
 #pragma pack(push, 1)
 struct e1_trace_rec {
-    int32_t iumd, slot, prn, ibit, ipage, _pad;
+    int32_t iumd, slot, prn, ibit, ipage, gain;
     double code_phase, f_code, f_carr, carr_phase, grx_sec, rho_range;
     uint8_t page[504];
 };
@@ -19,7 +19,7 @@ struct e1_trace_rec {
 
 static FILE *g_fp = NULL;
 
-void e1_oracle_trace_hook(int line, int isamp, int iumd, const channel_t *chan, const galtime_t *grx)
+void e1_oracle_trace_hook(int line, int isamp, int iumd, const channel_t *chan, const galtime_t *grx, const int *gain)
 {
     if (line != 485 || isamp != 0)
         return;
@@ -34,7 +34,7 @@ void e1_oracle_trace_hook(int line, int isamp, int iumd, const channel_t *chan, 
         e1_trace_rec r;
         memset(&r, 0, sizeof r);
         r.iumd = iumd; r.slot = i; r.prn = chan[i].prn;
-        r.ibit = chan[i].ibit; r.ipage = chan[i].ipage;
+        r.ibit = chan[i].ibit; r.ipage = chan[i].ipage; r.gain = gain[i];
         r.code_phase = chan[i].code_phase; r.f_code = chan[i].f_code; r.f_carr = chan[i].f_carr;
         r.carr_phase = chan[i].carr_phase; r.grx_sec = grx->sec; r.rho_range = chan[i].rho0.range;
         for (int k = 0; k < PAGE_SIZE; k++)

@@ -15,8 +15,9 @@
 #endif
 #include E1_REF_HEADER
 
-void e1_oracle_trace_hook(int line, int isamp, int iumd, const channel_t *chan, const galtime_t *grx);
+void e1_oracle_trace_hook(int line, int isamp, int iumd, const channel_t *chan, const galtime_t *grx, const int *gain);
 int e1_oracle_pinned_rinex(std::vector<ephem_t> eph_vector[MAX_SAT], ionoutc_t *ionoutc, char *fname);
 
-#define get_nanos() (e1_oracle_trace_hook(__LINE__, isamp, iumd, chan, &grx), 0L)
+// `gain` is galileo_task()'s local gain[MAX_CHAN] (src/galileo-sdr.cpp:119,477): computed per block, never used (:520-521)
+#define get_nanos() (e1_oracle_trace_hook(__LINE__, isamp, iumd, chan, &grx, gain), 0L)
 #define readRinexV3(a, b, c) e1_oracle_pinned_rinex(a, b, c)

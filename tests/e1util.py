@@ -16,7 +16,7 @@ E1_REC_SET_PHASE = 1
 PAGE_BYTES = 64
 
 REC_DTYPE = np.dtype([
-    ("prn", "<i4"), ("ibit0", "<i4"), ("flags", "<u4"), ("reserved", "<u4"),
+    ("prn", "<i4"), ("ibit0", "<i4"), ("flags", "<u4"), ("gain_q7", "<i4"),
     ("code_phase0", "<f8"), ("f_code", "<f8"), ("f_carr", "<f8"), ("carr_phase_init", "<f8"),
     ("page_cur", "u1", PAGE_BYTES), ("page_next", "u1", PAGE_BYTES),
 ])
@@ -30,7 +30,7 @@ RANGE_DTYPE = np.dtype([
 assert RANGE_DTYPE.itemsize == 168
 
 TRACE_DTYPE = np.dtype([
-    ("iumd", "<i4"), ("slot", "<i4"), ("prn", "<i4"), ("ibit", "<i4"), ("ipage", "<i4"), ("pad", "<i4"),
+    ("iumd", "<i4"), ("slot", "<i4"), ("prn", "<i4"), ("ibit", "<i4"), ("ipage", "<i4"), ("gain", "<i4"),
     ("code_phase", "<f8"), ("f_code", "<f8"), ("f_carr", "<f8"), ("carr_phase", "<f8"),
     ("grx", "<f8"), ("rho", "<f8"), ("page", "u1", 504),
 ])
@@ -72,6 +72,7 @@ def oracle():
         lib.e1o_restate.argtypes = [C.c_double] * 4 + [dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.e1o_synth_epochs.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, dp, C.c_void_p]
         lib.e1o_synth_epochs_mt.argtypes = lib.e1o_synth_epochs.argtypes + [C.c_int]
+        lib.e1o_synth_epochs_float.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, dp, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
         lib.e1o_carrier_phases.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, dp, dp, C.c_int]
         _oracle = lib
     return _oracle
@@ -89,6 +90,21 @@ def oracle_synth(fs_hz, n_samp, recs, carr_phase=None, threads=1):
         lib.e1o_synth_epochs_mt(*args, threads)
     else:
         lib.e1o_synth_epochs(*args)
+    return out, ph
+
+
+ALPHA_CBOC, BETA_CBOC = (10.0 / 11.0) ** 0.5, (1.0 / 11.0) ** 0.5     # Galileo OS SIS ICD: CBOC(6,1,1/11)
+
+
+def oracle_synth_float(fs_hz, n_samp, recs, carr_phase=None, cboc=True, use_gain=False, threads=1):
+    """SURVEY 8 f4 oracle (parity unpinned): CBOC sub-carrier and/or per-record gain, double accumulate, nearest int16."""
+    recs = np.ascontiguousarray(recs)
+    n_epochs, max_chan = recs.shape
+    ph = np.zeros(max_chan) if carr_phase is None else np.array(carr_phase, dtype=np.float64)
+    out = np.empty((n_epochs * n_samp, 2), np.int16)
+    a, b = (ALPHA_CBOC, BETA_CBOC) if cboc else (1.0, 0.0)
+    oracle().e1o_synth_epochs_float(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data_as(C.POINTER(C.c_double)),
+                                    out.ctypes.data, a, b, int(use_gain), threads)
     return out, ph
 
 
@@ -164,7 +180,10 @@ def product_lut():
     return lut
 
 
-def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1, planner=2):
+CFG_CBOC, CFG_GAIN = 2, 4     # E1B200_CFG_CBOC / E1B200_CFG_GAIN (include/e1b200.h)
+
+
+def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1, planner=2, cfg_flags=0):
     """Same contract as oracle_synth, through the product's core header on the host.
     planner 1 = serial exact walk per channel, 2 = the parallel planner's passes (default, what the
     kernels run).  Returns (int16 [n_epochs*n_samp, 2], final phases, stats[5]): stats = fallback
@@ -175,8 +194,12 @@ def hostsim_synth(fs_hz, n_samp, recs, carr_phase=None, groups=4, amb_scale=1, p
     out = np.zeros((n_epochs * n_samp, 2), np.int16)
     st = np.zeros(5, np.uint64)
     lut = product_lut()
-    rc = hostsim().hs_synth_epochs_p(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, out.ctypes.data,
-                                     groups, amb_scale, lut.ctypes.data, st.ctypes.data, planner)
+    hostsim().hs_set_cfg_flags(cfg_flags)
+    try:
+        rc = hostsim().hs_synth_epochs_p(fs_hz, n_samp, max_chan, n_epochs, recs.ctypes.data, ph.ctypes.data, out.ctypes.data,
+                                         groups, amb_scale, lut.ctypes.data, st.ctypes.data, planner)
+    finally:
+        hostsim().hs_set_cfg_flags(0)
     assert rc == 0, f"hostsim planner errors: {st}"
     assert hostsim().hs_lut_oob() == 0, "a fast-form lookup left the carrier table"
     assert hostsim().hs_clean_violations() == 0, "a run of a tile marked E1_PAR_CLEAN was flagged by the tracking sample loop"
@@ -209,6 +232,7 @@ def trace_to_recs(trace, max_chan):
         e, s = int(t["iumd"]) - e0, int(t["slot"])
         r = recs[e, s]
         r["prn"], r["ibit0"] = t["prn"], t["ibit"]
+        r["gain_q7"] = t["gain"]           # the reference's gain[i] of this block (src/galileo-sdr.cpp:477; it never uses it)
         r["code_phase0"], r["f_code"], r["f_carr"] = t["code_phase"], t["f_code"], t["f_carr"]
         r["page_cur"] = pack_page(t["page"][:500])
         phase[e, s] = t["carr_phase"]

@@ -76,6 +76,10 @@ unsigned long long hs_clean_violations(void) { return g_clean_violations; }
 // for the whole tile and widens its zone by thr_code for this
 static double g_max_ab = 0.0;
 double hs_max_code_ab_units(void) { return g_max_ab; }
+// E1B200_CFG_CBOC / E1B200_CFG_GAIN for the following hs_synth_epochs* calls (0 = the integer path): the float
+// path of e1_synth_float_kernel -- e1_channel_run_float per (thread, channel), FP32 sums, e1_f2i16 store.
+static uint32_t g_cfg_flags = 0;
+void hs_set_cfg_flags(unsigned int flags) { g_cfg_flags = flags; }
 
 // Whole pipeline on the host.  lut: int32[642][32] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
@@ -173,7 +177,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                 const int sp = t / geo.span_tiles;
                 e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile,
                             e1_trans_at(&delta[(size_t)ch * n_units + (size_t)e * S + sp], (t - sp * geo.span_tiles) * tile), tc_code,
-                            &par[nact]);
+                            &par[nact], g_cfg_flags);
                 if (run == E1C_MAX_RUN && par[nact].j_w != E1C_NO_WRAP && !(par[nact].misc & E1_PAR_FORCE)) {
                     const int64_t d51 = (int64_t)((par[nact].HA - par[nact].HB) << 13) >> 13; // mod 2^51, signed
                     const double units = (double)(d51 < 0 ? -d51 : d51) / 524288.0;
@@ -191,6 +195,28 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
             }
             const int n_valid = (n_samp - t * tile) < tile ? (n_samp - t * tile) : tile;
             int16_t *o = out + ((size_t)e * n_samp + (size_t)t * tile) * 2;
+            if (g_cfg_flags & (E1B200_CFG_CBOC | E1B200_CFG_GAIN)) { // e1_synth_float_kernel: 512 threads x 16 samples
+                const float alpha = (g_cfg_flags & E1B200_CFG_CBOC) ? (float)E1C_ALPHA_CBOC : 1.0f;
+                const float beta = (g_cfg_flags & E1B200_CFG_CBOC) ? (float)E1C_BETA_CBOC : 0.0f;
+                for (int tid = 0; tid < threads; tid++) {
+                    const int j0 = tid * run;
+                    if (j0 >= n_valid)
+                        continue;
+                    const unsigned char *lut_lane = (const unsigned char *)lut + 4 * (tid & (E1C_LUT_REP - 1));
+                    float fi[E1C_MAX_RUN] = {0}, fq[E1C_MAX_RUN] = {0};
+                    for (int a = 0; a < nact; a++) {
+                        const float g = e1_bits_float(par[a].pat_a);
+                        e1_channel_run_float(&par[a], codes.data(), lut_lane, j0, run, fi, fq, g * alpha, g * beta, thr_carr, thr_code,
+                                             e1_bias_h(tc_code), &stats[0]);
+                    }
+                    for (int i = 0; i < run; i++)
+                        if (j0 + i < n_valid) {
+                            o[(size_t)(j0 + i) * 2] = (int16_t)e1_f2i16(fi[i]);
+                            o[(size_t)(j0 + i) * 2 + 1] = (int16_t)e1_f2i16(fq[i]);
+                        }
+                }
+                continue;
+            }
             if (run == E1C_MAX_RUN) { // e1_synth_pair_kernel: 256 threads per tile, two runs of 16 samples each
                 for (int tid = 0; tid < threads / 2; tid++) {
                     const int j0 = tid * 2 * run;

@@ -38,11 +38,26 @@ def replica(hc, n, fs, code_phase, f_code):
     return hc[np.floor(2.0 * (code_phase + k * (f_code / fs))).astype(np.int64) % (2 * CODE_LEN)]
 
 
-def acquire(x, prn, fs, periods=4, f_max=5000.0, f_step=125.0):
-    """-> (metric = peak / mean of the search grid, doppler [Hz], code phase of sample 0 [chips])."""
+def cboc_replica(prn, n, fs, code_phase, f_code, alpha, beta, component=0):
+    """E1-B (component 0: alpha sc_a + beta sc_b) or E1-C (1: alpha sc_a - beta sc_b) CBOC(6,1,1/11) replica sampled
+    at fs (Galileo OS SIS ICD): sc_a / sc_b the BOC(1,1) / BOC(6,1) sub-carriers, negative on their first half period."""
+    hc = halfchips(prn, component)
+    chips = hc[1::2]                                            # +chip sits on the odd half-chip
+    k = np.arange(n, dtype=np.float64)
+    sub = np.floor(12.0 * (code_phase + k * (f_code / fs))).astype(np.int64) % (12 * CODE_LEN)
+    tw = sub % 12
+    sc_a = np.where(tw < 6, -1.0, 1.0)
+    sc_b = np.where(tw & 1, 1.0, -1.0)
+    return (chips[sub // 12] * (alpha * sc_a + (beta if component == 0 else -beta) * sc_b)).astype(np.float32)
+
+
+def acquire(x, prn, fs, periods=4, f_max=5000.0, f_step=125.0, cboc=None, raw=False):
+    """-> (metric = peak / mean of the search grid, doppler [Hz], code phase of sample 0 [chips]).
+    cboc = (alpha, beta): correlate against the E1-B CBOC replica instead of BOC(1,1); raw: also return the peak power."""
     n = int(round(fs * CODE_LEN / F_CODE))                      # samples per 4 ms code period
     hc = halfchips(prn)
-    L = np.conj(np.fft.fft(replica(hc, n, fs, 0.0, F_CODE)))
+    rep = replica(hc, n, fs, 0.0, F_CODE) if cboc is None else cboc_replica(prn, n, fs, 0.0, F_CODE, cboc[0], cboc[1])
+    L = np.conj(np.fft.fft(rep))
     t = np.arange(n * periods) / fs
     best = (0.0, 0.0, 0)
     total, cells = 0.0, 0
@@ -57,6 +72,8 @@ def acquire(x, prn, fs, periods=4, f_max=5000.0, f_step=125.0):
     peak, fd, delay = best
     # the replica's chip 0 sits at sample `delay`: sample 0 is (n - delay) samples into a code period
     code_phase = ((n - delay) % n) * F_CODE / fs
+    if raw:
+        return peak / (total / cells), fd, code_phase % CODE_LEN, peak
     return peak / (total / cells), fd, code_phase % CODE_LEN
 
 

@@ -24,6 +24,11 @@ SCENARIOS = {
     "cfg1": dict(llh=(-6, 51, 100), duration_s=10),
     # tools/make_golden.py's second scenario: crosses the 30 s re-allocation and many page turns
     "paris45": dict(llh=(48.85, 2.35, 35), start=(2021, 6, 20, 11, 59, 40), duration_s=45),
+    # the patched builds of the reference (oracle/ref_patches): 25 MS/s; 36 slots with the mask off (24 satellites,
+    # the 30 s re-allocation, every page turn); both
+    "fs25": dict(llh=(-6, 51, 100), duration_s=3, fs_hz=25e6),
+    "ch36": dict(llh=(-6, 51, 100), duration_s=35, max_chan=36, elev_mask_deg=-90.0),
+    "fs25ch36": dict(llh=(-6, 51, 100), duration_s=3, fs_hz=25e6, max_chan=36, elev_mask_deg=-90.0),
 }
 
 
@@ -117,8 +122,10 @@ def test_range_records_restate_to_the_epoch_records(H):
             lib.e1b200_restate(r["rho_prev"], r["rho_cur"], 0.100000023142, r["grx_sec"], *[C.byref(x) for x in out], C.byref(ib), C.byref(ip))
             g = recs[e, c]
             assert (out[0].value, out[1].value, out[2].value, ib.value) == (g["f_carr"], g["f_code"], g["code_phase0"], g["ibit0"]), (e, c)
-    for f in ("flags", "carr_phase_init", "page_cur", "page_next"):
+    for f in ("carr_phase_init", "page_cur", "page_next"):
         assert np.array_equal(rng[f], recs[f]), f
+    # e1_range_rec has no spare field: E1_REC_* in the low byte of flags, the block's gain[i] above it
+    assert np.array_equal(rng["flags"] & 0xFF, recs["flags"]) and np.array_equal(rng["flags"] >> 8, recs["gain_q7"].astype(np.uint32))
 
 
 def test_receiver_motion_table_and_location_updates(H):
@@ -211,3 +218,35 @@ def test_cli_second_scenario_blocks(tmp_path):
         for e in range(449):
             assert hashlib.sha256(f.read(blk)).hexdigest() == sha[e], e
         assert f.read(1) == b""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra,n", [
+    ("ch36", ["-c", "36", "-m", "-90", "-d", "35"], 260000),
+    ("fs25ch36", ["-f", "25e6", "-c", "36", "-m", "-90", "-d", "3"], 2500000),
+])
+def test_cli_at_the_rates_and_channel_counts_of_the_patched_reference(tmp_path, name, extra, n):
+    """e1sim -f / -c / -m: the rates, slot counts and mask the reference fixes at compile time -- the files equal
+    the patched reference builds' (oracle/ref_patches), block for block."""
+    exe = B.build_cli()
+    out = tmp_path / f"{name}.ishort"
+    r = subprocess.run([str(exe), "-e", str(NAV), "-l", "-6,51,100", "-o", str(out)] + extra, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = (GOLD / f"{name}_sha256.txt").read_text().splitlines()
+    assert hashlib.md5(out.read_bytes()).hexdigest() == lines[0].split()[2]
+
+
+@pytest.mark.gpu
+def test_cli_cboc_and_gain_options(tmp_path):
+    """-C / -A select the float path: another stream than the default, the same size, louder satellites louder."""
+    exe = B.build_cli()
+    outs = {}
+    for tag, extra in (("boc", []), ("cboc", ["-C"]), ("gain", ["-A"])):
+        out = tmp_path / f"{tag}.ishort"
+        r = subprocess.run([str(exe), "-e", str(NAV), "-l", "-6,51,100", "-d", "1", "-o", str(out)] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = np.frombuffer(out.read_bytes(), np.int16).astype(np.float64)
+    assert outs["boc"].size == outs["cboc"].size == outs["gain"].size == 9 * 260000 * 2
+    c = np.corrcoef(outs["boc"], outs["cboc"])[0, 1]
+    assert 0.90 < c < 0.99
+    assert 0.3 < np.abs(outs["gain"]).mean() / np.abs(outs["boc"]).mean() < 0.7
