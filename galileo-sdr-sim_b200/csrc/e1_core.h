@@ -331,7 +331,7 @@ typedef struct e1_tile_ck { /* 32 bytes, one per (epoch, tile, channel) */
 #define E1_CK_ACTIVE 16u
 #define E1_CK_ERROR 32u
 
-typedef struct e1_chan_par { /* 96 bytes, one per active channel of a tile (HBM -> shared memory by bulk copy) */
+typedef struct e1_chan_par { /* 112 bytes, one per active channel of a tile (HBM -> shared memory by bulk copy) */
     uint64_t U0, dU;        /* |carrier phase| and its per-sample step, 2^-64 cycle                    */
     uint64_t HA, HB;        /* code phase at sample 0 / extrapolated back from j_w to sample 0,
                                2^-51 half-chip, plus the fast path's bias (e1_bias_h)                 */
@@ -348,11 +348,19 @@ typedef struct e1_chan_par { /* 96 bytes, one per active channel of a tile (HBM 
                                the magnitude is the two's complement of U and the regime flips), bit 7:
                                no sample of the tile is near an index boundary (e1_par_clean)          */
     double phi, sp, cp, sc; /* exact checkpoint for the exact fallback                                */
+    uint32_t Dlo;           /* E1_PAR_SLOW: low word of the table position's step per sample, 2^-32 entry:
+                               floor(511 dU / 2^32) of the SIGNED step, negated for phase < 0 (the mirrored walk);
+                               its sign is E1_PAR_DOWN                                                 */
+    uint32_t pad[3];
 } e1_chan_par;
 #define E1_PAR_NEG 16u
 #define E1_PAR_FORCE 32u
 #define E1_PAR_HASZ 64u
 #define E1_PAR_CLEAN 128u /* no run of this tile can be ambiguous (e1_par_clean): the sample loop skips its tracking */
+#define E1_PAR_SLOW 256u  /* the carrier moves by less than one table entry per sample (|step| < 1/512 cycle: 5 kHz at
+                             2.6 MS/s) and the tile is regular (no FORCE / HASZ): the paired-run kernel walks the table
+                             by CARRIES of the index fraction, one carrier start per 32 or 64 samples (e1_run_cw)      */
+#define E1_PAR_DOWN 512u  /* with E1_PAR_SLOW: the table position decreases from sample to sample                      */
 
 /* One tile's parameter block in HBM: header (16 bytes: n_active, 3 x pad) + max_chan e1_chan_par,
  * active channels first. */
@@ -1017,6 +1025,10 @@ E1_HD double e1_v2_chain(const e1_prep *pp, int n_units, double phi0, int tile, 
  * itself is within e1_thr_carr / e1_thr_code of the serial value.  Adding the half-width as a bias
  * makes "possibly on the other side of an integer" read as "fraction < 2*half-width + 1".        */
 E1_HD uint32_t e1_tc_carr(uint32_t thr_carr, int R) { return thr_carr + 511u * (uint32_t)R; }
+/* carry-walked runs (e1_run_cw) step floor(511 U / 2^32) by floor(511 dU / 2^32): sample i of the run is below the exact
+   closed form by less than i + 1 <= n_samples units (one floor at the start, one per step) */
+E1_HD uint32_t e1_tc_carr_cw(uint32_t thr_carr, int n_samples) { return thr_carr + (uint32_t)n_samples + 1u; }
+E1_HD uint32_t e1_lim_carr_cw(uint32_t thr_carr, int n_samples) { return e1_tc_carr_cw(thr_carr, n_samples) + thr_carr + 1u; }
 /* code: a run that contains the code wrap keeps stepping the pre-wrap closed form, which is within
  * thr_code of the serial value at the wrap; the serial recurrence restarts there and drifts by at
  * most thr_code more -> 2*thr_code on either side */
@@ -1091,6 +1103,18 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     p->pat_a = ((da & 2u) ? 0xAAAAAAAAu : 0u) | ((da & 1u) ? 0x55555555u : 0u);
     p->pat_b = ((db & 2u) ? 0xAAAAAAAAu : 0u) | ((db & 1u) ? 0x55555555u : 0u);
     p->code_off = (uint32_t)(r->prn - 1) * E1C_CODE_WORDS_PER_PRN;
+    p->Dlo = 0u;
+    p->pad[0] = p->pad[1] = p->pad[2] = 0u;
+    if (!(misc & (E1_PAR_FORCE | E1_PAR_HASZ)) && e1_fabs(p->sp) < 1.0 / 512.0) {
+        /* step of the table position 511 |phase| / 2^32 (entry in the high word): floor(511 dU / 2^32) with dU read as
+           a signed 64-bit number -- |D| < 2^32 because |sp| < 1/512 -- and negated when the table is walked mirrored */
+        const uint64_t lo = (p->dU & 0xffffffffull) * 511ull;                          /* < 2^41 */
+        int64_t D = (int64_t)(int32_t)(uint32_t)(p->dU >> 32) * 511 + (int64_t)(lo >> 32); /* floor: the dropped bits are non-negative */
+        if (misc & E1_PAR_NEG)
+            D = -D;
+        p->Dlo = (uint32_t)(uint64_t)D;
+        misc |= E1_PAR_SLOW | (D < 0 ? E1_PAR_DOWN : 0u);
+    }
     p->misc = misc;
     if (cfg_flags & (E1B200_CFG_CBOC | E1B200_CFG_GAIN)) { /* float path: gain[i] / 2^7 (src/galileo-sdr.cpp:477), exact in float below 2^24 */
         const int32_t g = ((cfg_flags & E1B200_CFG_GAIN) && r->gain_q7 != 0) ? r->gain_q7 : 128;
@@ -1209,16 +1233,29 @@ E1_HD int e1_any_hit(int64_t a, int64_t d, int64_t M, int64_t L, int64_t n) { re
  *            runs that start before the code wrap, HB (= HA to within thr_code) after;
  *   both     the 40-bit sequence used here is below the exact one by less than (T + 1) / 256 <= 33.
  * FORCE / HASZ tiles are not examined (the kernel takes them through the single-run path anyway). */
-E1_HD int e1_par_clean(const e1_chan_par *p, int T, uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code, uint32_t thr_code)
+E1_HD int e1_par_clean(const e1_chan_par *p, int T, uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code, uint32_t thr_code,
+                        int cw_samples = 2 * E1C_MAX_RUN)
 {
     if ((p->misc & (E1_PAR_FORCE | E1_PAR_HASZ)) || T > 8192)
         return 0;
     const int64_t M = (int64_t)1 << E1_AMB_BITS;
     const int R = E1C_MAX_RUN, sh = 64 - E1_AMB_BITS, slack = 33;
     {
+        /* E1_PAR_SLOW tiles step the carrier position through BOTH halves of a pair from one start: the same
+           statement with a run of 2 R samples (bias and limit 511 R larger, e1_tc_carr_pair / e1_lim_carr_pair) */
+        /* E1_PAR_SLOW tiles step the full-precision position 511 U / 2^32 through both halves of a pair from one start:
+           the loop's biased fraction lies in (r + tc - (cw_samples + 1), r + tc] (e1_carrier_start_p), tc and lim are
+           those of a run of cw_samples (e1_tc_carr_cw / e1_lim_carr_cw; 32 or 64 samples per thread) */
+        int64_t step_slack = 511 * R;
+        if (p->misc & E1_PAR_SLOW) {
+            const uint32_t thr_carr = tc_carr - 511u * (uint32_t)R;
+            tc_carr = e1_tc_carr_cw(thr_carr, cw_samples);
+            lim_carr = e1_lim_carr_cw(thr_carr, cw_samples);
+            step_slack = cw_samples + 1;
+        }
         const uint64_t G0 = p->U0 * 511ull, GB = p->dU * 511ull; /* mod 2^64: the index fraction, 2^-64 */
         const int64_t a = (int64_t)(((G0 >> sh) + (((uint64_t)tc_carr + slack) << (E1_AMB_BITS - 32))) & (uint64_t)(M - 1));
-        const int64_t L = ((int64_t)lim_carr + 511 * R + slack + 1) << (E1_AMB_BITS - 32);
+        const int64_t L = ((int64_t)lim_carr + step_slack + slack + 1) << (E1_AMB_BITS - 32);
         if (L >= M / 2)
             return 0;
         if (e1_any_hit(a, (int64_t)(GB >> sh), M, L, T))
@@ -1442,6 +1479,7 @@ static __device__ __forceinline__ uint32_t e1_ld32(e1_sptr a)
 #else
 #if defined(E1_CHECK_LUT_BOUNDS)
 static unsigned long long e1_lut_oob = 0;
+static const unsigned char *e1_lut_base = 0; /* carrier table of the running test (lane copy 0): address-walking loops check against it */
 #endif
 typedef const unsigned char *e1_sptr;
 static inline e1_sptr e1_sp(const void *p) { return (const unsigned char *)p; }
@@ -1615,6 +1653,203 @@ E1_HD uint32_t e1_run_fast_pair(const e1_chan_par *p, const uint32_t *codes, con
         rc |= e1_sample_loop<E1C_MAX_RUN, CHECK>(y, D, lut, (uint32_t)(H >> 19), dF, win, acc + h * R, lim_carr, lim_code) << (2 * h);
     }
     return rc;
+}
+
+/* ---- paired runs, carrier table walked by carries (E1_PAR_SLOW tiles) -------------------------------------
+ * The table position of e1_sample_loop is a 64-bit number, entry in the high word, index fraction in the low
+ * word, stepped by D per sample.  When |D| < 2^32 (less than one entry per sample) the high word changes by at
+ * most one: the loop keeps the fraction and the table ADDRESS instead, adds the low word of D to the fraction
+ * with its carry flag, and moves the address by one entry (128 bytes) on a carry (D >= 0) or on a missing carry
+ * (D < 0, i.e. a borrow) -- the same integers as the 64-bit add, one instruction per sample less (no
+ * multiply-add from entry number to address).  At most 2 R < E1C_LUT_EXT entries are walked from one start, so
+ * ONE carrier start serves both halves of the pair (bias and limit for a run of 2 R samples).  The code side is
+ * what e1_run_fast_pair does, half by half.  Returns 1 when some sample of the pair is ambiguous (CHECK): the
+ * caller takes the terms back out and redoes the samples with the generic form (e1_cw_rest_impl). */
+
+/* Sample loop with the table walked by carries: see e1_cw_step below.  `one` is the value 1 in a register ptxas
+ * cannot see through (the kernel derives it from a launch argument): the address step is spelled
+ * mad.lo(one, +-128, addr) so that it is issued to the multiplier pipe.  The loop is bound by its two integer pipes
+ * (each takes an instruction every other clock): with the step as a plain add the ALU pipe carries four of the six
+ * arithmetic instructions per sample, this way three and three. */
+/* e1_carrier_start at full precision, for the carry-walked pairs: table position of the run's first sample from
+ * floor(511 U / 2^32) (U: |phase|, 2^-64 cycle), entry in the high word, fraction in the low word.  up = the
+ * unmirrored position increases (only then can a carrier wrap fall into the run).  Same layout rules as
+ * e1_carrier_start. */
+E1_HD uint64_t e1_carrier_start_p(uint64_t U, uint32_t neg, uint32_t up, uint32_t tc_carr, uint32_t lim_carr)
+{
+    const uint64_t lo = (U & 0xffffffffull) * 511ull;
+    const uint64_t y0 = (U >> 32) * 511ull + (lo >> 32) + tc_carr;
+    const uint64_t wrap = (up && (uint32_t)(y0 >> 32) >= 511u - E1C_LUT_EXT) ? (511ull << 32) : 0ull;
+    if (!neg)
+        return y0 + ((uint64_t)E1C_LUT_EXT << 32) - wrap;
+    return (((uint64_t)(513 + E1C_LUT_EXT) << 32) - 1ull) - y0 + wrap + lim_carr;
+}
+
+/* One step of the carry-walked sample loop (see e1_sample_loop_cw), on one run's state. */
+template <bool CHECK, bool DOWN>
+E1_HD void e1_cw_step(uint32_t &ylo, e1_sptr &addr, uint32_t Dlo, uint32_t &F, uint32_t dF, uint32_t &win, int &acc, uint32_t &mY, uint32_t &mF,
+                      uint32_t one)
+{
+    if (CHECK) {
+        mY = ylo < mY ? ylo : mY;
+        mF = F < mF ? F : mF;
+    }
+#if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
+    if ((size_t)(addr - e1_lut_base) >= (size_t)E1C_LUT_IDX * 4u * E1C_LUT_REP)
+        e1_lut_oob++;
+#endif
+    const int w = (int)e1_ld32(addr);
+    acc += w * ((int)win >> 30);
+#if defined(__CUDA_ARCH__)
+    uint32_t cy, cz;
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(ylo), "=r"(cy) : "r"(Dlo));
+    if (DOWN) {
+        if (!cy)
+            asm("mad.lo.u32 %0, %1, -128, %0;" : "+r"(addr) : "r"(one));
+    } else {
+        if (cy)
+            asm("mad.lo.u32 %0, %1, 128, %0;" : "+r"(addr) : "r"(one));
+    }
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(F), "=r"(cz) : "r"(dF));
+    if (cz)
+        win <<= 2;
+#else
+    (void)one;
+    const uint32_t y2 = ylo + Dlo;
+    if (DOWN) {
+        if (!(y2 < ylo))
+            addr -= 4u * E1C_LUT_REP;
+    } else {
+        if (y2 < ylo)
+            addr += 4u * E1C_LUT_REP;
+    }
+    ylo = y2;
+    const uint32_t F2 = F + dF;
+    if (F2 < F)
+        win <<= 2;
+    F = F2;
+#endif
+}
+
+/* NH consecutive runs of R = 16 samples (NH = 2: 32 samples per thread, NH = 4: 64) from ONE carrier start: every
+ * run's table position is the start's plus a multiple of 16 D (|D| < 1 entry per sample and NH R <= E1C_LUT_EXT keep all of
+ * them inside the table's extension); the code side is set up run by run as in e1_run_fast_pair.  All set-up comes
+ * first, then ONE loop of R iterations steps the NH runs side by side: NH independent dependency chains for the
+ * scheduler instead of one of NH R steps.  codes_s / lut_s: the code words and this lane's copy of the carrier table
+ * as shared-memory operands (e1_sptr).  Returns 1 when some sample is ambiguous. */
+template <int NH, bool CHECK, bool DOWN>
+E1_HD uint32_t e1_run_cw(const e1_chan_par *p, e1_sptr codes_s, e1_sptr lut_s, int j0, int *acc, uint32_t tc_carr, uint32_t lim_carr,
+                         uint32_t lim_code, uint32_t one)
+{
+    const int R = E1C_MAX_RUN;
+    const int jw = p->j_w;
+    const uint64_t dH = p->dH;
+    const uint32_t dF = p->dF;
+    const e1_sptr code = codes_s + 4u * p->code_off;
+    const uint32_t neg = p->misc & E1_PAR_NEG;
+    const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
+    /* the mirrored walk goes down when the unmirrored one goes up */
+    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (DOWN || p->Dlo == 0u) : !DOWN, tc_carr, lim_carr);
+    const uint32_t Dlo = p->Dlo; /* |D| < 2^32 and sign(D) = DOWN (e1_make_par): the low word says it all */
+    const uint64_t D16 = ((uint64_t)Dlo << 4) - (DOWN ? (1ull << 36) : 0ull); /* 16 D as a 64-bit two's complement number */
+    uint32_t ylo[NH], F[NH], win[NH];
+    e1_sptr addr[NH];
+    uint32_t mY = 0xffffffffu, mF = 0xffffffffu;
+    int after_prev = j0 >= jw;
+    uint64_t H = (after_prev ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * dH;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int h = 0; h < NH; h++) {
+        const int jh = j0 + h * R;
+        if (h > 0) { /* a run continues the previous one's code phase unless the code wrapped in between */
+            const int after = jh >= jw;
+            H = after != after_prev ? p->HB + (uint64_t)(uint32_t)jh * dH : H + (uint64_t)R * dH;
+            after_prev = after;
+        }
+        win[h] = e1_code_window(p, code, H, jh, R, jw);
+        F[h] = (uint32_t)(H >> 19);
+        const uint64_t yh = y + (uint64_t)h * D16;
+        ylo[h] = (uint32_t)yh;
+        addr[h] = lut_s + (uint32_t)(yh >> 32) * (4u * E1C_LUT_REP);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < R; i++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int h = 0; h < NH; h++)
+            e1_cw_step<CHECK, DOWN>(ylo[h], addr[h], Dlo, F[h], dF, win[h], acc[h * R + i], mY, mF, one);
+    }
+    return CHECK ? (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code) : 0u;
+}
+
+/* One channel's contribution to the NH R samples of a thread.  E1_PAR_SLOW tiles -- all of them at the Dopplers of a
+ * terrestrial receiver -- are walked by carries, inline (four instances: tracking on / off, position up / down).
+ * Returns 0 when the terms are in acc and final; E1_RC_CW when they are in acc but some sample is ambiguous;
+ * E1_RC_OLD when nothing was added because the tile is not E1_PAR_SLOW (fast carrier, forced generic form, zero
+ * crossing): the caller then takes the out-of-line path (e1_cw_rest_impl), which keeps the common loop small. */
+#define E1_RC_CW 16u
+#define E1_RC_OLD 32u
+template <int NH>
+E1_HD uint32_t e1_cw_add(const e1_chan_par *p, e1_sptr codes_s, e1_sptr lut_s, int j0, int *acc, uint32_t thr_carr, uint32_t lim_code,
+                         int check, uint32_t one)
+{
+    const uint32_t misc = p->misc;
+    if (!(misc & E1_PAR_SLOW))
+        return E1_RC_OLD;
+    const uint32_t tc = e1_tc_carr_cw(thr_carr, NH * E1C_MAX_RUN), lim = e1_lim_carr_cw(thr_carr, NH * E1C_MAX_RUN);
+    uint32_t rc;
+    if (check)
+        rc = (misc & E1_PAR_DOWN) ? e1_run_cw<NH, true, true>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one)
+                                  : e1_run_cw<NH, true, false>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one);
+    else
+        rc = (misc & E1_PAR_DOWN) ? e1_run_cw<NH, false, true>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one)
+                                  : e1_run_cw<NH, false, false>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one);
+    return rc ? E1_RC_CW : 0u;
+}
+
+/* The out-of-line rest: d[0 .. NH R) receives what has to be ADDED to the accumulators.
+ *   E1_RC_CW   the generic form of all NH R samples minus the carry-walk's terms (recomputed: same integers)
+ *   E1_RC_OLD  the samples as runs of R in the 64-bit-position form (e1_run_fast, tracking on), each flagged or
+ *              unhandled run replaced by the generic form                                                      */
+template <int NH>
+E1_HD void e1_cw_rest_impl(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *d, uint32_t rc,
+                           uint32_t thr_carr, uint32_t thr_code, uint32_t tc_carr, uint32_t tc_code, unsigned long long *n_exact,
+                           unsigned long long *n_slow)
+{
+    const int R = E1C_MAX_RUN;
+    const uint32_t lim_carr = e1_lim_carr(tc_carr, thr_carr), lim_code = e1_lim_code(tc_code, thr_code);
+    if (rc == E1_RC_CW) {
+        int t[NH * E1C_MAX_RUN];
+        for (int i = 0; i < NH * R; i++)
+            t[i] = 0;
+        e1_cw_add<NH>(p, e1_sp(codes), e1_sp(lut_lane), j0, t, thr_carr, lim_code, 0, 1u);
+        e1_channel_run(p, codes, lut_lane, j0, NH * R, d, thr_carr, thr_code, e1_bias_h(tc_code), n_exact);
+        for (int i = 0; i < NH * R; i++)
+            d[i] -= t[i];
+        if (n_slow)
+            (*n_slow)++;
+        return;
+    }
+    for (int i = 0; i < NH * R; i++)
+        d[i] = 0;
+    for (int h = 0; h < NH; h++) {
+        const uint32_t rc2 = e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0 + h * R, d + h * R, tc_carr, lim_carr, lim_code);
+        if (rc2) {
+            int t[E1C_MAX_RUN], g[E1C_MAX_RUN];
+            for (int i = 0; i < R; i++)
+                t[i] = 0;
+            e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0 + h * R, t, tc_carr, lim_carr, lim_code);
+            e1_channel_run(p, codes, lut_lane, j0 + h * R, R, g, thr_carr, thr_code, e1_bias_h(tc_code), n_exact);
+            for (int i = 0; i < R; i++)
+                d[h * R + i] += g[i] - t[i];
+            if (n_slow)
+                (*n_slow)++;
+        }
+    }
 }
 
 /* acc = I + 65536*Q  ->  the sink's little-endian (int16 I, int16 Q) pair (:536-537) */

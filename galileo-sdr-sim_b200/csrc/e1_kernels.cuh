@@ -8,14 +8,14 @@
  *   e1_finalize_kernel       checkpoints + translations -> one parameter block per tile
  *   e1_clean_kernel          tile-level ambiguity test (e1_par_clean): marks the (tile, channel) sets whose runs
  *                            cannot be ambiguous, so the sample loop skips its per-sample tracking for them
- *   e1_synth_pair_kernel     the sample loop (src/galileo-sdr.cpp:481-539): per sample, all channels,
- *                            int32 accumulate, packed int16 I/Q, 128-bit stores; 32 samples per thread
+ *   e1_synth_cw_kernel<NH,T> the sample loop (src/galileo-sdr.cpp:481-539): per sample, all channels,
+ *                            int32 accumulate, packed int16 I/Q, 128-bit stores; 32 or 64 samples per thread
  *   e1_synth_kernel<R>       the same with R = 4, 8 or 16 samples per thread (tiles shorter than 8192 samples)
  *
  * HBM layout
  *   recs   e1_epoch_rec[n_epochs][max_chan]                         176 B each (caller / H2D)
  *   ck     e1_tile_ck[n_epochs][tiles_per_epoch][max_chan]           32 B each (scratch)
- *   blk    per tile: 16 B header + max_chan e1_chan_par (96 B), active channels first (scratch)
+ *   blk    per tile: 16 B header + max_chan e1_chan_par (112 B), active channels first (scratch)
  *   out    int16 I,Q interleaved, sample (epoch*N + k) at byte 4*(epoch*N + k)
  *   codes  uint32[50][516]: one 2-bit field per BOC(1,1) half-chip (see e1_core.h)   103 200 B
  *   lut    int32[642][32]: carrier term by table position, one copy per lane         82 176 B
@@ -560,6 +560,7 @@ struct e1_clean_args {
     long n_tiles;
     int max_chan, tile;
     uint32_t tc_carr, lim_carr, lim_code, thr_code;
+    int cw_samples; /* samples a thread of the synthesis kernel walks from one carrier start (32 or 64) */
 };
 __global__ void __launch_bounds__(128) e1_clean_kernel(const e1_clean_args A)
 {
@@ -573,8 +574,8 @@ __global__ void __launch_bounds__(128) e1_clean_kernel(const e1_clean_args A)
         return;
     e1_chan_par *p = reinterpret_cast<e1_chan_par *>(blk + E1C_BLK_HEADER) + slot;
     e1_chan_par q;
-    q.U0 = p->U0, q.dU = p->dU, q.HA = p->HA, q.HB = p->HB, q.dH = p->dH, q.j_w = p->j_w, q.misc = p->misc;
-    if (e1_par_clean(&q, A.tile, A.tc_carr, A.lim_carr, A.lim_code, A.thr_code))
+    q.U0 = p->U0, q.dU = p->dU, q.HA = p->HA, q.HB = p->HB, q.dH = p->dH, q.j_w = p->j_w, q.misc = p->misc, q.Dlo = p->Dlo;
+    if (e1_par_clean(&q, A.tile, A.tc_carr, A.lim_carr, A.lim_code, A.thr_code, A.cw_samples))
         p->misc = q.misc | E1_PAR_CLEAN;
 }
 
@@ -594,6 +595,17 @@ __device__ __noinline__ void e1_fix_run(const e1_chan_par *p, const uint32_t *co
 #pragma unroll
     for (int i = 0; i < R; i++)
         d[i] = g[i] - t[i];
+}
+
+/* The out-of-line rest of a carry-walked run (rc from e1_cw_add; see e1_cw_rest_impl).  Takes the shared-memory
+ * operands the kernel holds and turns them back into generic pointers for the generic-form functions. */
+template <int NH>
+__device__ __noinline__ void e1_cw_rest(const e1_chan_par *p, uint32_t codes_s, uint32_t lut_s, int j0, int *d, uint32_t rc, uint32_t thr_carr,
+                                        uint32_t thr_code, uint32_t tc_carr, uint32_t tc_code, unsigned long long *n_exact)
+{
+    const uint32_t *codes = (const uint32_t *)__cvta_shared_to_generic((size_t)codes_s);
+    const unsigned char *lut_lane = (const unsigned char *)__cvta_shared_to_generic((size_t)lut_s);
+    e1_cw_rest_impl<NH>(p, codes, lut_lane, j0, d, rc, thr_carr, thr_code, tc_carr, tc_code, n_exact, (unsigned long long *)0);
 }
 
 /* Persistent CTA, one per SM.  Shared memory: code words of all PRNs (103 200 B) and the replicated
@@ -806,39 +818,43 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_float_kernel(con
         atomicAdd(&A.counters[0], s_cnt);
 }
 
-/* ------------------------------------------------------------------ synthesis, paired runs
- * Same work as e1_synth_kernel<16> with 32 consecutive samples per thread (e1_run_fast_pair: the
- * per-(thread, channel) set-up -- a third of the instructions of the 16-sample kernel -- is paid once
- * per 32 samples).  A tile is still 8192 samples (one code wrap per tile at most), so a tile needs
- * 256 threads: the CTA's 512 threads are two TEAMS of 256 that walk their own tiles independently --
- * own parameter buffers, own mbarriers, own named barrier -- and share the code and carrier tables. */
-#define E1_TEAM_THREADS 256
-#define E1_PAIR_RUN (2 * E1C_MAX_RUN)
+/* ------------------------------------------------------------------ synthesis, carry-walked runs, teams
+ * The sample loop for 8192-sample tiles.  A thread owns NH x 16 consecutive samples of a tile (NH = 2: 32 samples,
+ * NH = 4: 64) and walks the active channels with the sums in registers (e1_cw_add: one carrier start per thread and
+ * channel, the table walked by carries, the per-(thread, channel) set-up paid once per 32 / 64 samples).  A tile
+ * needs 8192 / (16 NH) threads: the CTA is TEAMS teams of that many threads (2 x 256 or 3 x 128) that walk their own
+ * tiles independently -- own parameter buffers, own mbarriers, own named barrier -- and share the code and carrier
+ * tables.  3 x 128 threads leave 168 registers per thread for the 64 sums of NH = 4. */
+#define E1_CW_RUN(NH) ((NH) * E1C_MAX_RUN)
+#define E1_CW_TEAM_THREADS(NH) (E1C_THREADS * E1C_MAX_RUN / E1_CW_RUN(NH))
 
+template <int TEAM_THREADS>
 __device__ __forceinline__ void e1_team_sync(int team)
 {
-    asm volatile("bar.sync %0, %1;" : : "r"(1 + team), "n"(E1_TEAM_THREADS) : "memory");
+    asm volatile("bar.sync %0, %1;" : : "r"(1 + team), "n"(TEAM_THREADS) : "memory");
 }
 
-__global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_pair_kernel(const e1_synth_args A)
+template <int NH, int TEAMS>
+__global__ void __launch_bounds__(TEAMS *E1_CW_TEAM_THREADS(NH), 1) e1_synth_cw_kernel(const e1_synth_args A)
 {
+    constexpr int TT = E1_CW_TEAM_THREADS(NH), RUN = E1_CW_RUN(NH), NT = TEAMS * TT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *s_codes = reinterpret_cast<uint32_t *>(smem_raw);
     unsigned char *s_lut = smem_raw + E1_CODES_BYTES;
     const uint32_t blk_bytes = (uint32_t)e1_blk_bytes(A.max_chan);
-    __shared__ __align__(8) uint64_t s_bar[5]; /* [0] tables, [1 + 2 team + b] parameter buffer b of a team */
+    __shared__ __align__(8) uint64_t s_bar[1 + 2 * TEAMS]; /* [0] tables, [1 + 2 team + b] parameter buffer b of a team */
     __shared__ unsigned long long s_cnt;
-    __shared__ long s_tile[2][2]; /* [team][b]: tile number whose block is (being) loaded into that buffer */
+    __shared__ long s_tile[TEAMS][2]; /* [team][b]: tile number whose block is (being) loaded into that buffer */
 
-    const int tid = threadIdx.x, team = tid >> 8, t = tid & (E1_TEAM_THREADS - 1);
+    const int tid = threadIdx.x, team = tid / TT, t = tid - team * TT;
     unsigned char *s_blk0 = smem_raw + E1_CODES_BYTES + E1_LUT_BYTES + (size_t)team * 2 * blk_bytes;
     uint64_t *bar = &s_bar[1 + 2 * team];
     const long total_tiles = (long)A.n_epochs * A.tiles_per_epoch;
-    const long first_wave = 2l * gridDim.x;
+    const long first_wave = (long)TEAMS * gridDim.x;
     long next_id = 0; /* team leader: the tile after the one in s_tile[team][...] */
     if (tid == 0) {
         s_cnt = 0;
-        for (int i = 0; i < 5; i++)
+        for (int i = 0; i < 1 + 2 * TEAMS; i++)
             e1_mbar_init(&s_bar[i], 1);
         e1_mbar_init_fence();
         if (A.use_bulk) {
@@ -849,7 +865,7 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_pair_kernel(cons
     }
     __syncthreads();
     if (t == 0) {
-        const long first = 2l * blockIdx.x + team;
+        const long first = (long)TEAMS * blockIdx.x + team;
         s_tile[team][0] = first;
         if (first < total_tiles) {
             e1_mbar_expect(&bar[0], blk_bytes);
@@ -861,16 +877,18 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_pair_kernel(cons
     if (A.use_bulk) {
         e1_mbar_wait(&s_bar[0], 0);
     } else {
-        for (int i = tid; i < E1_CODES_BYTES / 4; i += E1_SYNTH_THREADS)
+        for (int i = tid; i < E1_CODES_BYTES / 4; i += NT)
             s_codes[i] = A.codes[i];
-        for (int i = tid; i < E1_LUT_ENTRIES; i += E1_SYNTH_THREADS)
+        for (int i = tid; i < E1_LUT_ENTRIES; i += NT)
             reinterpret_cast<int32_t *>(s_lut)[i] = A.lut[i];
         __syncthreads();
     }
 
-    const unsigned char *lut_lane = s_lut + 4 * (tid & (E1C_LUT_REP - 1)); /* this lane's copy of every entry */
-    const uint32_t lim_carr = e1_lim_carr(A.tc_carr, A.thr_carr), lim_code = e1_lim_code(A.tc_code, A.thr_code);
-    const int j0 = t * E1_PAIR_RUN;
+    const uint32_t codes_s = e1_smem_u32(s_codes);
+    const uint32_t lut_s = e1_smem_u32(s_lut) + 4u * (uint32_t)(tid & (E1C_LUT_REP - 1)); /* this lane's copy of every entry */
+    const uint32_t lim_code = e1_lim_code(A.tc_code, A.thr_code);
+    const uint32_t one = (uint32_t)A.use_bulk | 1u; /* the value 1, opaque to ptxas (e1_sample_loop_cw) */
+    const int j0 = t * RUN;
     unsigned long long n_exact = 0;
     for (int it = 0;; it++) {
         const int b = it & 1;
@@ -895,42 +913,36 @@ __global__ void __launch_bounds__(E1_SYNTH_THREADS, 1) e1_synth_pair_kernel(cons
         const int n_valid = min(A.tile, A.n_samp - tt * A.tile);
 
         if (j0 < n_valid) {
-            int acc[E1_PAIR_RUN];
+            int acc[RUN];
 #pragma unroll
-            for (int i = 0; i < E1_PAIR_RUN; i++)
+            for (int i = 0; i < RUN; i++)
                 acc[i] = 0;
             for (int a = 0; a < nact; a++) {
-                const uint32_t rc = (par[a].misc & E1_PAR_CLEAN)
-                                        ? e1_run_fast_pair<false>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code)
-                                        : e1_run_fast_pair<true>(&par[a], s_codes, lut_lane, j0, acc, A.tc_carr, lim_carr, lim_code);
-                if (rc) { /* rare: a half of this (thread, channel) goes through the generic form */
+                const uint32_t rc = e1_cw_add<NH>(&par[a], codes_s, lut_s, j0, acc, A.thr_carr, lim_code, !(par[a].misc & E1_PAR_CLEAN), one);
+                if (rc) { /* rare: this (thread, channel) goes through the generic form; the correction comes back in an array of
+                             its own so that the accumulators never have to live in local memory */
+                    int d[RUN];
+                    e1_cw_rest<NH>(&par[a], codes_s, lut_s, j0, d, rc, A.thr_carr, A.thr_code, A.tc_carr, A.tc_code, &n_exact);
 #pragma unroll
-                    for (int h = 0; h < 2; h++)
-                        if ((rc >> (2 * h)) & 3u) {
-                            int d[E1C_MAX_RUN];
-                            e1_fix_run<E1C_MAX_RUN>(&par[a], s_codes, lut_lane, j0 + h * E1C_MAX_RUN, d, A.thr_carr, A.thr_code, A.tc_carr,
-                                                    A.tc_code, &n_exact);
-#pragma unroll
-                            for (int i = 0; i < E1C_MAX_RUN; i++)
-                                acc[h * E1C_MAX_RUN + i] += d[i];
-                        }
+                    for (int i = 0; i < RUN; i++)
+                        acc[i] += d[i];
                 }
             }
             /* a6 + sink format (:536-537): (short)I, (short)Q interleaved; acc = I + 65536*Q */
             int16_t *dst = A.out + ((size_t)e * A.n_samp + (size_t)tt * A.tile + j0) * 2;
-            if (A.vec_ok && j0 + E1_PAIR_RUN <= n_valid) {
+            if (A.vec_ok && j0 + RUN <= n_valid) {
 #pragma unroll
-                for (int i = 0; i < E1_PAIR_RUN; i += 4)
+                for (int i = 0; i < RUN; i += 4)
                     *reinterpret_cast<uint4 *>(dst + 2 * i) =
                         make_uint4(e1_pack_iq(acc[i]), e1_pack_iq(acc[i + 1]), e1_pack_iq(acc[i + 2]), e1_pack_iq(acc[i + 3]));
             } else {
 #pragma unroll
-                for (int i = 0; i < E1_PAIR_RUN; i++)
+                for (int i = 0; i < RUN; i++)
                     if (j0 + i < n_valid)
                         *reinterpret_cast<uint32_t *>(dst + 2 * i) = e1_pack_iq(acc[i]);
             }
         }
-        e1_team_sync(team); /* all reads of this tile's block (and of s_tile[team][b]) are done */
+        e1_team_sync<TT>(team); /* all reads of this tile's block (and of s_tile[team][b]) are done */
     }
     if (n_exact)
         atomicAdd(&s_cnt, n_exact);

@@ -25,7 +25,9 @@ struct e1b200_ctx {
     int tile;           /* samples per planner checkpoint / synthesis tile              */
     int run;            /* consecutive samples per thread: tile = 512 * run             */
     int elide;          /* mark tiles that cannot hold an ambiguous sample (e1_clean_kernel) so the sample loop skips its tracking */
-    int pair;           /* run == 16: two runs per thread, two 256-thread teams per CTA (e1_synth_pair_kernel) */
+    int pair;           /* run == 16: 8192-sample tiles through e1_synth_cw_kernel (teams, carry-walked runs) */
+    int quad;           /* ... with 64 samples per thread in 3 teams of 128 threads instead of 32 in 2 teams of 256 */
+    int synth_threads;  /* threads per synthesis CTA */
     int tiles_per_epoch;
     int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
     int plan_epochs;    /* epochs per planner pass (bounds scratch)                     */
@@ -110,10 +112,10 @@ static int env_int(const char *name, int dflt)
 }
 
 typedef void (*synth_fn)(const e1_synth_args);
-static synth_fn synth_for(int run, int pair = 0)
+static synth_fn synth_for(int run, int pair = 0, int quad = 0)
 {
     if (pair)
-        return e1_synth_pair_kernel;
+        return quad ? e1_synth_cw_kernel<4, 3> : e1_synth_cw_kernel<2, 2>;
     switch (run) {
     case 4: return e1_synth_kernel<4>;
     case 8: return e1_synth_kernel<8>;
@@ -168,6 +170,8 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
         return E1B200_EINVAL;
     }
     ctx->pair = (run == E1C_MAX_RUN) && !env_int("E1B200_NO_PAIR", 0) && !ctx->float_path;
+    ctx->quad = ctx->pair && env_int("E1B200_QUAD", 1);
+    ctx->synth_threads = ctx->pair ? (ctx->quad ? 3 * E1_CW_TEAM_THREADS(4) : 2 * E1_CW_TEAM_THREADS(2)) : E1_SYNTH_THREADS;
     ctx->tile = run * E1_SYNTH_THREADS;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
     ctx->geo = e1_span_geometry(ctx->tiles_per_epoch);
@@ -184,21 +188,21 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     long pe = (long)(((size_t)env_int("E1B200_PLAN_MB", 2048) << 20) / ck_epoch_bytes);
     ctx->plan_epochs = pe < 1 ? 1 : (pe > 4096 ? 4096 : (int)pe);
     ctx->sm_count = prop.multiProcessorCount;
-    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + (ctx->pair ? 4 : 2) * (int)e1_blk_bytes(cfg->max_chan);
+    ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + (ctx->pair ? (ctx->quad ? 6 : 4) : 2) * (int)e1_blk_bytes(cfg->max_chan);
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    synth_fn fn = synth_for(run, ctx->pair);
+    synth_fn fn = synth_for(run, ctx->pair, ctx->quad);
     int occ = 0;
     if (ctx->float_path) {
         CK(cudaFuncSetAttribute(e1_synth_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e1_synth_float_kernel, E1_SYNTH_THREADS, ctx->smem_bytes));
     } else {
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, E1_SYNTH_THREADS, ctx->smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, ctx->synth_threads, ctx->smem_bytes));
     }
     if (occ < 1)
         return fail(ctx, E1B200_ECUDA, "synthesis kernel does not fit on this device", cudaSuccess);
@@ -434,6 +438,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
             const uint32_t thr_carr = e1_thr_carr(ctx->tile, ctx->amb_scale), thr_code = e1_thr_code(ctx->tile, ctx->amb_scale);
             C.tc_carr = e1_tc_carr(thr_carr, ctx->run);
             C.lim_carr = e1_lim_carr(C.tc_carr, thr_carr);
+            C.cw_samples = ctx->quad ? E1_CW_RUN(4) : E1_CW_RUN(2);
             C.lim_code = e1_lim_code(F.tc_code, thr_code);
             C.thr_code = thr_code;
             e1_clean_kernel<<<(unsigned)((tiles * cfg->max_chan + 127) / 128), 128, 0, ctx->stream>>>(C);
@@ -469,7 +474,8 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     A.use_bulk = ctx->use_bulk;
     long total_tiles = (long)n * ctx->tiles_per_epoch;
     long grid = (long)ctx->sm_count * ctx->ctas_per_sm;
-    const long cta_tiles = ctx->pair ? (total_tiles + 1) / 2 : total_tiles; /* a paired-run CTA starts on two tiles */
+    const int teams = ctx->pair ? (ctx->quad ? 3 : 2) : 1;
+    const long cta_tiles = (total_tiles + teams - 1) / teams; /* a CTA of the team kernel starts on one tile per team */
     if (grid > cta_tiles)
         grid = cta_tiles;
     CK(cudaMemsetAsync(ctx->d_next_tile, 0, sizeof(unsigned int), ctx->stream));
@@ -479,7 +485,7 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     if (ctx->float_path)
         e1_synth_float_kernel<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A, ctx->alpha, ctx->beta);
     else
-        synth_for(ctx->run, ctx->pair)<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A);
+        synth_for(ctx->run, ctx->pair, ctx->quad)<<<(unsigned)grid, ctx->synth_threads, ctx->smem_bytes, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     ctx->timing.synth_launches += 1;

@@ -78,8 +78,57 @@ static double g_max_ab = 0.0;
 double hs_max_code_ab_units(void) { return g_max_ab; }
 // E1B200_CFG_CBOC / E1B200_CFG_GAIN for the following hs_synth_epochs* calls (0 = the integer path): the float
 // path of e1_synth_float_kernel -- e1_channel_run_float per (thread, channel), FP32 sums, e1_f2i16 store.
+static unsigned long long g_cw_pairs = 0; // (thread, channel) pairs that went through the carry-walk form since load
+unsigned long long hs_cw_pairs(void) { return g_cw_pairs; }
+static int g_cw_nh = 4; // runs of 16 samples per thread of the team kernel: 4 (64 samples, 3 x 128 threads) or 2
+void hs_set_cw_runs(int nh) { g_cw_nh = nh == 2 ? 2 : 4; }
 static uint32_t g_cfg_flags = 0;
 void hs_set_cfg_flags(unsigned int flags) { g_cfg_flags = flags; }
+
+} // extern "C"
+// One tile of e1_synth_cw_kernel<NH, .>: every thread's NH x 16 samples, channel by channel.
+template <int NH>
+static void cw_tile(const e1_chan_par *par, int nact, const uint32_t *codes, const unsigned char *lut, int n_valid, int16_t *o, uint32_t thr_carr,
+                    uint32_t thr_code, uint32_t tc_carr, uint32_t tc_code, uint32_t lim_code, unsigned long long *stats)
+{
+    const int RUN = NH * E1C_MAX_RUN, threads = E1C_THREADS * E1C_MAX_RUN / RUN;
+    for (int tid = 0; tid < threads; tid++) {
+        const int j0 = tid * RUN;
+        if (j0 >= n_valid)
+            continue;
+        const unsigned char *lut_lane = lut + 4 * (tid & (E1C_LUT_REP - 1));
+        int acc[NH * E1C_MAX_RUN] = {0};
+        for (int a = 0; a < nact; a++) {
+            uint32_t rc;
+            if ((par[a].misc & E1_PAR_CLEAN) && (par[a].misc & E1_PAR_SLOW)) { // (tiles that are not SLOW take the out-of-line form, tracking on)
+                // what the kernel does, and beside it the tracking loop: it must not flag anything and must add the same terms
+                int a0[NH * E1C_MAX_RUN] = {0}, a1[NH * E1C_MAX_RUN] = {0};
+                rc = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, a0, thr_carr, lim_code, 0, 1u);
+                const uint32_t rc1 = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, a1, thr_carr, lim_code, 1, 1u);
+                if (rc1 || rc || memcmp(a0, a1, sizeof a0))
+                    g_clean_violations++;
+                for (int i = 0; i < RUN; i++)
+                    acc[i] += a0[i];
+            } else
+                rc = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, acc, thr_carr, lim_code, 1, 1u);
+            if (par[a].misc & E1_PAR_SLOW)
+                g_cw_pairs++;
+            if (rc) { // e1_cw_rest
+                int d[NH * E1C_MAX_RUN];
+                e1_cw_rest_impl<NH>(&par[a], codes, lut_lane, j0, d, rc, thr_carr, thr_code, tc_carr, tc_code, &stats[0], &stats[2]);
+                for (int i = 0; i < RUN; i++)
+                    acc[i] += d[i];
+            }
+        }
+        for (int i = 0; i < RUN; i++)
+            if (j0 + i < n_valid) {
+                uint32_t w = e1_pack_iq(acc[i]);
+                o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
+                o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
+            }
+    }
+}
+extern "C" {
 
 // Whole pipeline on the host.  lut: int32[642][32] in the product layout (passed in by the test
 // from the oracle's tables so this file holds no second copy of them).
@@ -104,6 +153,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                       int16_t *out, int groups, int amb_scale, const int32_t *lut, unsigned long long *stats, int planner)
 {
     const double delt = 1.0 / fs_hz;
+    e1_lut_base = (const unsigned char *)lut;
     const int threads = E1C_THREADS, run = 4 * groups, tile = threads * run;
     const int tpe = (n_samp + tile - 1) / tile;
     std::vector<uint32_t> codes(E1C_N_PRN * E1C_CODE_WORDS_PER_PRN);
@@ -185,7 +235,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                         g_max_ab = units;
                 }
                 if (run == E1C_MAX_RUN) { // e1_clean_kernel
-                    if (e1_par_clean(&par[nact], tile, tc_carr, lim_carr, lim_code, thr_code)) {
+                    if (e1_par_clean(&par[nact], tile, tc_carr, lim_carr, lim_code, thr_code, g_cw_nh * E1C_MAX_RUN)) {
                         par[nact].misc |= E1_PAR_CLEAN;
                         g_clean_tiles++;
                     } else
@@ -217,45 +267,11 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                 }
                 continue;
             }
-            if (run == E1C_MAX_RUN) { // e1_synth_pair_kernel: 256 threads per tile, two runs of 16 samples each
-                for (int tid = 0; tid < threads / 2; tid++) {
-                    const int j0 = tid * 2 * run;
-                    if (j0 >= n_valid)
-                        continue;
-                    const unsigned char *lut_lane = (const unsigned char *)lut + 4 * (tid & (E1C_LUT_REP - 1));
-                    int acc[2 * E1C_MAX_RUN] = {0};
-                    for (int a = 0; a < nact; a++) {
-                        uint32_t rc;
-                        if (par[a].misc & E1_PAR_CLEAN) {
-                            // what the kernel does, and beside it the tracking loop: it must not flag anything
-                            // and must add the same terms
-                            int a0[2 * E1C_MAX_RUN] = {0}, a1[2 * E1C_MAX_RUN] = {0};
-                            rc = e1_run_fast_pair<false>(&par[a], codes.data(), lut_lane, j0, a0, tc_carr, lim_carr, lim_code);
-                            const uint32_t rc1 = e1_run_fast_pair<true>(&par[a], codes.data(), lut_lane, j0, a1, tc_carr, lim_carr, lim_code);
-                            if (rc1 || rc || memcmp(a0, a1, sizeof a0))
-                                g_clean_violations++;
-                            for (int i = 0; i < 2 * run; i++)
-                                acc[i] += a0[i];
-                        } else
-                            rc = e1_run_fast_pair<true>(&par[a], codes.data(), lut_lane, j0, acc, tc_carr, lim_carr, lim_code);
-                        for (int h = 0; h < 2; h++) {
-                            if (!((rc >> (2 * h)) & 3u))
-                                continue;
-                            stats[2]++; // e1_fix_run
-                            int tt[E1C_MAX_RUN] = {0}, g[E1C_MAX_RUN];
-                            e1_run_fast<16>(&par[a], codes.data(), lut_lane, j0 + h * run, tt, tc_carr, lim_carr, lim_code);
-                            e1_channel_run(&par[a], codes.data(), lut_lane, j0 + h * run, run, g, thr_carr, thr_code, e1_bias_h(tc_code), &stats[0]);
-                            for (int i = 0; i < run; i++)
-                                acc[h * run + i] += g[i] - tt[i];
-                        }
-                    }
-                    for (int i = 0; i < 2 * run; i++)
-                        if (j0 + i < n_valid) {
-                            uint32_t w = e1_pack_iq(acc[i]);
-                            o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
-                            o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
-                        }
-                }
+            if (run == E1C_MAX_RUN) { // e1_synth_cw_kernel<NH, TEAMS>: 8192 / (16 NH) threads per tile, NH runs of 16 samples each
+                if (g_cw_nh == 4)
+                    cw_tile<4>(par.data(), nact, codes.data(), (const unsigned char *)lut, n_valid, o, thr_carr, thr_code, tc_carr, tc_code, lim_code, stats);
+                else
+                    cw_tile<2>(par.data(), nact, codes.data(), (const unsigned char *)lut, n_valid, o, thr_carr, thr_code, tc_carr, tc_code, lim_code, stats);
                 continue;
             }
             for (int tid = 0; tid < threads; tid++) { // e1_synth_kernel, one thread
