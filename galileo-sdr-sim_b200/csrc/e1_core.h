@@ -1786,35 +1786,34 @@ E1_HD uint32_t e1_run_cw(const e1_chan_par *p, e1_sptr codes_s, e1_sptr lut_s, i
     return CHECK ? (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code) : 0u;
 }
 
-/* One channel's contribution to the NH R samples of a thread.  E1_PAR_SLOW tiles -- all of them at the Dopplers of a
- * terrestrial receiver -- are walked by carries, inline (four instances: tracking on / off, position up / down).
- * Returns 0 when the terms are in acc and final; E1_RC_CW when they are in acc but some sample is ambiguous;
- * E1_RC_OLD when nothing was added because the tile is not E1_PAR_SLOW (fast carrier, forced generic form, zero
- * crossing): the caller then takes the out-of-line path (e1_cw_rest_impl), which keeps the common loop small. */
-#define E1_RC_CW 16u
+/* One channel's contribution to the NH R samples of a thread: the INLINE part.  Tiles that are E1_PAR_SLOW and
+ * E1_PAR_CLEAN -- 99 % of them at the Dopplers of a terrestrial receiver -- are walked by carries without tracking
+ * (two instances: position up / down), their terms go to acc and are final: returns 0.  Everything else returns a
+ * code for the out-of-line part (e1_cw_rest_impl) and adds nothing, which keeps the hot loop's code small:
+ *   E1_RC_CHECK  E1_PAR_SLOW tile with a sample near an index boundary: the same walk with the tracking on
+ *   E1_RC_OLD    not E1_PAR_SLOW (fast carrier, forced generic form, zero crossing): runs of R in the 64-bit form */
+#define E1_RC_CHECK 16u
 #define E1_RC_OLD 32u
 template <int NH>
 E1_HD uint32_t e1_cw_add(const e1_chan_par *p, e1_sptr codes_s, e1_sptr lut_s, int j0, int *acc, uint32_t thr_carr, uint32_t lim_code,
-                         int check, uint32_t one)
+                         uint32_t one)
 {
     const uint32_t misc = p->misc;
-    if (!(misc & E1_PAR_SLOW))
-        return E1_RC_OLD;
+    if ((misc & (E1_PAR_SLOW | E1_PAR_CLEAN)) != (E1_PAR_SLOW | E1_PAR_CLEAN))
+        return (misc & E1_PAR_SLOW) ? E1_RC_CHECK : E1_RC_OLD;
     const uint32_t tc = e1_tc_carr_cw(thr_carr, NH * E1C_MAX_RUN), lim = e1_lim_carr_cw(thr_carr, NH * E1C_MAX_RUN);
-    uint32_t rc;
-    if (check)
-        rc = (misc & E1_PAR_DOWN) ? e1_run_cw<NH, true, true>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one)
-                                  : e1_run_cw<NH, true, false>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one);
+    if (misc & E1_PAR_DOWN)
+        e1_run_cw<NH, false, true>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one);
     else
-        rc = (misc & E1_PAR_DOWN) ? e1_run_cw<NH, false, true>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one)
-                                  : e1_run_cw<NH, false, false>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one);
-    return rc ? E1_RC_CW : 0u;
+        e1_run_cw<NH, false, false>(p, codes_s, lut_s, j0, acc, tc, lim, lim_code, one);
+    return 0u;
 }
 
-/* The out-of-line rest: d[0 .. NH R) receives what has to be ADDED to the accumulators.
- *   E1_RC_CW   the generic form of all NH R samples minus the carry-walk's terms (recomputed: same integers)
- *   E1_RC_OLD  the samples as runs of R in the 64-bit-position form (e1_run_fast, tracking on), each flagged or
- *              unhandled run replaced by the generic form                                                      */
+/* The out-of-line part: d[0 .. NH R) receives what has to be ADDED to the accumulators.
+ *   E1_RC_CHECK  the carry walk with the tracking on; if it flags a sample, the generic form of all NH R samples
+ *   E1_RC_OLD    the samples as runs of R in the 64-bit-position form (e1_run_fast, tracking on), each flagged or
+ *                unhandled run replaced by the generic form
+ * check_clean (host test build): a tile marked clean is walked with the tracking on as well and must not be flagged. */
 template <int NH>
 E1_HD void e1_cw_rest_impl(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *d, uint32_t rc,
                            uint32_t thr_carr, uint32_t thr_code, uint32_t tc_carr, uint32_t tc_code, unsigned long long *n_exact,
@@ -1822,20 +1821,19 @@ E1_HD void e1_cw_rest_impl(const e1_chan_par *p, const uint32_t *codes, const un
 {
     const int R = E1C_MAX_RUN;
     const uint32_t lim_carr = e1_lim_carr(tc_carr, thr_carr), lim_code = e1_lim_code(tc_code, thr_code);
-    if (rc == E1_RC_CW) {
-        int t[NH * E1C_MAX_RUN];
-        for (int i = 0; i < NH * R; i++)
-            t[i] = 0;
-        e1_cw_add<NH>(p, e1_sp(codes), e1_sp(lut_lane), j0, t, thr_carr, lim_code, 0, 1u);
-        e1_channel_run(p, codes, lut_lane, j0, NH * R, d, thr_carr, thr_code, e1_bias_h(tc_code), n_exact);
-        for (int i = 0; i < NH * R; i++)
-            d[i] -= t[i];
-        if (n_slow)
-            (*n_slow)++;
-        return;
-    }
     for (int i = 0; i < NH * R; i++)
         d[i] = 0;
+    if (rc == E1_RC_CHECK) {
+        const uint32_t tc = e1_tc_carr_cw(thr_carr, NH * R), lim = e1_lim_carr_cw(thr_carr, NH * R);
+        const uint32_t flagged = (p->misc & E1_PAR_DOWN) ? e1_run_cw<NH, true, true>(p, e1_sp(codes), e1_sp(lut_lane), j0, d, tc, lim, lim_code, 1u)
+                                                         : e1_run_cw<NH, true, false>(p, e1_sp(codes), e1_sp(lut_lane), j0, d, tc, lim, lim_code, 1u);
+        if (flagged) { /* the walk's terms are dropped: the generic form decides every sample */
+            e1_channel_run(p, codes, lut_lane, j0, NH * R, d, thr_carr, thr_code, e1_bias_h(tc_code), n_exact);
+            if (n_slow)
+                (*n_slow)++;
+        }
+        return;
+    }
     for (int h = 0; h < NH; h++) {
         const uint32_t rc2 = e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0 + h * R, d + h * R, tc_carr, lim_carr, lim_code);
         if (rc2) {

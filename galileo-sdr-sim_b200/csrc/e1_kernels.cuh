@@ -918,9 +918,9 @@ __global__ void __launch_bounds__(TEAMS *E1_CW_TEAM_THREADS(NH), 1) e1_synth_cw_
             for (int i = 0; i < RUN; i++)
                 acc[i] = 0;
             for (int a = 0; a < nact; a++) {
-                const uint32_t rc = e1_cw_add<NH>(&par[a], codes_s, lut_s, j0, acc, A.thr_carr, lim_code, !(par[a].misc & E1_PAR_CLEAN), one);
-                if (rc) { /* rare: this (thread, channel) goes through the generic form; the correction comes back in an array of
-                             its own so that the accumulators never have to live in local memory */
+                const uint32_t rc = e1_cw_add<NH>(&par[a], codes_s, lut_s, j0, acc, A.thr_carr, lim_code, one);
+                if (rc) { /* 1 % of the tiles: the out-of-line forms (tracking on / 64-bit positions / generic); their terms come back
+                             in an array of their own so that the accumulators never have to live in local memory */
                     int d[RUN];
                     e1_cw_rest<NH>(&par[a], codes_s, lut_s, j0, d, rc, A.thr_carr, A.thr_code, A.tc_carr, A.tc_code, &n_exact);
 #pragma unroll

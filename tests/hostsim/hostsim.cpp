@@ -99,21 +99,18 @@ static void cw_tile(const e1_chan_par *par, int nact, const uint32_t *codes, con
         const unsigned char *lut_lane = lut + 4 * (tid & (E1C_LUT_REP - 1));
         int acc[NH * E1C_MAX_RUN] = {0};
         for (int a = 0; a < nact; a++) {
-            uint32_t rc;
-            if ((par[a].misc & E1_PAR_CLEAN) && (par[a].misc & E1_PAR_SLOW)) { // (tiles that are not SLOW take the out-of-line form, tracking on)
-                // what the kernel does, and beside it the tracking loop: it must not flag anything and must add the same terms
-                int a0[NH * E1C_MAX_RUN] = {0}, a1[NH * E1C_MAX_RUN] = {0};
-                rc = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, a0, thr_carr, lim_code, 0, 1u);
-                const uint32_t rc1 = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, a1, thr_carr, lim_code, 1, 1u);
-                if (rc1 || rc || memcmp(a0, a1, sizeof a0))
-                    g_clean_violations++;
-                for (int i = 0; i < RUN; i++)
-                    acc[i] += a0[i];
-            } else
-                rc = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, acc, thr_carr, lim_code, 1, 1u);
+            const uint32_t rc = e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, acc, thr_carr, lim_code, 1u);
             if (par[a].misc & E1_PAR_SLOW)
                 g_cw_pairs++;
-            if (rc) { // e1_cw_rest
+            if (!rc) { // a tile marked clean went through the walk without tracking: beside it, the tracking walk --
+                       // it must not flag anything and must add the same terms
+                int a1[NH * E1C_MAX_RUN], a0[NH * E1C_MAX_RUN] = {0};
+                unsigned long long dummy[2] = {0, 0};
+                e1_cw_rest_impl<NH>(&par[a], codes, lut_lane, j0, a1, E1_RC_CHECK, thr_carr, thr_code, tc_carr, tc_code, &dummy[0], &dummy[1]);
+                e1_cw_add<NH>(&par[a], e1_sp(codes), e1_sp(lut_lane), j0, a0, thr_carr, lim_code, 1u);
+                if (dummy[1] || memcmp(a0, a1, sizeof a0))
+                    g_clean_violations++;
+            } else { // e1_cw_rest
                 int d[NH * E1C_MAX_RUN];
                 e1_cw_rest_impl<NH>(&par[a], codes, lut_lane, j0, d, rc, thr_carr, thr_code, tc_carr, tc_code, &stats[0], &stats[2]);
                 for (int i = 0; i < RUN; i++)
