@@ -486,8 +486,121 @@ def main():
         barrier()
         e2e = {"value": world * samples_per_step / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": rec_bytes, "d2h_bytes_per_step": out_bytes,
-               "api": ("e1b200_synth_ranges" if use_ranges else "e1b200_synth_epochs") + " (host buffers, pinned), timed on the host clock around the call"}
+               "api": ("e1b200_synth_ranges" if use_ranges else "e1b200_synth_epochs") + " (host buffers, pinned), timed on the host clock around the call",
+               "bound": f"PCIe D2H: {out_bytes / 1e9:.2f} GB per step leave the GPU at {out_bytes / (e2e_ms * 1e-3) / 1e9:.1f} GB/s (plain pinned copies on these boxes: "
+                        "55 GB/s for one GPU, 118 GB/s for all eight together: profiles/r1_d2h_diag_8gpu.txt); the kernels take a quarter of the call"}
         h_recs.free(), h_out.free()
+
+    # ---- strong-scaling arm (N > 1): ONE scenario of this size, time axis sharded over the N GPUs ----------------
+    # rank 0's scenario (seed 1000) split into contiguous block ranges (shard.split_epochs).  Per step, timed:
+    #   hand-off  every rank runs the carrier planner over all blocks BEFORE its range (shard.replan_start_phases: no
+    #             communication, no serial chain; the alternative, a plan-and-send chain over NCCL, is timed as handoff_chain_ms)
+    #   synthesis of the rank's range, its kernel storing straight into rank 0's stream buffer over NVLink (peer memory,
+    #             e1b200_peer_*): compute and gather are one kernel, there is no gather step
+    #   (for comparison) the same with a local buffer and an NCCL point-to-point gather of the device-resident segments
+    # The stream that ends up in rank 0's HBM must equal rank 0's own single-GPU stream.
+    strong = None
+    if dist is not None and not use_ranges:
+        import shard as S
+        recs_all = recs if rank == 0 else U.synthetic_recs_fast(n_epochs, n_chan, fs, seed=1000)
+        ranges = S.split_epochs(n_epochs, world)
+        lo, hi = ranges[rank]
+        d_seg_recs = torch.from_numpy(np.ascontiguousarray(recs_all[lo:hi]).view(np.uint8).reshape(-1)).to(dev)
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        full = None
+        if rank == 0:
+            full = E.PeerBuffer.alloc(local_rank, out_bytes)
+            handle.copy_(torch.frombuffer(bytearray(full.handle), dtype=torch.uint8))
+        dist.broadcast(handle, 0)
+        if rank != 0:
+            full = E.PeerBuffer.open(local_rank, bytes(handle.cpu().numpy().tobytes()), out_bytes)
+        seg_engine = E.Synth(fs, n_samp, n_chan, device=local_rank)
+        d_seg = torch.empty((hi - lo) * n_samp, dtype=torch.int32, device=dev)          # NCCL variant: one (I, Q) pair = one int32
+        d_full = torch.empty(n_epochs * n_samp, dtype=torch.int32, device=dev) if rank == 0 else None
+
+        h_seg_recs = E.PinnedBuffer(max(recs_all[lo:hi].nbytes, 1))
+        h_seg_recs.u8[:recs_all[lo:hi].nbytes] = np.ascontiguousarray(recs_all[lo:hi]).view(np.uint8).reshape(-1)
+        seg_recs_view = h_seg_recs.view(U.REC_DTYPE)[: (hi - lo) * n_chan].reshape(hi - lo, n_chan)
+
+        def strong_step(fused, chain=False):
+            t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            t[0].record()
+            if chain:
+                S.handoff_start_phases(seg_engine, recs_all, rank, world, dist, dist_device=dev)
+            else:
+                S.replan_start_phases(seg_engine, recs_all, rank, world)
+            t[1].record()
+            if fused == "dma":       # slices by the copy engines over NVLink, behind the kernels (records from pinned host memory)
+                seg_engine.synth_epochs_to(seg_recs_view, full.ptr + lo * n_samp * 4)
+            elif fused:              # the kernel's own stores cross NVLink
+                seg_engine.synth_epochs_device(hi - lo, d_seg_recs.data_ptr(), full.ptr + lo * n_samp * 4)
+                seg_engine.sync()
+            else:
+                seg_engine.synth_epochs_device(hi - lo, d_seg_recs.data_ptr(), d_seg.data_ptr())
+                seg_engine.sync()
+            t[2].record()
+            if fused:
+                dist.barrier()                   # every rank's stores have landed in rank 0's buffer
+            else:
+                S.gather_segments_device(d_seg, rank, world, dist, n_epochs, n_samp, d_full)
+            t[3].record()
+            torch.cuda.synchronize()
+            return [t[i].elapsed_time(t[i + 1]) for i in range(3)]
+
+        def timed(fused, chain=False):
+            for _ in range(max(args.warmup, 1)):
+                strong_step(fused, chain)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            parts = np.zeros(3)
+            for _ in range(args.steps):
+                parts += np.array(strong_step(fused, chain))
+            s1.record()
+            barrier()
+            return max_over_ranks(s0.elapsed_time(s1)) / args.steps, [max_over_ranks(float(v)) / args.steps for v in parts]
+
+        ms_d, parts_d = timed("dma")
+        equal_d = None
+        if rank == 0:
+            import ctypes as C
+            got = torch.empty(n_epochs * n_samp, dtype=torch.int32, device=dev)
+            C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(got.data_ptr()), C.c_void_p(full.ptr), C.c_size_t(out_bytes), 3)   # device to device
+            equal_d = bool(torch.equal(got, d_out.view(torch.int32)))
+            C.CDLL("libcudart.so").cudaMemset(C.c_void_p(full.ptr), 0, C.c_size_t(out_bytes))
+            del got
+        ms_f, parts_f = timed(True)
+        equal = None
+        if rank == 0:
+            got = torch.empty(n_epochs * n_samp, dtype=torch.int32, device=dev)
+            import ctypes as C
+            C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(got.data_ptr()), C.c_void_p(full.ptr), C.c_size_t(out_bytes), 3)   # device to device
+            equal = bool(torch.equal(got, d_out.view(torch.int32)))
+            del got
+        ms_n, parts_n = timed(False)
+        equal_n = bool(torch.equal(d_full, d_out.view(torch.int32))) if rank == 0 else None
+        ms_c, parts_c = timed(True, chain=True)
+        strong = {"scaling": "strong", "value": samples_per_step / (ms_d * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_d,
+                  "handoff_ms": parts_d[0], "synth_and_gather_ms": parts_d[1], "barrier_ms": parts_d[2],
+                  "what": f"ONE scenario ({n_epochs} blocks) split into {world} contiguous block ranges: every rank plans the carrier over the "
+                          "blocks before its range (no communication), then synthesises its range through e1b200_synth_epochs with rank 0's "
+                          "stream buffer (peer memory, e1b200_peer_*) as destination: every finished 96 MB slice travels over NVLink by the "
+                          "copy engines while the SMs synthesise the next one -- no collective, no gather step after the kernels; "
+                          "CUDA events, max over ranks",
+                  "stream_in_rank0_hbm_equals_single_gpu_stream": equal_d,
+                  "kernel_stores_variant": {"value": samples_per_step / (ms_f * 1e-3) / 1e6, "ms_per_step": ms_f, "handoff_ms": parts_f[0],
+                                            "synth_ms": parts_f[1], "equals_single_gpu_stream": equal,
+                                            "what": "the synthesis kernel's own 128-bit stores go to rank 0's buffer over NVLink (fused compute + gather)"},
+                  "nccl_gather_variant": {"value": samples_per_step / (ms_n * 1e-3) / 1e6, "ms_per_step": ms_n, "handoff_ms": parts_n[0],
+                                          "synth_ms": parts_n[1], "gather_ms": parts_n[2], "equals_single_gpu_stream": equal_n,
+                                          "what": "local segment buffers + NCCL isend/irecv of the device-resident segments into rank 0's HBM"},
+                  "handoff_chain_variant": {"ms_per_step": ms_c, "handoff_chain_ms": parts_c[0],
+                                            "what": "plan-and-send chain (carrier planner on the own range, phases to the next rank over NCCL) instead of re-planning"}}
+        seg_engine.close()
+        barrier()
+        full.close()
+        h_seg_recs.free()
+        del d_seg, d_full, d_seg_recs
 
     # ---- the timed bytes against the oracle (after both timed regions) ---------------------
     parity = None
@@ -528,7 +641,7 @@ def main():
                        "host_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "kernel": "e1_synth_pair_kernel", "peak_source": peak_src,
+                         "kernel": "e1_synth_cw_kernel<4,3>", "peak_source": peak_src,
                          "ms_per_launch": per_launch_ms, "launches_per_step": synth_launches / args.steps,
                          "planner_ms_per_step": plan_ms / args.steps, "synth_ms_per_step": synth_ms / args.steps,
                          "note": f"issue-bound, not HBM-bound: {n_chan} channel visits x ~{(issue or {}).get('inst_per_channel_sample', 12.3):.1f} integer instructions per 4-byte sample "
@@ -543,6 +656,8 @@ def main():
         if e2e:
             line["e2e"] = e2e
         line["parity_check"] = parity
+        if strong:
+            line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
             unbind_cpus()
             ref = reference_binary_cfg1() if args.workload == "cfg1" else None

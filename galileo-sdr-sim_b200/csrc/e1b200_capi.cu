@@ -303,6 +303,30 @@ int e1b200_get_carrier_phase(e1b200_ctx *ctx, int slot, double *out)
     return E1B200_OK;
 }
 
+/* all slots at once (a time-axis shard's hand-off: one copy instead of max_chan round trips) */
+int e1b200_get_carrier_phases(e1b200_ctx *ctx, int n, double *out)
+{
+    if (!ctx || !out || n < 1 || n > ctx->cfg.max_chan)
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaMemcpyAsync(out, ctx->d_phase, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return E1B200_OK;
+}
+
+int e1b200_set_carrier_phases(e1b200_ctx *ctx, int n, const double *phases)
+{
+    if (!ctx || !phases || n < 1 || n > ctx->cfg.max_chan)
+        return E1B200_EINVAL;
+    for (int i = 0; i < n; i++)
+        if (!(fabs(phases[i]) < 1.0))
+            return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaMemcpyAsync(ctx->d_phase, phases, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return E1B200_OK;
+}
+
 static int ensure_plan_scratch(e1b200_ctx *ctx)
 {
     if (ctx->d_ck)
@@ -638,8 +662,11 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
                 CK(cudaEventCreate(&t1));
                 CK(cudaEventRecord(t0, ctx->copy_stream));
             }
+            /* cudaMemcpyDefault: `out` is normally the caller's (pinned) host buffer -- a D2H over PCIe -- but may as well be
+               device memory of this or of a PEER GPU (e1b200_peer_open): then the copy engines carry the slice over NVLink
+               while the SMs synthesise the next one (time-axis shards: the gather without a collective) */
             CK(cudaMemcpyAsync(out + (size_t)(p0 + e0) * epoch_i16, d_slot, (size_t)n * epoch_i16 * 2,
-                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+                               cudaMemcpyDefault, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
             if (trace) {
                 CK(cudaEventRecord(t1, ctx->copy_stream));
@@ -701,6 +728,24 @@ int e1b200_plan_phases(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs)
         CK(cudaStreamSynchronize(ctx->stream)); /* recs may be pageable: the copy must be done before the caller reuses it */
     }
     return e1b200_sync(ctx);
+}
+
+/* the same from records that are already on the device; asynchronous like the other *_device entry points */
+int e1b200_plan_phases_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *d_recs)
+{
+    if (!ctx || n_epochs < 0 || (n_epochs && !d_recs))
+        return E1B200_EINVAL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_plan_scratch(ctx);
+    if (rc)
+        return rc;
+    reset_call(ctx);
+    for (int p0 = 0; p0 < n_epochs; p0 += ctx->plan_epochs) {
+        const int np = n_epochs - p0 < ctx->plan_epochs ? n_epochs - p0 : ctx->plan_epochs;
+        if ((rc = enqueue_plan(ctx, np, d_recs + (size_t)p0 * ctx->cfg.max_chan, 1)))
+            return rc;
+    }
+    return E1B200_OK;
 }
 
 int e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *d_rr, int16_t *d_out)
@@ -843,6 +888,44 @@ int e1b200_selftest_any_hit(int device, int n_cases, const int64_t *cases, int32
 }
 
 void *e1b200_stream(e1b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+/* ---- time-axis shards on several GPUs of a node: the gather without a collective ---------------------------------
+ * The writer rank allocates the whole stream's buffer in its HBM and exports it; every other rank (one process per
+ * GPU) opens the handle and passes `its pointer + its segment's offset` as d_out to e1b200_synth_*_device: the
+ * synthesis kernel's own 128-bit stores then travel over NVLink straight into the writer's memory, tile by tile,
+ * while the kernel computes -- no staging copy, no separate gather step.  (CUDA IPC; the devices must be peers.) */
+int e1b200_peer_alloc(int device, size_t bytes, void **d_ptr, unsigned char handle[E1B200_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == E1B200_IPC_HANDLE_BYTES, "handle size");
+    if (!d_ptr || !handle || !bytes)
+        return E1B200_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess)
+        return E1B200_ENODEV;
+    if (cudaMalloc(d_ptr, bytes) != cudaSuccess)
+        return E1B200_ENOMEM;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, *d_ptr) != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return E1B200_ECUDA;
+    }
+    memcpy(handle, &h, sizeof h);
+    return E1B200_OK;
+}
+
+int e1b200_peer_open(int device, const unsigned char handle[E1B200_IPC_HANDLE_BYTES], void **d_ptr)
+{
+    if (!d_ptr || !handle)
+        return E1B200_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess)
+        return E1B200_ENODEV;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    return cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? E1B200_OK : E1B200_ECUDA;
+}
+
+int e1b200_peer_close(void *d_ptr) { return cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? E1B200_OK : E1B200_ECUDA; }
+int e1b200_peer_free(void *d_ptr) { return cudaFree(d_ptr) == cudaSuccess ? E1B200_OK : E1B200_ECUDA; }
 
 int e1b200_host_alloc(void **p, size_t bytes)
 {

@@ -54,6 +54,8 @@ SYMBOLS = [
     "e1b200_restate", "e1b200_get_timing", "e1b200_get_stats", "e1b200_stream", "e1b200_last_error",
     "e1b200_version", "e1b200_host_alloc", "e1b200_host_free", "e1b200_selftest_any_hit",
     "e1b200_code_wraps", "e1b200_host_register", "e1b200_host_unregister",
+    "e1b200_get_carrier_phases", "e1b200_set_carrier_phases", "e1b200_plan_phases_device",
+    "e1b200_peer_alloc", "e1b200_peer_open", "e1b200_peer_close", "e1b200_peer_free",
 ]
 
 _lib = None
@@ -95,6 +97,13 @@ def load():
     lib.e1b200_host_free.argtypes = [vp]
     lib.e1b200_selftest_any_hit.argtypes = [C.c_int, C.c_int, vp, vp]
     lib.e1b200_code_wraps.argtypes = [C.c_double, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32)]
+    lib.e1b200_get_carrier_phases.argtypes = [vp, C.c_int, dp]
+    lib.e1b200_set_carrier_phases.argtypes = [vp, C.c_int, dp]
+    lib.e1b200_plan_phases_device.argtypes = [vp, C.c_int, vp]
+    lib.e1b200_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.e1b200_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    lib.e1b200_peer_close.argtypes = [vp]
+    lib.e1b200_peer_free.argtypes = [vp]
     lib.e1b200_host_register.argtypes = [vp, C.c_size_t]
     lib.e1b200_host_unregister.argtypes = [vp]
     _lib = lib
@@ -197,11 +206,17 @@ class Synth:
         return v.value
 
     def carrier_phases(self):
-        return np.array([self.get_carrier_phase(s) for s in range(self.max_chan)])
+        out = np.zeros(self.max_chan)
+        self._check(self._lib.e1b200_get_carrier_phases(self._h, self.max_chan, out.ctypes.data_as(C.POINTER(C.c_double))), "get_carrier_phases")
+        return out
 
     def set_carrier_phases(self, phases):
-        for slot, ph in enumerate(np.asarray(phases, dtype=np.float64)[: self.max_chan]):
-            self.set_carrier_phase(slot, float(ph))
+        ph = np.ascontiguousarray(np.asarray(phases, dtype=np.float64)[: self.max_chan])
+        self._check(self._lib.e1b200_set_carrier_phases(self._h, len(ph), ph.ctypes.data_as(C.POINTER(C.c_double))), "set_carrier_phases")
+
+    def plan_phases_device(self, n_epochs, d_recs_ptr):
+        """Carrier planner only, records on the device; asynchronous (sync() waits)."""
+        self._check(self._lib.e1b200_plan_phases_device(self._h, n_epochs, d_recs_ptr), "plan_phases_device")
 
     def plan_phases(self, recs):
         """Advance the carrier phases over recs [n_epochs, max_chan] without synthesising (shard hand-off)."""
@@ -209,6 +224,13 @@ class Synth:
         assert recs.ndim == 2 and recs.shape[1] == self.max_chan, recs.shape
         self._check(self._lib.e1b200_plan_phases(self._h, recs.shape[0], recs.ctypes.data), "plan_phases")
         return self.carrier_phases()
+
+    def synth_epochs_to(self, recs, out_ptr):
+        """e1b200_synth_epochs with a raw destination pointer: host memory, or device memory of this GPU or of a peer
+        (PeerBuffer): the finished slices are copied there by the copy engines behind the kernels."""
+        recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        assert recs.ndim == 2 and recs.shape[1] == self.max_chan, recs.shape
+        self._check(self._lib.e1b200_synth_epochs(self._h, recs.shape[0], recs.ctypes.data, out_ptr), "synth_epochs")
 
     def _host_call(self, fn, recs, dtype, out):
         recs = np.ascontiguousarray(recs, dtype=dtype)
@@ -248,3 +270,33 @@ class Synth:
         s = Stats()
         self._check(self._lib.e1b200_get_stats(self._h, C.byref(s)), "get_stats")
         return s
+
+
+class PeerBuffer:
+    """The writer rank's stream buffer in HBM, shared with the other ranks of the node (e1b200_peer_*): rank 0
+    PeerBuffer.alloc()s and ships .handle (64 bytes); the others PeerBuffer.open() it.  .ptr is a device pointer valid
+    in this process; synthesis kernels store straight into it over NVLink."""
+
+    def __init__(self, ptr, handle, owner, nbytes):
+        self.ptr, self.handle, self.owner, self.nbytes = ptr, handle, owner, nbytes
+
+    @classmethod
+    def alloc(cls, device, nbytes):
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        rc = load().e1b200_peer_alloc(device, nbytes, C.byref(p), h)
+        if rc:
+            raise E1B200Error(f"e1b200_peer_alloc: {rc}")
+        return cls(p.value, h.raw, True, nbytes)
+
+    @classmethod
+    def open(cls, device, handle, nbytes):
+        p = C.c_void_p()
+        rc = load().e1b200_peer_open(device, bytes(handle), C.byref(p))
+        if rc:
+            raise E1B200Error(f"e1b200_peer_open: {rc} (are the GPUs peers?)")
+        return cls(p.value, bytes(handle), False, nbytes)
+
+    def close(self):
+        if self.ptr:
+            (load().e1b200_peer_free if self.owner else load().e1b200_peer_close)(self.ptr)
+            self.ptr = None

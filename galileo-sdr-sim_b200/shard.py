@@ -15,8 +15,10 @@ Output segments are contiguous byte ranges of the reference's headerless ishort 
 (src/galileo-sdr.cpp:536-542): sample k of block b sits at byte 4*(b*N + k).  Two sinks:
   write_segment()   every rank pwrite()s its own range -- no collective, each GPU uses its own
                     PCIe link (the default; the per-GPU stream is a few GB/s, far below NVLink)
-  gather_segments() the north star's single-writer variant: segments travel to rank 0 through
-                    torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests)
+  gather_segments_device()  the north star's single-writer variant: the device-resident segments travel to
+                    rank 0's HBM over NCCL (NVLink) point-to-point, all transfers posted at once; rank 0 then
+                    holds the whole stream on the device (one D2H, or none)
+  gather_segments() the same through host arrays (gloo in the CPU tests; no GPU path uses it)
 
 `engine` is anything with set_carrier_phases / plan_phases / synth_epochs / carrier_phases and
 max_chan: the product passes e1b200.Synth (CUDA, no CPU fallback); the GPU-less tests pass a stub
@@ -65,6 +67,19 @@ def handoff_start_phases(engine, recs, rank, world, dist=None, phases0=None, dis
     return lo, hi, start
 
 
+def replan_start_phases(engine, recs, rank, world, phases0=None):
+    """The hand-off without a chain: every rank runs the carrier planner over ALL blocks before its range, in
+    parallel with the others -- redundant work (rank r plans lo_r blocks, the last rank nearly the whole scenario,
+    ~1 us per channel-block) instead of world - 1 serial plan-and-send hops, each with the fixed cost of a planner
+    pass.  No communication.  Returns (lo, hi, start_phases); the engine holds start_phases."""
+    lo, hi = split_epochs(recs.shape[0], world)[rank]
+    start = np.zeros(engine.max_chan) if phases0 is None else np.asarray(phases0, dtype=np.float64).copy()
+    engine.set_carrier_phases(start)
+    if lo > 0:
+        start = engine.plan_phases(recs[:lo])
+    return lo, hi, start
+
+
 def synth_shard(engine, recs, rank, world, dist=None, phases0=None, dist_device="cpu", out=None):
     """This rank's segment of the scenario: (lo, hi, int16 [ (hi-lo)*N, 2 ])."""
     lo, hi, _ = handoff_start_phases(engine, recs, rank, world, dist, phases0, dist_device)
@@ -107,3 +122,29 @@ def gather_segments(seg, rank, world, dist, n_epochs, n_samp, dist_device="cpu")
         dist.recv(t, src=r)
         out[lo * n_samp:hi * n_samp] = t.cpu().numpy().view(np.int16).reshape(-1, 2)
     return out
+
+
+def gather_segments_device(d_seg, rank, world, dist, n_epochs, n_samp, d_full=None):
+    """Device-resident gather over NCCL: d_seg is this rank's segment as a 1-D int32 CUDA tensor (one (I, Q) pair
+    per element: NCCL has no int16), d_full rank 0's receive buffer of n_epochs * n_samp int32 (allocated if
+    None).  Every rank's isend / rank 0's irecvs are posted in one batch, so the N - 1 transfers share NVLink
+    instead of queueing behind each other.  Returns d_full on rank 0, None elsewhere."""
+    import torch
+    ranges = split_epochs(n_epochs, world)
+    ops = []
+    if rank == 0:
+        if d_full is None:
+            d_full = torch.empty(n_epochs * n_samp, dtype=torch.int32, device=d_seg.device)
+        lo, hi = ranges[0]
+        d_full[lo * n_samp:hi * n_samp].copy_(d_seg[: (hi - lo) * n_samp])
+        for r in range(1, world):
+            lo, hi = ranges[r]
+            if hi > lo:
+                ops.append(dist.P2POp(dist.irecv, d_full[lo * n_samp:hi * n_samp], r))
+    else:
+        lo, hi = ranges[rank]
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, d_seg[: (hi - lo) * n_samp], 0))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    return d_full if rank == 0 else None

@@ -21,6 +21,8 @@
  *   `code_phase -= 4092; ibit++` count of a block, i.e.     e1b200_code_wraps
  *     whether the in-loop generateINavMsg ran (:491-506)
  *   calloc'd iq_buff (:326)                                 e1b200_host_register / host_alloc
+ *   (nothing: one process, one thread)                      e1b200_plan_phases*, e1b200_peer_*: time-axis shards
+ *                                                          over the GPUs of a node
  *   (nothing: diagnostics of this library)                 e1b200_get_timing / get_stats / last_error,
  *                                                          e1b200_selftest_any_hit
  *
@@ -131,10 +133,15 @@ int  e1b200_set_channel(e1b200_ctx *ctx, int slot, int prn, double carr_phase0);
 int  e1b200_clear_channel(e1b200_ctx *ctx, int slot);
 int  e1b200_get_carrier_phase(e1b200_ctx *ctx, int slot, double *out);
 int  e1b200_set_carrier_phase(e1b200_ctx *ctx, int slot, double phase);
+/* slots 0 .. n-1 in one copy (the state a time-axis shard hands to the next one)                          */
+int  e1b200_get_carrier_phases(e1b200_ctx *ctx, int n, double *out);
+int  e1b200_set_carrier_phases(e1b200_ctx *ctx, int n, const double *phases);
 
 /* Host-buffer entry point (what the patched galileo_task() calls): copies recs H2D,
  * synthesises n_epochs * samples_per_epoch samples, copies int16 I/Q D2H into out.
- * recs is [n_epochs][max_chan]; out is [n_epochs * samples_per_epoch * 2] int16.       */
+ * recs is [n_epochs][max_chan]; out is [n_epochs * samples_per_epoch * 2] int16.
+ * out may also be DEVICE memory -- of this GPU or of a peer (e1b200_peer_open): the copy engines then move
+ * every finished slice there (over NVLink for a peer) behind the kernels that synthesise the next one.   */
 int  e1b200_synth_epochs(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, int16_t *out);
 
 /* Device-resident variant: d_recs and d_out are device pointers on cfg.device.  Runs on the
@@ -150,6 +157,7 @@ int  e1b200_sync(e1b200_ctx *ctx);
  * over those blocks (src/galileo-sdr.cpp:531-532).  Used for the phase hand-off between
  * time-axis shards and for checkpoint/resume.                                               */
 int  e1b200_plan_phases(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs);
+int  e1b200_plan_phases_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *d_recs); /* device records, asynchronous */
 
 /* Same two, from pseudoranges (restate evaluated on the device).                            */
 int  e1b200_synth_ranges(e1b200_ctx *ctx, int n_epochs, const e1_range_rec *recs, int16_t *out);
@@ -192,6 +200,18 @@ const char *e1b200_version(void);
  * loop: out[i] = 1 when some j in [0, n[i]) has (a[i] + j d[i]) mod M[i] < L[i].  Host pointers,
  * 5 int64 per case in `cases` (a, d, M, L, n).  No counterpart in the reference. */
 int  e1b200_selftest_any_hit(int device, int n_cases, const int64_t *cases, int32_t *out);
+
+/* Time-axis shards on several GPUs of one node (one process per GPU), gather without a collective: the writer
+ * rank allocates the whole stream in its HBM (e1b200_peer_alloc) and ships the 64-byte handle to the others (any
+ * channel: torch.distributed, a pipe); they e1b200_peer_open it and pass `pointer + 4 * first_sample_of_my_segment`
+ * as `out` to e1b200_synth_epochs / _ranges (slices travel by the copy engines over NVLink behind the synthesis
+ * kernels: the fast way) or as d_out to e1b200_synth_*_device (the kernel's own stores cross NVLink: works, but 16-byte
+ * remote stores run at a fifth of the link).  The reference has no counterpart (single process, single thread). */
+#define E1B200_IPC_HANDLE_BYTES 64
+int  e1b200_peer_alloc(int device, size_t bytes, void **d_ptr, unsigned char handle[E1B200_IPC_HANDLE_BYTES]);
+int  e1b200_peer_open(int device, const unsigned char handle[E1B200_IPC_HANDLE_BYTES], void **d_ptr);
+int  e1b200_peer_close(void *d_ptr);   /* a pointer from e1b200_peer_open  */
+int  e1b200_peer_free(void *d_ptr);    /* a pointer from e1b200_peer_alloc */
 
 /* pinned host allocation helpers so the reference's fwrite/FIFO memcpy consumers
  * (src/galileo-sdr.cpp:542,588) can stay unchanged while D2H runs at full PCIe rate        */

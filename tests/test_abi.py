@@ -84,7 +84,7 @@ def test_no_cpu_fallback_without_device(lib):
 
 def test_bench_reads_the_newest_ncu_summary():
     """bench.py takes the synthesis kernel's DRAM traffic and instruction count from the newest committed
-    `ncu --set full` summary under profiles/: newest by build number (r1_v10 comes after r1_v9), and the
+    `ncu --set full` summary under profiles/: newest by round and build number (r1_v10 comes after r1_v9, r2_v1 after both), and the
     file it names exists and holds both figures."""
     import importlib.util
     root = Path(__file__).resolve().parent.parent
@@ -92,9 +92,10 @@ def test_bench_reads_the_newest_ncu_summary():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     traffic, name, inst = bench.ncu_summary_numbers()
-    builds = sorted(int(f.name.split("_v")[1].split("_")[0]) for f in (root / "profiles").glob("r1_v*_synth_ncu_summary.txt")
+    import re
+    builds = sorted(tuple(map(int, re.match(r"r(\d+)_v(\d+)_", f.name).groups())) for f in (root / "profiles").glob("r*_v*_synth_ncu_summary.txt")
                     if "cfg3" not in f.name)
-    assert name == f"r1_v{builds[-1]}_synth_ncu_summary.txt" and (root / "profiles" / name).exists()
+    assert name == "r%d_v%d_synth_ncu_summary.txt" % builds[-1] and (root / "profiles" / name).exists()
     assert 3.0e9 < traffic < 4.0e9 and 5.0e9 < inst < 2.0e10
 
 

@@ -50,6 +50,7 @@ def _scenario(n_epochs, n_chan, max_chan, seed):
 
 
 def _rank_main(rank, world, port, n_samp, n_epochs, n_chan, max_chan, seed, path, mode, use_gpu):
+    import torch
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
@@ -60,7 +61,38 @@ def _rank_main(rank, world, port, n_samp, n_epochs, n_chan, max_chan, seed, path
         else:
             eng = U.OracleEngine(FS, n_samp, max_chan)
         phases0 = np.linspace(0.05, 0.6, max_chan)
-        lo, hi, seg = S.synth_shard(eng, recs, rank, world, dist, phases0=phases0)
+        if mode == "peer":
+            # the bench's strong-scaling arm in small: no hand-off chain (every rank re-plans the blocks before its
+            # range), the finished segment copied by the library into the writer rank's device buffer (CUDA IPC)
+            import e1b200 as E
+            nbytes = n_epochs * n_samp * 4
+            h = torch.zeros(64, dtype=torch.uint8)
+            full = None
+            if rank == 0:
+                full = E.PeerBuffer.alloc(0, nbytes)
+                h.copy_(torch.frombuffer(bytearray(full.handle), dtype=torch.uint8))
+            dist.broadcast(h, 0)
+            if rank != 0:
+                full = E.PeerBuffer.open(0, h.numpy().tobytes(), nbytes)
+            lo, hi, _ = S.replan_start_phases(eng, recs, rank, world, phases0=phases0)
+            if hi > lo:
+                eng.synth_epochs_to(recs[lo:hi], full.ptr + lo * n_samp * 4)
+            dist.barrier()
+            if rank == 0:
+                import ctypes as C
+                whole = np.empty((n_epochs * n_samp, 2), dtype=np.int16)
+                assert C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(whole.ctypes.data), C.c_void_p(full.ptr), C.c_size_t(nbytes), 2) == 0
+                whole.tofile(path)
+            dist.barrier()
+            full.close()
+            eng.close()
+            return
+        if mode == "replan":
+            lo, hi, _ = S.replan_start_phases(eng, recs, rank, world, phases0=phases0)
+            seg = eng.synth_epochs(recs[lo:hi]) if hi > lo else np.zeros((0, 2), dtype=np.int16)
+            mode = "pwrite"
+        else:
+            lo, hi, seg = S.synth_shard(eng, recs, rank, world, dist, phases0=phases0)
         assert seg.shape[0] == (hi - lo) * n_samp
         if mode == "pwrite":
             S.write_segment(path, lo, n_samp, seg, total_epochs=n_epochs)
@@ -99,9 +131,22 @@ def test_three_ranks_with_an_empty_shard(tmp_path):
     _run(3, 5200, 2, 3, 4, 5, tmp_path, "pwrite")
 
 
+def test_three_ranks_replan_instead_of_chain(tmp_path):
+    """shard.replan_start_phases: every rank plans the carrier over all blocks before its range (no communication);
+    same stream as the plan-and-send chain and as the single run."""
+    _run(3, 5200, 8, 4, 5, 7, tmp_path, "replan")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["pwrite", "gather"])
 def test_two_ranks_cuda_engine(tmp_path, mode):
     """Same hand-off with two real synthesiser contexts (both on cuda:0; gloo carries the phases):
     e1b200_plan_phases + e1b200_set_carrier_phase reproduce the single-run stream bit for bit."""
     _run(2, 52000, 9, 7, 8, 3, tmp_path, mode, use_gpu=True)
+
+
+@pytest.mark.gpu
+def test_two_ranks_peer_buffer_sink(tmp_path):
+    """e1b200_peer_alloc / _open: rank 0 owns the whole stream's device buffer, rank 1 (another process; on this
+    one-GPU box the same device) opens the IPC handle and e1b200_synth_epochs delivers its segment there."""
+    _run(2, 52000, 9, 7, 8, 3, tmp_path, "peer", use_gpu=True)
