@@ -351,7 +351,11 @@ typedef struct e1_chan_par { /* 112 bytes, one per active channel of a tile (HBM
     uint32_t Dlo;           /* E1_PAR_SLOW: low word of the table position's step per sample, 2^-32 entry:
                                floor(511 dU / 2^32) of the SIGNED step, negated for phase < 0 (the mirrored walk);
                                its sign is E1_PAR_DOWN                                                 */
-    uint32_t pad[3];
+    uint32_t ev_n0;         /* E1_PAR_EV: samples between two carries of the 32-bit fraction accumulators, rounded down:
+                               floor(2^32 / dF) in bits 0-15 (code), floor(2^32 / dG) capped at 0xffff in bits 16-31
+                               (carrier; dG = Dlo walking up, 2^32 - Dlo walking down)                                 */
+    uint32_t ev_rcp_f;      /* 1.0f / (float)dF as IEEE bits (first carry of a run: e1_ev_first)                       */
+    uint32_t ev_rcp_g;      /* 1.0f / (float)dG, +inf for dG = 0                                                        */
 } e1_chan_par;
 #define E1_PAR_NEG 16u
 #define E1_PAR_FORCE 32u
@@ -361,6 +365,12 @@ typedef struct e1_chan_par { /* 112 bytes, one per active channel of a tile (HBM
                              2.6 MS/s) and the tile is regular (no FORCE / HASZ): the paired-run kernel walks the table
                              by CARRIES of the index fraction, one carrier start per 32 or 64 samples (e1_run_cw)      */
 #define E1_PAR_DOWN 512u  /* with E1_PAR_SLOW: the table position decreases from sample to sample                      */
+#define E1_PAR_EV 1024u   /* with E1_PAR_SLOW, set when the context runs the event-driven kernel (E1_INT_EV): a half-chip
+                             lasts several samples, a thread's E1C_EV_RUN samples fit one 16-field code window, and the
+                             ev_* fields are filled in (e1_ev_add)                                                      */
+/* internal bit of the cfg_flags argument of e1_make_par (never in e1b200_config.flags): fill in the event fields */
+#define E1_INT_EV 0x40000000u
+#define E1C_EV_RUN 64 /* consecutive samples per thread of the event-driven kernel (= E1C_LUT_EXT: one carrier start) */
 
 /* One tile's parameter block in HBM: header (16 bytes: n_active, 3 x pad) + max_chan e1_chan_par,
  * active channels first. */
@@ -1104,7 +1114,7 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
     p->pat_b = ((db & 2u) ? 0xAAAAAAAAu : 0u) | ((db & 1u) ? 0x55555555u : 0u);
     p->code_off = (uint32_t)(r->prn - 1) * E1C_CODE_WORDS_PER_PRN;
     p->Dlo = 0u;
-    p->pad[0] = p->pad[1] = p->pad[2] = 0u;
+    p->ev_n0 = p->ev_rcp_f = p->ev_rcp_g = 0u;
     if (!(misc & (E1_PAR_FORCE | E1_PAR_HASZ)) && e1_fabs(p->sp) < 1.0 / 512.0) {
         /* step of the table position 511 |phase| / 2^32 (entry in the high word): floor(511 dU / 2^32) with dU read as
            a signed 64-bit number -- |D| < 2^32 because |sp| < 1/512 -- and negated when the table is walked mirrored */
@@ -1114,6 +1124,21 @@ E1_HD void e1_make_par(const e1_tile_ck *c, const e1_epoch_rec *r, double delt, 
             D = -D;
         p->Dlo = (uint32_t)(uint64_t)D;
         misc |= E1_PAR_SLOW | (D < 0 ? E1_PAR_DOWN : 0u);
+        if (cfg_flags & E1_INT_EV) {
+            /* event-driven runs: both index fractions are 32-bit accumulators whose CARRIES are the events.  Not for a
+               step that divides 2^32 (n0 steps land exactly on 2^32: the carry test of e1_ev_sub would miss it) and
+               only while E1C_EV_RUN samples cross fewer than 15 half-chips (one code window) */
+            const uint32_t dF = p->dF, dG = D < 0 ? (uint32_t)(uint64_t)(-D) : (uint32_t)(uint64_t)D;
+            if (dF != 0u && (uint64_t)dF * E1C_EV_RUN < (14ull << 32) && dG < 0x40000000u) {
+                const uint64_t n0c = 0x100000000ull / dF, n0r = dG ? 0x100000000ull / dG : 0xffffull;
+                if (n0c <= 0xffffull && n0c * dF != 0x100000000ull && (dG == 0u || n0r * dG != 0x100000000ull)) {
+                    p->ev_n0 = (uint32_t)n0c | ((n0r > 0xffffull ? 0xffffu : (uint32_t)n0r) << 16);
+                    p->ev_rcp_f = e1_float_bits(1.0f / (float)dF);
+                    p->ev_rcp_g = dG ? e1_float_bits(1.0f / (float)dG) : 0x7f800000u;
+                    misc |= E1_PAR_EV;
+                }
+            }
+        }
     }
     p->misc = misc;
     if (cfg_flags & (E1B200_CFG_CBOC | E1B200_CFG_GAIN)) { /* float path: gain[i] / 2^7 (src/galileo-sdr.cpp:477), exact in float below 2^24 */
@@ -1234,7 +1259,7 @@ E1_HD int e1_any_hit(int64_t a, int64_t d, int64_t M, int64_t L, int64_t n) { re
  *   both     the 40-bit sequence used here is below the exact one by less than (T + 1) / 256 <= 33.
  * FORCE / HASZ tiles are not examined (the kernel takes them through the single-run path anyway). */
 E1_HD int e1_par_clean(const e1_chan_par *p, int T, uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code, uint32_t thr_code,
-                        int cw_samples = 2 * E1C_MAX_RUN)
+                        int cw_samples = 2 * E1C_MAX_RUN, int code_run = E1C_MAX_RUN)
 {
     if ((p->misc & (E1_PAR_FORCE | E1_PAR_HASZ)) || T > 8192)
         return 0;
@@ -1267,7 +1292,9 @@ E1_HD int e1_par_clean(const e1_chan_par *p, int T, uint32_t tc_carr, uint32_t l
            e1_tc_code) and has the same step -- the zone grows by thr_code on either side */
         const int hs = 51 - E1_AMB_BITS;
         const uint64_t m51 = ((uint64_t)1 << 51) - 1ull;
-        const int64_t L = ((int64_t)lim_code + R + slack + 1 + 2 * (int64_t)thr_code) << (E1_AMB_BITS - 32);
+        /* code_run: samples the code fraction is stepped from one start (R in the run kernels, E1C_EV_RUN in the
+           event-driven one, whose bias and limit are those of runs of that length as well) */
+        const int64_t L = ((int64_t)lim_code + code_run + slack + 1 + 2 * (int64_t)thr_code) << (E1_AMB_BITS - 32);
         const uint64_t bias = ((uint64_t)slack + thr_code) << (E1_AMB_BITS - 32);
         if (L >= M / 2)
             return 0;
@@ -1847,6 +1874,369 @@ E1_HD void e1_cw_rest_impl(const e1_chan_par *p, const uint32_t *codes, const un
             if (n_slow)
                 (*n_slow)++;
         }
+    }
+}
+
+/* ---- event-driven runs (E1_PAR_EV; sample rates where a half-chip lasts several samples) ---------------------
+ * At 25 MS/s a BOC(1,1) half-chip lasts 12.2 samples and, at 4 kHz of Doppler, so does an entry of the carrier
+ * table: the term  m x (cos, sin)  a channel adds to the stream (src/galileo-sdr.cpp:509-525) is piecewise constant and
+ * the per-sample loop recomputes the same product five times out of six.  Here a thread owns E1C_EV_RUN consecutive
+ * samples of a tile as a column of DIFFERENCES in shared memory; per channel it adds the term of its first sample
+ * and, at every sample where the term changes, the change; after the last channel ONE running sum over the column
+ * gives the samples (integer additions are associative: the same sums as the per-sample loop, bit for bit).
+ *
+ * The change points are the CARRIES of the two 32-bit index fractions the carry-walked loop (e1_run_cw) steps:
+ *   code     F += dF, a carry = the next half-chip (the window moves up by one field)
+ *   carrier  G += dG, a carry = the next table entry (G = the position's low word walking up, its complement walking
+ *            down, dG = |D|: the borrow of the low word is the carry of its complement)
+ * -- the same integers as that loop, so everything proved for it (bias, limits, E1_PAR_CLEAN) carries over; the code
+ * fraction is stepped from ONE start per E1C_EV_RUN samples instead of one per 16, which the bias and the limits of an
+ * event-driven context are sized for (tc_code of a run of E1C_EV_RUN, e1_par_clean's code_run).  Between carries
+ * nothing is computed: the first carry of a run comes from one reciprocal multiply (e1_ev_first), the following ones
+ * are n0 or n0 + 1 steps apart (n0 = floor(2^32 / step): one add of n0 x step and its carry flag say which).  The
+ * two event streams run as two independent loops: at a code event the table entry is evaluated directly (number of
+ * carrier carries so far = high word of G_a + n dG), at a carrier event the chip field likewise (high word of
+ * F_a + (n - 1) dF: the chip of the sample BEFORE, so that coinciding events add up to new - old exactly).
+ * A code wrap inside the thread's samples splits them into two sub-ranges (HA / pat_a before, HB / pat_b after).   */
+#if defined(__CUDA_ARCH__)
+typedef uint32_t e1_dptr; /* this thread's column: shared-memory address of entry 0, entries 128 bytes apart */
+static __device__ __forceinline__ void e1_diff_add(e1_dptr d, int k, int v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" : : "r"(d + 128u * (uint32_t)k), "r"(v) : "memory");
+}
+#else
+typedef int *e1_dptr;
+static inline void e1_diff_add(e1_dptr d, int k, int v) { d[k] += v; }
+#endif
+
+/* a code word of the event-driven kernel: it reads them from GLOBAL memory (read-only path, L1 / L2: two words per
+   thread and channel), which leaves the shared memory to the columns -- five tiles in flight per SM instead of three */
+E1_HD uint32_t e1_ldg32(const uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+E1_HD uint32_t e1_hi_mad(uint32_t a, uint32_t b, uint32_t c) /* high word of a * b + c */
+{
+    return (uint32_t)(((uint64_t)a * b + c) >> 32);
+}
+
+/* Smallest n >= 1 with g + n d >= 2^32 (the first carry of the accumulator g stepped by d < 2^30), or a number above
+ * E1C_EV_RUN when there is none within reach.  rcp = 1.0f / (float)d (+inf for d = 0): the float quotient is within one
+ * of floor((2^32 - 1 - g) / d) as long as that is small, and one remainder settles it (mod 2^32: the true remainder of
+ * the estimate lies in [-d, 2 d), and 3 d < 2^32 keeps "negative" and "d or more" apart). */
+E1_HD uint32_t e1_ev_first(uint32_t g, uint32_t d, float rcp)
+{
+    const uint32_t x = ~g;
+    const float qf = (float)x * rcp;
+    if (!(qf < (float)(E1C_EV_RUN + 2)))
+        return 0xffffu;
+    uint32_t q = (uint32_t)qf;
+    const uint32_t r = x - q * d;
+    if (r >= d)
+        q += r >= 0u - d ? 0xffffffffu : 1u;
+    return q + 1u;
+}
+
+/* F += E0 (n0 steps at once); a carry: the next event is n0 samples on; none: one more step, n0 + 1.  n01 = n0 + 1. */
+E1_HD void e1_ev_next(uint32_t &F, uint32_t &krel, uint32_t E0, uint32_t dF, uint32_t n01)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t cy;
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(F), "=r"(cy) : "r"(E0));
+    krel += n01 - cy;
+    if (!cy)
+        F += dF;
+#else
+    const uint32_t F2 = F + E0;
+    if (F2 < F) {
+        F = F2;
+        krel += n01 - 1u;
+    } else {
+        F = F2 + dF;
+        krel += n01;
+    }
+#endif
+}
+
+/* One sub-range [ka, kb) of a thread's samples (tile-relative; the thread's first sample is j0): adds the channel's
+ * differences to the column (CHECK: scale x them).  after: the sub-range lies behind the tile's code wrap.  close: the term
+ * of sample kb - 1 is taken back out at kb (the next sub-range starts from nothing).  Returns 1 when CHECK and some
+ * sample's biased fraction is below its limit (the caller takes the differences back out: scale = -1).
+ * Both event loops run a trip count that is the same for every thread working on the channel (the most carries
+ * E1C_EV_RUN - 1 steps can produce) and are straight-line inside: an iteration past the thread's last event adds zero to
+ * the column's last entry.  lut1_s: the single-copy carrier table and its two difference tables (e1_build_lut1). */
+#define E1C_LUT1_WORDS ((E1C_LUT_IDX + 3) / 4 * 4)
+template <bool CHECK>
+E1_HD uint32_t e1_ev_sub(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1_s, int ka, int kb, int j0, int after, int close, e1_dptr diff,
+                         int scale, uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
+{
+    const uint32_t misc = p->misc, dF = p->dF, Dlo = p->Dlo;
+    const uint32_t neg = misc & E1_PAR_NEG, down = misc & E1_PAR_DOWN;
+    const uint32_t n0c = p->ev_n0 & 0xffffu, n0r = p->ev_n0 >> 16;
+    const uint32_t kn = (uint32_t)(kb - ka); /* samples of the sub-range */
+    /* code side at ka */
+    const uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)ka * p->dH;
+    const uint32_t Fa = (uint32_t)(H >> 19), h0 = (uint32_t)(H >> 51);
+    const uint32_t *cw = codes + p->code_off + (h0 >> 4);
+    uint32_t win = e1_funnel_l(e1_ldg32(cw + 1), e1_ldg32(cw), 2u * (h0 & 15u)) ^ (after ? p->pat_b : p->pat_a);
+    win &= (win << 1) | 0x55555555u; /* fields are now y - x in two's complement (e1_code_window) */
+    /* carrier side at ka: the table position of e1_run_cw, one start for the whole sub-range */
+    const uint64_t U = p->U0 + (uint64_t)(uint32_t)ka * p->dU;
+    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr);
+    const uint32_t Ga = down ? ~(uint32_t)y : (uint32_t)y, dG = down ? 0u - Dlo : Dlo;
+    const int sstep = down ? -4 : 4; /* bytes per entry of the single-copy table */
+    const e1_sptr addr_a = lut1_s + 4u * (uint32_t)(y >> 32);
+    /* walking up entry E takes over from E - 1, walking down from E + 1: one difference table each */
+    const e1_sptr daddr_a = addr_a + (down ? 8u : 4u) * E1C_LUT1_WORDS;
+#if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
+    {
+        const int64_t last = (int64_t)(uint32_t)(y >> 32) + (down ? -1 : 1) * (int64_t)e1_hi_mad(kn - 1u, dG, Ga);
+        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT_IDX || last < 0 || last >= E1C_LUT_IDX)
+            e1_lut_oob++;
+    }
+#endif
+    uint32_t mF = Fa, mY = (uint32_t)y;
+    if (CHECK && down) /* walking down the low word shrinks until it borrows: the last sample's is a minimum too */
+        mY = ~(Ga + (kn - 1u) * dG);
+    int sgn = (int)win >> 30;
+    {
+        const int w0 = (int)e1_ld32(addr_a);
+        e1_diff_add(diff, ka - j0, CHECK ? scale * sgn * w0 : sgn * w0);
+    }
+    const int kbase = ka - j0;
+    { /* code events: the chip changes, the table entry is whatever it is at that sample */
+        const uint32_t nmax = e1_hi_mad((uint32_t)(E1C_EV_RUN - 1), dF, 0xffffffffu);
+        const uint32_t E0 = n0c * dF, n01 = n0c + 1u;
+        uint32_t krel = e1_ev_first(Fa, dF, e1_bits_float(p->ev_rcp_f));
+        uint32_t F = Fa + krel * dF, wn = win;
+        for (uint32_t i = 0; i < nmax; i++) {
+            const uint32_t valid = krel < kn, kc = valid ? krel : kn - 1u;
+            if (CHECK && valid)
+                mF = F < mF ? F : mF;
+            wn <<= 2;
+            const int s2 = (int)wn >> 30;
+            const int w = (int)e1_ld32(addr_a + sstep * (int)e1_hi_mad(kc, dG, Ga));
+            int d = valid ? (s2 - sgn) * w : 0;
+            if (CHECK)
+                d *= scale;
+            e1_diff_add(diff, kbase + (int)kc, d);
+            sgn = valid ? s2 : sgn;
+            e1_ev_next(F, krel, E0, dF, n01);
+        }
+    }
+    { /* carrier events: the table entry changes under the chip of the sample before */
+        const uint32_t nmax = e1_hi_mad((uint32_t)(E1C_EV_RUN - 1), dG, 0xffffffffu);
+        const uint32_t E0 = n0r * dG, n01 = n0r + 1u;
+        uint32_t krel = e1_ev_first(Ga, dG, e1_bits_float(p->ev_rcp_g));
+        uint32_t G = Ga + krel * dG;
+        for (uint32_t i = 0; i < nmax; i++) {
+            const uint32_t valid = krel < kn, kc = valid ? krel : kn - 1u;
+            if (CHECK && valid) { /* low word at this sample (up: G) / at the sample before (down: the complement of G - dG) */
+                const uint32_t lw = down ? dG - 1u - G : G;
+                mY = lw < mY ? lw : mY;
+            }
+            const int dw = (int)e1_ld32(daddr_a + sstep * (int)e1_hi_mad(kc, dG, Ga));
+            const uint32_t idx = e1_hi_mad(kc - 1u, dF, Fa) & 15u; /* (the mask only matters in an iteration that adds nothing) */
+            const int s = (int)(win << (2u * idx)) >> 30;
+            int d = valid ? s * dw : 0;
+            if (CHECK)
+                d *= scale;
+            e1_diff_add(diff, kbase + (int)kc, d);
+            e1_ev_next(G, krel, E0, dG, n01);
+        }
+    }
+    if (close) { /* the sub-range's last term, evaluated directly */
+        const int w = (int)e1_ld32(addr_a + sstep * (int)e1_hi_mad(kn - 1u, dG, Ga));
+        const int d = sgn * w;
+        e1_diff_add(diff, kb - j0, CHECK ? -(scale * d) : -d);
+    }
+    return CHECK ? (uint32_t)(mY < lim_carr) | (uint32_t)(mF < lim_code) : 0u;
+}
+
+/* krel += the distance to the next carry of an accumulator stepped by d, n0 or n0 + 1 steps.  The accumulator's value
+ * right after a carry, F in [0, d), is kept as its complement Fc = d - 1 - F.  E1 = (n0 + 1) d - 2^32 in (0, d): n0 + 1
+ * steps on the accumulator reads F + E1 < 2 d; below d the carry came with that last step, otherwise one step earlier
+ * and the value there was d less.  On the complement: Fc - E1 does not borrow <=> n0 + 1 steps.  (sub.cc leaves the
+ * hardware carry, 1 = no borrow, in CC.CF.) */
+E1_HD void e1_ev_step(uint32_t &Fc, uint32_t &krel, uint32_t E1, uint32_t d, uint32_t n0)
+{
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .u32 t;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\t"
+        "addc.u32 %1, %1, %4;\n\t"
+        "add.u32 t, %0, %3;\n\t"
+        "min.u32 %0, %0, t;\n\t}"
+        : "+r"(Fc), "+r"(krel)
+        : "r"(E1), "r"(d), "r"(n0));
+#else
+    if (Fc >= E1) {
+        Fc -= E1;
+        krel += n0 + 1u;
+    } else {
+        Fc = Fc - E1 + d;
+        krel += n0;
+    }
+#endif
+}
+
+/* The common case of e1_ev_sub, lean: all E1C_EV_RUN samples of the thread (first one: tile sample j0), no code wrap among
+ * them, clean tile (no tracking).  E1C_EV_RUN - 1 steps from any start produce nmax or nmax - 1 carries (nmax = the most
+ * they can): all iterations but the last are events of every thread and run unguarded, only the last one is clamped
+ * and zeroed where the thread has no event left.
+ * lut1_s: the carrier table, E1C_LUT1_WORDS words, then the difference table walking up (entry E = table[E] -
+ * table[E - 1]) and the one walking down (table[E] - table[E + 1]). */
+E1_HD void e1_ev_run64(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1_s, int j0, e1_dptr diff, uint32_t tc_carr, uint32_t lim_carr)
+{
+    const uint32_t misc = p->misc, dF = p->dF, Dlo = p->Dlo;
+    const uint32_t neg = misc & E1_PAR_NEG, down = misc & E1_PAR_DOWN;
+    const uint32_t n0c = p->ev_n0 & 0xffffu, n0r = p->ev_n0 >> 16;
+    const int after = j0 >= p->j_w;
+    const uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * p->dH;
+    const uint32_t Fa = (uint32_t)(H >> 19), h0 = (uint32_t)(H >> 51);
+    const uint32_t *cw = codes + p->code_off + (h0 >> 4);
+    uint32_t win = e1_funnel_l(e1_ldg32(cw + 1), e1_ldg32(cw), 2u * (h0 & 15u)) ^ (after ? p->pat_b : p->pat_a);
+    win &= (win << 1) | 0x55555555u;
+    const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
+    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr);
+    const uint32_t Ga = down ? ~(uint32_t)y : (uint32_t)y, dG = down ? 0u - Dlo : Dlo;
+    const int sstep = down ? -4 : 4;
+    const e1_sptr addr_a = lut1_s + 4u * (uint32_t)(y >> 32);
+    const e1_sptr daddr_a = addr_a + (down ? 8u : 4u) * E1C_LUT1_WORDS;
+    const uint32_t last = (uint32_t)(E1C_EV_RUN - 1);
+#if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
+    {
+        const int64_t le = (int64_t)(uint32_t)(y >> 32) + (down ? -1 : 1) * (int64_t)e1_hi_mad(last, dG, Ga);
+        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT_IDX || le < 0 || le >= E1C_LUT_IDX)
+            e1_lut_oob++;
+    }
+#endif
+    int sgn = (int)win >> 30;
+    e1_diff_add(diff, 0, sgn * (int)e1_ld32(addr_a));
+    { /* code events */
+        const uint32_t nmax = e1_hi_mad(last, dF, 0xffffffffu);
+        const uint32_t E1 = (n0c + 1u) * dF;
+        uint32_t krel = e1_ev_first(Fa, dF, e1_bits_float(p->ev_rcp_f));
+        uint32_t F = dF - 1u - (Fa + krel * dF), wn = win; /* complement of the post-carry value (e1_ev_step) */
+        for (uint32_t i = 1; i < nmax; i++) {
+#if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
+            if (krel > last) /* an unguarded iteration without an event: must not happen */
+                e1_lut_oob++;
+#endif
+            wn <<= 2;
+            const int s2 = (int)wn >> 30;
+            const int w = (int)e1_ld32(addr_a + sstep * (int)e1_hi_mad(krel, dG, Ga));
+            e1_diff_add(diff, (int)krel, (s2 - sgn) * w);
+            sgn = s2;
+            e1_ev_step(F, krel, E1, dF, n0c);
+        }
+        if (nmax) {
+            const uint32_t kc = krel < last ? krel : last;
+            const int s2 = (int)(wn << 2) >> 30;
+            const int w = (int)e1_ld32(addr_a + sstep * (int)e1_hi_mad(kc, dG, Ga));
+            e1_diff_add(diff, (int)kc, krel <= last ? (s2 - sgn) * w : 0);
+        }
+    }
+    { /* carrier events */
+        const uint32_t nmax = e1_hi_mad(last, dG, 0xffffffffu);
+        const uint32_t E1 = (n0r + 1u) * dG;
+        const uint64_t C = (uint64_t)Fa - (uint64_t)dF; /* chip field of the sample before: high word of (k - 1) dF + Fa */
+        uint32_t krel = e1_ev_first(Ga, dG, e1_bits_float(p->ev_rcp_g));
+        uint32_t G = dG - 1u - (Ga + krel * dG);
+        for (uint32_t i = 1; i < nmax; i++) {
+#if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
+            if (krel > last)
+                e1_lut_oob++;
+#endif
+            const int dw = (int)e1_ld32(daddr_a + sstep * (int)e1_hi_mad(krel, dG, Ga));
+            const uint32_t idx = (uint32_t)(((uint64_t)krel * dF + C) >> 32);
+            const int s = (int)(win << (2u * idx)) >> 30;
+            e1_diff_add(diff, (int)krel, s * dw);
+            e1_ev_step(G, krel, E1, dG, n0r);
+        }
+        if (nmax) {
+            const uint32_t kc = krel < last ? krel : last;
+            const int dw = (int)e1_ld32(daddr_a + sstep * (int)e1_hi_mad(kc, dG, Ga));
+            const uint32_t idx = (uint32_t)(((uint64_t)kc * dF + C) >> 32) & 15u;
+            const int s = (int)(win << (2u * idx)) >> 30;
+            e1_diff_add(diff, (int)kc, krel <= last ? s * dw : 0);
+        }
+    }
+}
+
+/* One E1_PAR_EV channel's differences for the n (<= E1C_EV_RUN) samples of a thread that start at tile sample j0. */
+template <bool CHECK>
+E1_HD uint32_t e1_ev_add(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1_s, int j0, int n, e1_dptr diff, int scale, uint32_t thr_carr,
+                         uint32_t lim_code)
+{
+    const uint32_t tc = e1_tc_carr_cw(thr_carr, E1C_EV_RUN), lim = e1_lim_carr_cw(thr_carr, E1C_EV_RUN);
+    const int jw = p->j_w, kend = j0 + n;
+    uint32_t rc = 0;
+    int ka = j0;
+    do {
+        const int kb = (jw > ka && jw < kend) ? jw : kend;
+        rc |= e1_ev_sub<CHECK>(p, codes, lut1_s, ka, kb, j0, ka >= jw, kb < kend, diff, scale, tc, lim, lim_code);
+        ka = kb;
+    } while (ka < kend);
+    return rc;
+}
+
+/* Everything that does not go through e1_ev_run64, out of line:
+ *   E1_PAR_EV, clean       the thread with the tile's code wrap among its samples, the threads of an epoch's last,
+ *                          shorter tile: the general form of the events (e1_ev_sub)
+ *   E1_PAR_EV, not clean   (about 1 % of the (tile, channel) sets) the same events with the tracking on; a flagged thread takes its differences back out and
+ *   anything else          goes through the generic form (e1_channel_run), 16 samples at a time, term by term
+ * codes / lut_lane: the code words and this lane's copy of the replicated carrier table as plain pointers (the kernel
+ * passes the arrays in global memory: it keeps neither in shared memory). */
+E1_HD void e1_ev_rest_impl(const e1_chan_par *p, e1_sptr lut1_s, const uint32_t *codes, const unsigned char *lut_lane,
+                           int j0, int n, e1_dptr diff, uint32_t thr_carr, uint32_t thr_code, uint32_t tc_code, unsigned long long *n_exact,
+                           unsigned long long *n_slow)
+{
+    const uint32_t lim_code = e1_lim_code(tc_code, thr_code);
+    if ((p->misc & (E1_PAR_EV | E1_PAR_CLEAN)) == (E1_PAR_EV | E1_PAR_CLEAN)) { /* clean, but a code wrap among the thread's samples or fewer than E1C_EV_RUN of them */
+        e1_ev_add<false>(p, codes, lut1_s, j0, n, diff, 1, thr_carr, lim_code);
+        return;
+    }
+    if (p->misc & E1_PAR_EV) {
+        if (!e1_ev_add<true>(p, codes, lut1_s, j0, n, diff, 1, thr_carr, lim_code))
+            return;
+        e1_ev_add<true>(p, codes, lut1_s, j0, n, diff, -1, thr_carr, lim_code);
+    }
+    if (n_slow)
+        (*n_slow)++;
+    int prev = 0;
+    for (int c = 0; c < n; c += E1C_MAX_RUN) {
+        int g[E1C_MAX_RUN];
+        const int m = n - c < E1C_MAX_RUN ? n - c : E1C_MAX_RUN;
+        e1_channel_run(p, codes, lut_lane, j0 + c, m, g, thr_carr, thr_code, e1_bias_h(tc_code), n_exact);
+        for (int i = 0; i < m; i++) {
+            e1_diff_add(diff, c + i, g[i] - prev);
+            prev = g[i];
+        }
+    }
+}
+
+/* The event-driven kernel serves contexts with 8192-sample tiles whose sample rate puts at least ~5 samples into a
+ * half-chip (a thread's E1C_EV_RUN samples must cross fewer than 15 of them, e1_make_par). */
+E1_HD int e1_ev_context(double fs_hz, int run) { return run == E1C_MAX_RUN && fs_hz >= 10.0e6; }
+
+/* carrier tables of the event-driven kernel, 3 E1C_LUT1_WORDS words: entry E of e1_build_lut, once; behind it the
+   differences walking up, table[E] - table[E - 1]; behind those the differences walking down, table[E] - table[E + 1]
+   (a walk only arrives at an entry from a neighbour: the entries without one are 0 and never read) */
+E1_HD void e1_build_lut1(const int32_t *lut, int32_t *lut1)
+{
+    for (int E = 0; E < 3 * E1C_LUT1_WORDS; E++)
+        lut1[E] = 0;
+    for (int E = 0; E < E1C_LUT_IDX; E++) {
+        lut1[E] = lut[E * E1C_LUT_REP];
+        if (E)
+            lut1[E1C_LUT1_WORDS + E] = lut[E * E1C_LUT_REP] - lut[(E - 1) * E1C_LUT_REP];
+        if (E + 1 < E1C_LUT_IDX)
+            lut1[2 * E1C_LUT1_WORDS + E] = lut[E * E1C_LUT_REP] - lut[(E + 1) * E1C_LUT_REP];
     }
 }
 

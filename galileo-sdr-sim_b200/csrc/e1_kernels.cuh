@@ -11,6 +11,8 @@
  *   e1_synth_cw_kernel<NH,T> the sample loop (src/galileo-sdr.cpp:481-539): per sample, all channels,
  *                            int32 accumulate, packed int16 I/Q, 128-bit stores; 32 or 64 samples per thread
  *   e1_synth_kernel<R>       the same with R = 4, 8 or 16 samples per thread (tiles shorter than 8192 samples)
+ *   e1_synth_ev_kernel<T>    the same, event-driven, for sample rates of 10 MS/s and more: a channel's term is piecewise constant
+ *                            there, only its change points are computed (e1_ev_add), one running sum per tile gives the samples
  *
  * HBM layout
  *   recs   e1_epoch_rec[n_epochs][max_chan]                         176 B each (caller / H2D)
@@ -561,6 +563,7 @@ struct e1_clean_args {
     int max_chan, tile;
     uint32_t tc_carr, lim_carr, lim_code, thr_code;
     int cw_samples; /* samples a thread of the synthesis kernel walks from one carrier start (32 or 64) */
+    int code_run;   /* ... and steps the code fraction from one start (16; E1C_EV_RUN in an event-driven context) */
 };
 __global__ void __launch_bounds__(128) e1_clean_kernel(const e1_clean_args A)
 {
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(128) e1_clean_kernel(const e1_clean_args A)
     e1_chan_par *p = reinterpret_cast<e1_chan_par *>(blk + E1C_BLK_HEADER) + slot;
     e1_chan_par q;
     q.U0 = p->U0, q.dU = p->dU, q.HA = p->HA, q.HB = p->HB, q.dH = p->dH, q.j_w = p->j_w, q.misc = p->misc, q.Dlo = p->Dlo;
-    if (e1_par_clean(&q, A.tile, A.tc_carr, A.lim_carr, A.lim_code, A.thr_code, A.cw_samples))
+    if (e1_par_clean(&q, A.tile, A.tc_carr, A.lim_carr, A.lim_code, A.thr_code, A.cw_samples, A.code_run))
         p->misc = q.misc | E1_PAR_CLEAN;
 }
 
@@ -940,6 +943,148 @@ __global__ void __launch_bounds__(TEAMS *E1_CW_TEAM_THREADS(NH), 1) e1_synth_cw_
                 for (int i = 0; i < RUN; i++)
                     if (j0 + i < n_valid)
                         *reinterpret_cast<uint32_t *>(dst + 2 * i) = e1_pack_iq(acc[i]);
+            }
+        }
+        e1_team_sync<TT>(team); /* all reads of this tile's block (and of s_tile[team][b]) are done */
+    }
+    if (n_exact)
+        atomicAdd(&s_cnt, n_exact);
+    __syncthreads();
+    if (tid == 0 && A.counters && s_cnt)
+        atomicAdd(&A.counters[0], s_cnt);
+}
+
+/* ------------------------------------------------------------------ synthesis, event-driven (high sample rates)
+ * e1_ev_context(fs, run): a half-chip and a carrier-table entry last several samples, so a channel's term is piecewise
+ * constant; see "event-driven runs" in e1_core.h.  Same frame as e1_synth_cw_kernel<4, .> -- persistent CTA, TEAMS teams
+ * of 128 threads, a team owns a tile at a time, parameter blocks double-buffered by bulk copy, thread t owns the 64
+ * samples [64 t, 64 t + 64) of the tile -- but the sums live in shared memory as a column of DIFFERENCES per thread
+ * (entry k of lane l of a warp at 128 k + 4 l: a warp's 32 accesses fall into 32 banks whatever the k are), the
+ * channels add their change points to it (e1_ev_add: red.shared) and one running sum per tile turns the column into the
+ * samples (a6 + the sink format).  Shared memory: ONE copy of the carrier table and its two difference tables (7 728 B: a
+ * table read per event, not per sample), the parameter buffers, 32 KB of columns per team; the code words (two per thread
+ * and channel) come from global memory through the read-only path, which is what lets five teams share an SM. */
+#define E1_EV_TEAM_THREADS (E1C_THREADS * E1C_MAX_RUN / E1C_EV_RUN)
+#define E1_LUT1_BYTES (3 * E1C_LUT1_WORDS * 4) /* the table and its two difference tables (e1_build_lut1) */
+#define E1_EV_SMEM(teams, max_chan)                                                                                    \
+    (E1_LUT1_BYTES + (teams) * 2 * (int)e1_blk_bytes(max_chan) + (teams) * E1_EV_TEAM_THREADS * E1C_EV_RUN * 4)
+#define E1_EV_MAX_TEAMS 5
+
+__device__ __noinline__ void e1_ev_rest(const e1_chan_par *p, uint32_t lut1_s, const uint32_t *codes_g, const unsigned char *lut_lane_g,
+                                        int j0, int n, uint32_t col, uint32_t thr_carr, uint32_t thr_code, uint32_t tc_code,
+                                        unsigned long long *n_exact)
+{
+    /* the casts are no-ops in the device pass (e1_sptr / e1_dptr are 32-bit shared-memory addresses there); they let the host
+       pass, which sees the pointer flavour of the two types, parse this */
+    e1_ev_rest_impl(p, (e1_sptr)(size_t)lut1_s, codes_g, lut_lane_g, j0, n, (e1_dptr)(size_t)col, thr_carr, thr_code, tc_code, n_exact,
+                    (unsigned long long *)0);
+}
+
+template <int TEAMS>
+__global__ void __launch_bounds__(TEAMS *E1_EV_TEAM_THREADS, 1) e1_synth_ev_kernel(const e1_synth_args A, const int32_t *lut1)
+{
+    constexpr int TT = E1_EV_TEAM_THREADS, RUN = E1C_EV_RUN;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *s_lut1 = smem_raw;
+    const uint32_t blk_bytes = (uint32_t)e1_blk_bytes(A.max_chan);
+    __shared__ __align__(8) uint64_t s_bar[1 + 2 * TEAMS]; /* [0] tables, [1 + 2 team + b] parameter buffer b of a team */
+    __shared__ unsigned long long s_cnt;
+    __shared__ long s_tile[TEAMS][2];
+
+    const int tid = threadIdx.x, team = tid / TT, t = tid - team * TT;
+    unsigned char *s_blk0 = smem_raw + E1_LUT1_BYTES + (size_t)team * 2 * blk_bytes;
+    unsigned char *s_diff = smem_raw + E1_LUT1_BYTES + (size_t)TEAMS * 2 * blk_bytes;
+    uint64_t *bar = &s_bar[1 + 2 * team];
+    const long total_tiles = (long)A.n_epochs * A.tiles_per_epoch;
+    const long first_wave = (long)TEAMS * gridDim.x;
+    long next_id = 0;
+    if (tid == 0) {
+        s_cnt = 0;
+        for (int i = 0; i < 1 + 2 * TEAMS; i++)
+            e1_mbar_init(&s_bar[i], 1);
+        e1_mbar_init_fence();
+        e1_mbar_expect(&s_bar[0], E1_LUT1_BYTES);
+        e1_bulk_g2s(s_lut1, lut1, E1_LUT1_BYTES, &s_bar[0]);
+    }
+    __syncthreads();
+    if (t == 0) {
+        const long first = (long)TEAMS * blockIdx.x + team;
+        s_tile[team][0] = first;
+        if (first < total_tiles) {
+            e1_mbar_expect(&bar[0], blk_bytes);
+            e1_bulk_g2s(s_blk0, A.blk + (size_t)first * blk_bytes, blk_bytes, &bar[0]);
+        }
+        next_id = first_wave + atomicAdd(A.next_tile, 1u);
+    }
+    /* this thread's column of differences: warp w of the CTA owns 8 KB, entry k of lane l at 128 k + 4 l */
+    const uint32_t col = e1_smem_u32(s_diff) + (uint32_t)(tid >> 5) * (32u * RUN * 4u) + 4u * (uint32_t)(tid & 31);
+#pragma unroll 8
+    for (int k = 0; k < RUN; k++)
+        asm volatile("st.shared.u32 [%0], %1;" : : "r"(col + 128u * (uint32_t)k), "r"(0u) : "memory");
+    __syncthreads();
+    e1_mbar_wait(&s_bar[0], 0);
+
+    const uint32_t lut1_s = e1_smem_u32(s_lut1);
+    const unsigned char *lut_lane_g = reinterpret_cast<const unsigned char *>(A.lut) + 4 * (tid & (E1C_LUT_REP - 1));
+    const uint32_t tc_cw = e1_tc_carr_cw(A.thr_carr, RUN), lim_cw = e1_lim_carr_cw(A.thr_carr, RUN);
+    const int j0 = t * RUN;
+    unsigned long long n_exact = 0;
+    for (int it = 0;; it++) {
+        const int b = it & 1;
+        const long tile_id = s_tile[team][b];
+        if (tile_id >= total_tiles)
+            break;
+        if (t == 0) {
+            s_tile[team][1 - b] = next_id;
+            if (next_id < total_tiles) {
+                e1_mbar_expect(&bar[1 - b], blk_bytes);
+                e1_bulk_g2s(s_blk0 + (size_t)(1 - b) * blk_bytes, A.blk + (size_t)next_id * blk_bytes, blk_bytes, &bar[1 - b]);
+                next_id = first_wave + atomicAdd(A.next_tile, 1u);
+            }
+        }
+        e1_mbar_wait(&bar[b], (uint32_t)(it >> 1) & 1u);
+        const unsigned char *blk = s_blk0 + (size_t)b * blk_bytes;
+        const int nact = *reinterpret_cast<const int *>(blk);
+        const e1_chan_par *par = reinterpret_cast<const e1_chan_par *>(blk + E1C_BLK_HEADER);
+        const int e = (int)(tile_id / A.tiles_per_epoch), tt = (int)(tile_id - (long)e * A.tiles_per_epoch);
+        const int n_valid = min(A.tile, A.n_samp - tt * A.tile);
+
+        if (j0 < n_valid) {
+            const int n = min(RUN, n_valid - j0);
+            for (int a = 0; a < nact; a++) {
+                const uint32_t want = E1_PAR_EV | E1_PAR_CLEAN;
+                const int jw = par[a].j_w;
+                if ((par[a].misc & want) == want && n == RUN && !(jw > j0 && jw < j0 + RUN))
+                    e1_ev_run64(&par[a], A.codes, (e1_sptr)(size_t)lut1_s, j0, (e1_dptr)(size_t)col, tc_cw, lim_cw);
+                else
+                    e1_ev_rest(&par[a], lut1_s, A.codes, lut_lane_g, j0, n, col, A.thr_carr, A.thr_code, A.tc_code, &n_exact);
+            }
+            /* running sum of the column = the samples; a6 + sink format (:536-537); the column is left zeroed */
+            int16_t *dst = A.out + ((size_t)e * A.n_samp + (size_t)tt * A.tile + j0) * 2;
+            int sum = 0;
+            if (A.vec_ok && n == RUN) {
+#pragma unroll
+                for (int i = 0; i < RUN; i += 4) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t v;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(col + 128u * (uint32_t)(i + q)) : "memory");
+                        asm volatile("st.shared.u32 [%0], %1;" : : "r"(col + 128u * (uint32_t)(i + q)), "r"(0u) : "memory");
+                        sum += (int)v;
+                        w[q] = e1_pack_iq(sum);
+                    }
+                    *reinterpret_cast<uint4 *>(dst + 2 * i) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+                for (int i = 0; i < RUN; i++) {
+                    uint32_t v;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(col + 128u * (uint32_t)i) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" : : "r"(col + 128u * (uint32_t)i), "r"(0u) : "memory");
+                    sum += (int)v;
+                    if (i < n)
+                        *reinterpret_cast<uint32_t *>(dst + 2 * i) = e1_pack_iq(sum);
+                }
             }
         }
         e1_team_sync<TT>(team); /* all reads of this tile's block (and of s_tile[team][b]) are done */

@@ -27,6 +27,8 @@ struct e1b200_ctx {
     int elide;          /* mark tiles that cannot hold an ambiguous sample (e1_clean_kernel) so the sample loop skips its tracking */
     int pair;           /* run == 16: 8192-sample tiles through e1_synth_cw_kernel (teams, carry-walked runs) */
     int quad;           /* ... with 64 samples per thread in 3 teams of 128 threads instead of 32 in 2 teams of 256 */
+    int evk;            /* event-driven synthesis (e1_synth_ev_kernel): e1_ev_context(fs, run); evk = teams per CTA (2 .. 5), 0 = off */
+    int tc_run;         /* samples the code fraction is stepped from one start: sizes the code bias and limits (run, or E1C_EV_RUN) */
     int synth_threads;  /* threads per synthesis CTA */
     int tiles_per_epoch;
     int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
@@ -43,6 +45,7 @@ struct e1b200_ctx {
     std::vector<int> ev_kind;      /* 0 = planner pass, 1 = synthesis launch */
     uint32_t *d_codes;
     int32_t *d_lut;
+    int32_t *d_lut1;    /* single-copy carrier table of the event-driven kernel */
     double *d_phase;
     unsigned long long *d_counters; /* [0] exact-fallback samples [1] planner errors [2] serial epochs [3] HAT epochs */
     unsigned int *d_next_tile;      /* dynamic tile counter of the synthesis kernel */
@@ -112,6 +115,16 @@ static int env_int(const char *name, int dflt)
 }
 
 typedef void (*synth_fn)(const e1_synth_args);
+typedef void (*ev_fn)(const e1_synth_args, const int32_t *);
+static ev_fn ev_for(int teams)
+{
+    switch (teams) {
+    case 5: return e1_synth_ev_kernel<5>;
+    case 4: return e1_synth_ev_kernel<4>;
+    case 3: return e1_synth_ev_kernel<3>;
+    default: return e1_synth_ev_kernel<2>;
+    }
+}
 static synth_fn synth_for(int run, int pair = 0, int quad = 0)
 {
     if (pair)
@@ -172,6 +185,17 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->pair = (run == E1C_MAX_RUN) && !env_int("E1B200_NO_PAIR", 0) && !ctx->float_path;
     ctx->quad = ctx->pair && env_int("E1B200_QUAD", 1);
     ctx->synth_threads = ctx->pair ? (ctx->quad ? 3 * E1_CW_TEAM_THREADS(4) : 2 * E1_CW_TEAM_THREADS(2)) : E1_SYNTH_THREADS;
+    ctx->evk = 0;
+    if (ctx->pair && e1_ev_context(cfg->fs_hz, run) && !env_int("E1B200_NO_EV", 0)) {
+        int want = env_int("E1B200_EV_TEAMS", E1_EV_MAX_TEAMS);
+        want = want < 2 ? 2 : (want > E1_EV_MAX_TEAMS ? E1_EV_MAX_TEAMS : want);
+        for (int teams = want; teams >= 2 && !ctx->evk; teams--)
+            if ((size_t)E1_EV_SMEM(teams, cfg->max_chan) + 256 <= prop.sharedMemPerBlockOptin)
+                ctx->evk = teams;
+    }
+    ctx->tc_run = ctx->evk ? E1C_EV_RUN : run;
+    if (ctx->evk)
+        ctx->synth_threads = ctx->evk * E1_EV_TEAM_THREADS;
     ctx->tile = run * E1_SYNTH_THREADS;
     ctx->tiles_per_epoch = (cfg->samples_per_epoch + ctx->tile - 1) / ctx->tile;
     ctx->geo = e1_span_geometry(ctx->tiles_per_epoch);
@@ -189,6 +213,8 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     ctx->plan_epochs = pe < 1 ? 1 : (pe > 4096 ? 4096 : (int)pe);
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_bytes = E1_CODES_BYTES + E1_LUT_BYTES + (ctx->pair ? (ctx->quad ? 6 : 4) : 2) * (int)e1_blk_bytes(cfg->max_chan);
+    if (ctx->evk)
+        ctx->smem_bytes = E1_EV_SMEM(ctx->evk, cfg->max_chan);
     *out = ctx; /* from here on errors leave a context the caller can query and destroy */
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -200,6 +226,10 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     if (ctx->float_path) {
         CK(cudaFuncSetAttribute(e1_synth_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e1_synth_float_kernel, E1_SYNTH_THREADS, ctx->smem_bytes));
+    } else if (ctx->evk) {
+        ev_fn efn = ev_for(ctx->evk);
+        CK(cudaFuncSetAttribute(efn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, efn, ctx->synth_threads, ctx->smem_bytes));
     } else {
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_bytes));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, ctx->synth_threads, ctx->smem_bytes));
@@ -221,6 +251,12 @@ int e1b200_create(const e1b200_config *cfg, e1b200_ctx **out)
     CK(cudaMalloc(&ctx->d_next_tile, sizeof(unsigned int)));
     CK(cudaMemcpy(ctx->d_codes, h_codes, E1_CODES_BYTES, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_lut, h_lut, E1_LUT_BYTES, cudaMemcpyHostToDevice));
+    if (ctx->evk) {
+        std::vector<int32_t> lut1_v(E1_LUT1_BYTES / 4, 0);
+        e1_build_lut1(h_lut, lut1_v.data());
+        CK(cudaMalloc(&ctx->d_lut1, E1_LUT1_BYTES));
+        CK(cudaMemcpy(ctx->d_lut1, lut1_v.data(), E1_LUT1_BYTES, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(ctx->d_phase, 0, sizeof(double) * E1B200_MAX_CHAN));
     CK(cudaMemset(ctx->d_counters, 0, sizeof ctx->counters));
     return E1B200_OK;
@@ -237,6 +273,7 @@ int e1b200_destroy(e1b200_ctx *ctx)
         cudaStreamSynchronize(ctx->copy_stream);
     cudaFree(ctx->d_codes);
     cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_lut1);
     cudaFree(ctx->d_phase);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_next_tile);
@@ -448,8 +485,8 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         F.max_chan = cfg->max_chan;
         F.tile = ctx->tile;
         F.tiles_per_epoch = ctx->tiles_per_epoch;
-        F.tc_code = e1_tc_code(e1_thr_code(ctx->tile, ctx->amb_scale), ctx->run);
-        F.cfg_flags = ctx->cfg.flags;
+        F.tc_code = e1_tc_code(e1_thr_code(ctx->tile, ctx->amb_scale), ctx->tc_run);
+        F.cfg_flags = ctx->cfg.flags | (ctx->evk ? E1_INT_EV : 0u);
         const long tiles = (long)n * ctx->tiles_per_epoch;
         e1_finalize_kernel<<<(unsigned)((tiles + 3) / 4), 128, 0, ctx->stream>>>(F);
         ctx->timing.kernel_launches += 1;
@@ -462,7 +499,8 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
             const uint32_t thr_carr = e1_thr_carr(ctx->tile, ctx->amb_scale), thr_code = e1_thr_code(ctx->tile, ctx->amb_scale);
             C.tc_carr = e1_tc_carr(thr_carr, ctx->run);
             C.lim_carr = e1_lim_carr(C.tc_carr, thr_carr);
-            C.cw_samples = ctx->quad ? E1_CW_RUN(4) : E1_CW_RUN(2);
+            C.cw_samples = ctx->evk ? E1C_EV_RUN : (ctx->quad ? E1_CW_RUN(4) : E1_CW_RUN(2));
+            C.code_run = ctx->evk ? E1C_EV_RUN : E1C_MAX_RUN;
             C.lim_code = e1_lim_code(F.tc_code, thr_code);
             C.thr_code = thr_code;
             e1_clean_kernel<<<(unsigned)((tiles * cfg->max_chan + 127) / 128), 128, 0, ctx->stream>>>(C);
@@ -493,12 +531,12 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
     A.thr_carr = e1_thr_carr(ctx->tile, ctx->amb_scale);
     A.thr_code = e1_thr_code(ctx->tile, ctx->amb_scale);
     A.tc_carr = e1_tc_carr(A.thr_carr, ctx->run);
-    A.tc_code = e1_tc_code(A.thr_code, ctx->run);
+    A.tc_code = e1_tc_code(A.thr_code, ctx->tc_run);
     A.vec_ok = (cfg->samples_per_epoch % 4 == 0) && (((uintptr_t)d_out & 15u) == 0);
     A.use_bulk = ctx->use_bulk;
     long total_tiles = (long)n * ctx->tiles_per_epoch;
     long grid = (long)ctx->sm_count * ctx->ctas_per_sm;
-    const int teams = ctx->pair ? (ctx->quad ? 3 : 2) : 1;
+    const int teams = ctx->evk ? ctx->evk : (ctx->pair ? (ctx->quad ? 3 : 2) : 1);
     const long cta_tiles = (total_tiles + teams - 1) / teams; /* a CTA of the team kernel starts on one tile per team */
     if (grid > cta_tiles)
         grid = cta_tiles;
@@ -508,6 +546,8 @@ static int enqueue_synth(e1b200_ctx *ctx, int e_off, int n, const e1_epoch_rec *
         return rc;
     if (ctx->float_path)
         e1_synth_float_kernel<<<(unsigned)grid, E1_SYNTH_THREADS, ctx->smem_bytes, ctx->stream>>>(A, ctx->alpha, ctx->beta);
+    else if (ctx->evk)
+        ev_for(ctx->evk)<<<(unsigned)grid, ctx->synth_threads, ctx->smem_bytes, ctx->stream>>>(A, ctx->d_lut1);
     else
         synth_for(ctx->run, ctx->pair, ctx->quad)<<<(unsigned)grid, ctx->synth_threads, ctx->smem_bytes, ctx->stream>>>(A);
     CK(cudaGetLastError());

@@ -162,7 +162,7 @@ def hostsim():
         hs.hs_chain_scan_compare.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         hs.hs_first_hit.restype = C.c_longlong
         hs.hs_first_hit.argtypes = [C.c_longlong] * 5
-        for f in (hs.hs_clean_tiles, hs.hs_checked_tiles, hs.hs_clean_violations, hs.hs_cw_pairs):
+        for f in (hs.hs_clean_tiles, hs.hs_checked_tiles, hs.hs_clean_violations, hs.hs_cw_pairs, hs.hs_ev_pairs, hs.hs_ev_rest):
             f.restype = C.c_ulonglong
         hs.hs_max_code_ab_units.restype = C.c_double
         hs.hs_plan_compare.restype = C.c_long

@@ -84,6 +84,12 @@ static int g_cw_nh = 4; // runs of 16 samples per thread of the team kernel: 4 (
 void hs_set_cw_runs(int nh) { g_cw_nh = nh == 2 ? 2 : 4; }
 static uint32_t g_cfg_flags = 0;
 void hs_set_cfg_flags(unsigned int flags) { g_cfg_flags = flags; }
+// event-driven kernel (e1_synth_ev_kernel): -1 = as the library decides (e1_ev_context), 0 = never, 1 = whenever the tile is 8192 samples
+static int g_ev_mode = -1;
+void hs_set_ev_mode(int m) { g_ev_mode = m; }
+static unsigned long long g_ev_pairs = 0, g_ev_rest = 0; // (thread, channel) pairs through e1_ev_add<false> / through e1_ev_rest_impl since load
+unsigned long long hs_ev_pairs(void) { return g_ev_pairs; }
+unsigned long long hs_ev_rest(void) { return g_ev_rest; }
 
 } // extern "C"
 // One tile of e1_synth_cw_kernel<NH, .>: every thread's NH x 16 samples, channel by channel.
@@ -123,6 +129,53 @@ static void cw_tile(const e1_chan_par *par, int nact, const uint32_t *codes, con
                 o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
                 o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
             }
+    }
+}
+// One tile of e1_synth_ev_kernel: every thread's E1C_EV_RUN samples as a column of differences, channel by channel, then the running sum.
+static void ev_tile(const e1_chan_par *par, int nact, const uint32_t *codes, const unsigned char *lut, const int32_t *lut1, int n_valid, int16_t *o,
+                    uint32_t thr_carr, uint32_t thr_code, uint32_t tc_code, uint32_t lim_code, unsigned long long *stats)
+{
+    const int RUN = E1C_EV_RUN, threads = E1C_THREADS * E1C_MAX_RUN / RUN;
+    for (int tid = 0; tid < threads; tid++) {
+        const int j0 = tid * RUN;
+        if (j0 >= n_valid)
+            continue;
+        const int n = n_valid - j0 < RUN ? n_valid - j0 : RUN;
+        const unsigned char *lut_lane = lut + 4 * (tid & (E1C_LUT_REP - 1));
+        int diff[E1C_EV_RUN + 1] = {0};
+        for (int a = 0; a < nact; a++) {
+            const uint32_t want = E1_PAR_EV | E1_PAR_CLEAN;
+            if ((par[a].misc & want) == want) {
+                if (n == RUN && !(par[a].j_w > j0 && par[a].j_w < j0 + RUN)) // the kernel's inline form
+                    e1_ev_run64(&par[a], codes, e1_sp(lut1), j0, diff, e1_tc_carr_cw(thr_carr, RUN), e1_lim_carr_cw(thr_carr, RUN));
+                else
+                    e1_ev_add<false>(&par[a], codes, e1_sp(lut1), j0, n, diff, 1, thr_carr, lim_code);
+                g_ev_pairs++;
+                // beside it: the same events with the tracking on must not flag anything, and the generic form must give the same terms
+                int d1[E1C_EV_RUN + 1] = {0}, d0[E1C_EV_RUN + 1] = {0}, d2[E1C_EV_RUN + 1] = {0};
+                unsigned long long dummy[2] = {0, 0};
+                e1_ev_add<false>(&par[a], codes, e1_sp(lut1), j0, n, d0, 1, thr_carr, lim_code);
+                const uint32_t flagged = e1_ev_add<true>(&par[a], codes, e1_sp(lut1), j0, n, d1, 1, thr_carr, lim_code);
+                const bool generic_too = (tid + a) % 4 == 0; // a quarter of the pairs (the generic form is 20 times slower)
+                if (generic_too) {
+                    e1_chan_par q = par[a];
+                    q.misc &= ~(uint32_t)E1_PAR_EV; // straight to the generic form
+                    e1_ev_rest_impl(&q, e1_sp(lut1), codes, lut_lane, j0, n, d2, thr_carr, thr_code, tc_code, &dummy[0], &dummy[1]);
+                }
+                if (flagged || dummy[0] || memcmp(d0, d1, sizeof(int) * n) || (generic_too && memcmp(d0, d2, sizeof(int) * n)))
+                    g_clean_violations++;
+            } else {
+                e1_ev_rest_impl(&par[a], e1_sp(lut1), codes, lut_lane, j0, n, diff, thr_carr, thr_code, tc_code, &stats[0], &stats[2]);
+                g_ev_rest++;
+            }
+        }
+        int s = 0;
+        for (int i = 0; i < n; i++) {
+            s += diff[i];
+            uint32_t w = e1_pack_iq(s);
+            o[(size_t)(j0 + i) * 2] = (int16_t)(w & 0xffffu);
+            o[(size_t)(j0 + i) * 2 + 1] = (int16_t)(w >> 16);
+        }
     }
 }
 extern "C" {
@@ -208,9 +261,14 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
         }
     }
     const uint32_t thr_carr = e1_thr_carr(tile, amb_scale), thr_code = e1_thr_code(tile, amb_scale);
-    const uint32_t tc_carr = e1_tc_carr(thr_carr, run), tc_code = e1_tc_code(thr_code, run);
+    // event-driven context (e1_synth_ev_kernel): the code fraction is stepped from one start per E1C_EV_RUN samples
+    const int ev = !(g_cfg_flags & (E1B200_CFG_CBOC | E1B200_CFG_GAIN)) && (g_ev_mode < 0 ? e1_ev_context(fs_hz, run) : (g_ev_mode && run == E1C_MAX_RUN));
+    const int code_run = ev ? E1C_EV_RUN : run;
+    const uint32_t tc_carr = e1_tc_carr(thr_carr, run), tc_code = e1_tc_code(thr_code, code_run);
     const uint32_t lim_carr = e1_lim_carr(tc_carr, thr_carr), lim_code = e1_lim_code(tc_code, thr_code);
     std::vector<e1_chan_par> par(max_chan);
+    std::vector<int32_t> lut1(3 * E1C_LUT1_WORDS);
+    e1_build_lut1(lut, lut1.data());
     stats[0] = stats[1] = stats[2] = 0;
     for (int e = 0; e < n_epochs; e++)
         for (int t = 0; t < tpe; t++) {
@@ -224,7 +282,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                 const int sp = t / geo.span_tiles;
                 e1_make_par(c, &recs[(size_t)e * max_chan + ch], delt, tile,
                             e1_trans_at(&delta[(size_t)ch * n_units + (size_t)e * S + sp], (t - sp * geo.span_tiles) * tile), tc_code,
-                            &par[nact], g_cfg_flags);
+                            &par[nact], g_cfg_flags | (ev ? E1_INT_EV : 0u));
                 if (run == E1C_MAX_RUN && par[nact].j_w != E1C_NO_WRAP && !(par[nact].misc & E1_PAR_FORCE)) {
                     const int64_t d51 = (int64_t)((par[nact].HA - par[nact].HB) << 13) >> 13; // mod 2^51, signed
                     const double units = (double)(d51 < 0 ? -d51 : d51) / 524288.0;
@@ -232,7 +290,7 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                         g_max_ab = units;
                 }
                 if (run == E1C_MAX_RUN) { // e1_clean_kernel
-                    if (e1_par_clean(&par[nact], tile, tc_carr, lim_carr, lim_code, thr_code, g_cw_nh * E1C_MAX_RUN)) {
+                    if (e1_par_clean(&par[nact], tile, tc_carr, lim_carr, lim_code, thr_code, ev ? E1C_EV_RUN : g_cw_nh * E1C_MAX_RUN, code_run)) {
                         par[nact].misc |= E1_PAR_CLEAN;
                         g_clean_tiles++;
                     } else
@@ -262,6 +320,10 @@ int hs_synth_epochs_p(double fs_hz, int n_samp, int max_chan, int n_epochs, cons
                             o[(size_t)(j0 + i) * 2 + 1] = (int16_t)e1_f2i16(fq[i]);
                         }
                 }
+                continue;
+            }
+            if (ev) { // e1_synth_ev_kernel
+                ev_tile(par.data(), nact, codes.data(), (const unsigned char *)lut, lut1.data(), n_valid, o, thr_carr, thr_code, tc_code, lim_code, stats);
                 continue;
             }
             if (run == E1C_MAX_RUN) { // e1_synth_cw_kernel<NH, TEAMS>: 8192 / (16 NH) threads per tile, NH runs of 16 samples each
