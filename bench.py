@@ -46,6 +46,8 @@ WORKLOADS = {
     "cfg4s": (25e6, 2500000, 36, 300, "BASELINE configs[3] slice: dynamic receiver, 25 MS/s, 36 ch, 30 s (300 blocks), per-block "
                                       "Doppler/code-phase restate on the device from pseudorange records"),
 }
+WORKLOADS["rt1"] = (2.6e6, 260000, 16, 1, "real-time call shape: ONE 0.1 s block per call (what the reference's galileo_task() loop hands over per iteration), "
+                                          "2.6 MS/s, 16 slots, 8 satellites; a step = one call: ms_per_step is the latency of a call")
 METRIC = "E1B/C IQ Msamples/sec"
 UNIT = "Msamples/s"
 
@@ -73,18 +75,20 @@ def synthetic_range_records(n_epochs, n_chan, dtype, seed=0, dt=0.100000023142, 
     return rr
 
 
-def ncu_summary_numbers():
-    """From the newest committed `ncu --set full` summary of e1_synth_kernel on the default workload
-    (profiles/*synth_ncu_summary.txt, one launch): DRAM traffic (dram__bytes_read.sum +
-    dram__bytes_write.sum) and warp instructions executed (smsp__inst_executed.sum)."""
+def ncu_summary_numbers(family="cfg2"):
+    """From the newest committed `ncu --set full` summary of the synthesis kernel (profiles/*synth_ncu_summary.txt, one
+    launch): DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) and warp instructions executed
+    (smsp__inst_executed.sum).  family "cfg2": the captures of the default workload (one launch = one step);
+    "cfg3": the captures of the 25 MS/s slice (names with cfg3: one launch = 300 blocks of 2.5 M samples; the caller
+    scales per sample)."""
     best = None
 
     def version(f):     # r<round>_v<build>_...: numeric order (v10 after v9)
         m = re.match(r"r(\d+)_v(\d+)_", f.name)
         return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
 
-    for f in sorted((ROOT / "profiles").glob("*synth_ncu_summary.txt"), key=version):
-        if "cfg3" in f.name:
+    for f in sorted((ROOT / "profiles").glob("*synth*ncu_summary.txt"), key=version):
+        if ("cfg3" in f.name) != (family == "cfg3"):
             continue
         tot, inst, mult = 0.0, None, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for ln in f.read_text().splitlines():
@@ -417,6 +421,8 @@ def main():
         recs = synthetic_range_records(n_epochs, n_chan, E.RANGE_DTYPE, seed=1000 + rank)
     if recs is None:
         recs = U.synthetic_recs_fast(n_epochs, n_chan, fs, seed=1000 + rank)     # each rank: its own time shard
+        if args.workload == "rt1":
+            recs[:, 8:]["prn"] = 0                                               # 8 of the 16 slots in use, like BASELINE configs[0]
     rec_bytes = recs.nbytes
     out_bytes = n_epochs * n_samp * 4
     samples_per_step = n_epochs * n_samp
@@ -619,7 +625,12 @@ def main():
         bytes_per_launch = out_bytes * args.steps / max(synth_launches, 1)
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
         tr = ncu_summary_numbers() if args.workload == "cfg2" else None
-        traffic, traffic_src = (tr[0], f"profiles/{tr[1]} (ncu --set full, one launch of this workload)") if tr else (None, None)
+        if args.workload in ("cfg3", "cfg3s", "cfg4s"):            # captured on the 30 s slice (750 M samples per launch): per-sample figures scale
+            t3 = ncu_summary_numbers("cfg3")
+            if t3:
+                k = samples_per_step / (300 * 2500000)
+                tr = (t3[0] * k, t3[1], t3[2] * k if t3[2] else None)
+        traffic, traffic_src = (tr[0], f"profiles/{tr[1]} (ncu --set full, one launch" + (" of this workload)" if args.workload == "cfg2" else " of the 30 s slice, scaled by samples)")) if tr else (None, None)
         # what actually bounds the kernel: warp-instruction issue slots (4 schedulers per SM, one instruction
         # per clock each).  Instructions per launch from the committed ncu capture of this workload, duration live.
         issue = None
@@ -641,7 +652,7 @@ def main():
                        "host_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "kernel": "e1_synth_cw_kernel<4,3>", "peak_source": peak_src,
+                         "kernel": st.kernel_name, "peak_source": peak_src,
                          "ms_per_launch": per_launch_ms, "launches_per_step": synth_launches / args.steps,
                          "planner_ms_per_step": plan_ms / args.steps, "synth_ms_per_step": synth_ms / args.steps,
                          "note": f"issue-bound, not HBM-bound: {n_chan} channel visits x ~{(issue or {}).get('inst_per_channel_sample', 12.3):.1f} integer instructions per 4-byte sample "

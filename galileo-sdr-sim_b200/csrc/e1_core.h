@@ -2090,16 +2090,34 @@ E1_HD void e1_ev_step(uint32_t &Fc, uint32_t &krel, uint32_t E1, uint32_t d, uin
  * and zeroed where the thread has no event left.
  * lut1_s: the carrier table, E1C_LUT1_WORDS words, then the difference table walking up (entry E = table[E] -
  * table[E - 1]) and the one walking down (table[E] - table[E + 1]). */
-E1_HD void e1_ev_run64(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1_s, int j0, e1_dptr diff, uint32_t tc_carr, uint32_t lim_carr)
+/* The two code words a thread's window is cut from (e1_ev_run64) and H, the thread's code phase at its first sample.
+ * (Fetching them one channel ahead was tried: the extra live registers cost more than the load latency, 6.26 -> 6.48 ms.) */
+E1_HD void e1_ev_fetch(const e1_chan_par *p, const uint32_t *codes, int j0, uint64_t *H, uint32_t *w0, uint32_t *w1)
+{
+    *H = (j0 >= p->j_w ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * p->dH;
+    const uint32_t *cw = codes + p->code_off + (((uint32_t)(*H >> 51) >> 4) & 511u);
+    *w0 = e1_ldg32(cw);
+    *w1 = e1_ldg32(cw + 1);
+}
+
+#if !defined(E1_EV_UNROLL)
+#define E1_EV_UNROLL 4
+#endif
+#define E1_PRAGMA_(x) _Pragma(#x)
+#if defined(__CUDA_ARCH__)
+#define E1_UNROLL(n) E1_PRAGMA_(unroll n)
+#else
+#define E1_UNROLL(n)
+#endif
+E1_HD void e1_ev_run64(const e1_chan_par *p, uint64_t H, uint32_t cw0, uint32_t cw1, e1_sptr lut1_s, int j0, e1_dptr diff, uint32_t tc_carr,
+                       uint32_t lim_carr)
 {
     const uint32_t misc = p->misc, dF = p->dF, Dlo = p->Dlo;
     const uint32_t neg = misc & E1_PAR_NEG, down = misc & E1_PAR_DOWN;
     const uint32_t n0c = p->ev_n0 & 0xffffu, n0r = p->ev_n0 >> 16;
     const int after = j0 >= p->j_w;
-    const uint64_t H = (after ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * p->dH;
     const uint32_t Fa = (uint32_t)(H >> 19), h0 = (uint32_t)(H >> 51);
-    const uint32_t *cw = codes + p->code_off + (h0 >> 4);
-    uint32_t win = e1_funnel_l(e1_ldg32(cw + 1), e1_ldg32(cw), 2u * (h0 & 15u)) ^ (after ? p->pat_b : p->pat_a);
+    uint32_t win = e1_funnel_l(cw1, cw0, 2u * (h0 & 15u)) ^ (after ? p->pat_b : p->pat_a);
     win &= (win << 1) | 0x55555555u;
     const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
     const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr);
@@ -2122,6 +2140,7 @@ E1_HD void e1_ev_run64(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1
         const uint32_t E1 = (n0c + 1u) * dF;
         uint32_t krel = e1_ev_first(Fa, dF, e1_bits_float(p->ev_rcp_f));
         uint32_t F = dF - 1u - (Fa + krel * dF), wn = win; /* complement of the post-carry value (e1_ev_step) */
+        E1_UNROLL(E1_EV_UNROLL)
         for (uint32_t i = 1; i < nmax; i++) {
 #if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
             if (krel > last) /* an unguarded iteration without an event: must not happen */
@@ -2147,6 +2166,7 @@ E1_HD void e1_ev_run64(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1
         const uint64_t C = (uint64_t)Fa - (uint64_t)dF; /* chip field of the sample before: high word of (k - 1) dF + Fa */
         uint32_t krel = e1_ev_first(Ga, dG, e1_bits_float(p->ev_rcp_g));
         uint32_t G = dG - 1u - (Ga + krel * dG);
+        E1_UNROLL(E1_EV_UNROLL)
         for (uint32_t i = 1; i < nmax; i++) {
 #if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
             if (krel > last)

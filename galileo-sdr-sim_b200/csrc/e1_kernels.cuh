@@ -1054,9 +1054,12 @@ __global__ void __launch_bounds__(TEAMS *E1_EV_TEAM_THREADS, 1) e1_synth_ev_kern
             for (int a = 0; a < nact; a++) {
                 const uint32_t want = E1_PAR_EV | E1_PAR_CLEAN;
                 const int jw = par[a].j_w;
-                if ((par[a].misc & want) == want && n == RUN && !(jw > j0 && jw < j0 + RUN))
-                    e1_ev_run64(&par[a], A.codes, (e1_sptr)(size_t)lut1_s, j0, (e1_dptr)(size_t)col, tc_cw, lim_cw);
-                else
+                if ((par[a].misc & want) == want && n == RUN && !(jw > j0 && jw < j0 + RUN)) {
+                    uint64_t H;
+                    uint32_t w0, w1;
+                    e1_ev_fetch(&par[a], A.codes, j0, &H, &w0, &w1);
+                    e1_ev_run64(&par[a], H, w0, w1, (e1_sptr)(size_t)lut1_s, j0, (e1_dptr)(size_t)col, tc_cw, lim_cw);
+                } else
                     e1_ev_rest(&par[a], lut1_s, A.codes, lut_lane_g, j0, n, col, A.thr_carr, A.thr_code, A.tc_code, &n_exact);
             }
             /* running sum of the column = the samples; a6 + sink format (:536-537); the column is left zeroed */

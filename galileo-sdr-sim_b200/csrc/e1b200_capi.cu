@@ -41,7 +41,8 @@ struct e1b200_ctx {
     cudaStream_t side_stream;            /* planner: the code-phase pass runs here, beside the carrier chain */
     cudaEvent_t ev_fork, ev_join;
     std::vector<cudaEvent_t> ev_buf, ev_copy; /* per staging slot: synthesis done / D2H done */
-    std::vector<cudaEvent_t> ev;   /* pairs (start, end) of the current call */
+    std::vector<cudaEvent_t> ev;   /* pairs (start, end) of the current call (borrowed from ev_pool) */
+    std::vector<cudaEvent_t> ev_pool; /* every timing event this context ever created */
     std::vector<int> ev_kind;      /* 0 = planner pass, 1 = synthesis launch */
     uint32_t *d_codes;
     int32_t *d_lut;
@@ -288,7 +289,7 @@ int e1b200_destroy(e1b200_ctx *ctx)
     cudaFree(ctx->d_recs);
     cudaFree(ctx->d_ranges);
     cudaFree(ctx->d_stage);
-    for (cudaEvent_t ev : ctx->ev)
+    for (cudaEvent_t ev : ctx->ev_pool)
         cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_buf)
         cudaEventDestroy(ev);
@@ -384,10 +385,17 @@ static int ensure_plan_scratch(e1b200_ctx *ctx)
     return E1B200_OK;
 }
 
+/* timing marks of a call: the events are created once and reused call after call (ev_pool), so the real-time call
+   shape pays no cudaEventCreate / cudaEventDestroy per block */
 static int mark(e1b200_ctx *ctx, int kind, int end)
 {
     cudaEvent_t ev;
-    CK(cudaEventCreate(&ev));
+    if (ctx->ev.size() < ctx->ev_pool.size()) {
+        ev = ctx->ev_pool[ctx->ev.size()];
+    } else {
+        CK(cudaEventCreate(&ev));
+        ctx->ev_pool.push_back(ev);
+    }
     ctx->ev.push_back(ev);
     if (!end)
         ctx->ev_kind.push_back(kind);
@@ -397,8 +405,6 @@ static int mark(e1b200_ctx *ctx, int kind, int end)
 
 static void reset_call(e1b200_ctx *ctx)
 {
-    for (cudaEvent_t ev : ctx->ev)
-        cudaEventDestroy(ev);
     ctx->ev.clear();
     ctx->ev_kind.clear();
     memset(&ctx->timing, 0, sizeof ctx->timing);
@@ -412,13 +418,43 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
     if (rc)
         return rc;
     const int nthr = n * cfg->max_chan;
-    const int n_units = n * ctx->geo.spans_per_epoch, nuthr = n_units * cfg->max_chan;
+    /* Span geometry of this pass.  A span is walked by ONE thread: the create-time geometry (8 tiles or more per span)
+       is what a large pass wants, but a pass of a few blocks -- the real-time call shape, one 0.1 s block per call --
+       has far fewer spans than the GPU has lanes and then the walk of one 65 536-sample span is its latency (0.5 ms).
+       Such a pass (up to E1B200_SMALL_PASS = 8 blocks) gets shorter spans, down to one tile, as long as they fit the scratch. */
+    e1_span_geo geo = ctx->geo;
+    {
+        const long cap = (long)ctx->plan_epochs * ctx->geo.spans_per_epoch; /* units per channel the scratch holds */
+        long units = (long)n * geo.spans_per_epoch * cfg->max_chan;
+        const long fill = (long)ctx->sm_count * 128;
+        const int small_max = env_int("E1B200_SMALL_PASS", 8); /* blocks; larger passes keep the long spans (their reach back to a
+                                                                 wrap to anchor on -- 64 spans -- matters at low Doppler) */
+        while (geo.span_tiles > 1 && n <= small_max && units < fill && !env_int("E1B200_COARSE_SPANS", 0)) {
+            const int st = (geo.span_tiles + 1) / 2, sp = (ctx->tiles_per_epoch + st - 1) / st;
+            if ((long)n * sp > cap)
+                break;
+            geo.span_tiles = st;
+            geo.spans_per_epoch = sp;
+            units = (long)n * sp * cfg->max_chan;
+        }
+    }
+    const int n_units = n * geo.spans_per_epoch, nuthr = n_units * cfg->max_chan;
     ctx->plan_n = n_units;
+    const bool small_pass = geo.span_tiles != ctx->geo.span_tiles;
     /* The code-phase pass writes the code fields of the tile checkpoints, the carrier passes only .phi:
        the two are independent until finalize.  With the parallel planner it runs on a side stream,
        released when the span pass is done, so that it fills the SMs the carrier chain (one block per
        channel) leaves idle. */
     const bool code_beside_chain = !carrier_only && !ctx->serial_planner;
+    if (code_beside_chain && small_pass) {
+        /* a small pass is a chain of short dependent kernels: the code-phase pass (one thread per block and channel, the
+           longest of them) runs beside ALL of the carrier passes, not just beside the chain */
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        e1_plan_code_kernel<<<(nthr + 31) / 32, 32, 0, ctx->side_stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
+                                                                         ctx->tile, ctx->tiles_per_epoch, ctx->delt);
+        CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    }
     if (carrier_only) {
         e1_validate_carrier_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(d_recs, nthr, ctx->delt, ctx->d_counters);
         ctx->timing.kernel_launches += 1;
@@ -451,7 +487,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         P.max_chan = cfg->max_chan;
         P.tile = ctx->tile;
         P.tiles_per_epoch = ctx->tiles_per_epoch;
-        P.geo = ctx->geo;
+        P.geo = geo;
         P.n_units = n_units;
         const int cb = cfg->max_chan; /* one channel per block */
         e1_v2_prep_kernel<<<(nthr + 127) / 128, 128, 0, ctx->stream>>>(P);
@@ -459,7 +495,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         e1_v2_drift_kernel<<<(nuthr + 63) / 64, 64, 0, ctx->stream>>>(P);
         e1_v2_estimate_kernel<<<cb, E1_SERIAL_THREADS, 0, ctx->stream>>>(P);
         e1_v2_span_kernel<<<(nuthr + 63) / 64, 64, 0, ctx->stream>>>(P);
-        if (code_beside_chain) {
+        if (code_beside_chain && !small_pass) {
             CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
             e1_plan_code_kernel<<<(nthr + 127) / 128, 128, 0, ctx->side_stream>>>(d_recs, ctx->d_ck, n, cfg->max_chan, cfg->samples_per_epoch,
@@ -477,7 +513,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
         F.ck = ctx->d_ck;
         F.delta = ctx->d_delta;
         F.delta_stride = n_units;
-        F.geo = ctx->geo;
+        F.geo = geo;
         F.blk = ctx->d_blk;
         F.counters = ctx->d_counters;
         F.delt = ctx->delt;
@@ -652,7 +688,12 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
     CK(cudaSetDevice(ctx->cfg.device));
     int rc = ensure_plan_scratch(ctx);
     if (!rc)
-        rc = ensure_staging(ctx, ranges != nullptr, n_epochs ? (n_epochs + ctx->batch_epochs - 1) / ctx->batch_epochs + 8 : 0);
+    {
+        /* ring slots: a job of many slices wants the kernels far ahead of the copies; a call of one or two slices (the
+           real-time shape) gets one spare slot, not eight (a slot is E1B200_BATCH_MB of device memory) */
+        const int slices = n_epochs ? (n_epochs + ctx->batch_epochs - 1) / ctx->batch_epochs : 0;
+        rc = ensure_staging(ctx, ranges != nullptr, slices ? (slices <= 2 ? slices + 1 : slices + 8) : 0);
+    }
     if (rc)
         return rc;
     reset_call(ctx);
@@ -897,6 +938,10 @@ int e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out)
     out->sm_count = ctx->sm_count;
     out->ctas_per_sm = ctx->ctas_per_sm;
     out->smem_bytes = ctx->smem_bytes;
+    out->synth_kernel = ctx->float_path ? E1B200_KERNEL_FLOAT
+                        : ctx->evk      ? (E1B200_KERNEL_EV | (ctx->evk << 8))
+                        : ctx->pair     ? (ctx->quad ? E1B200_KERNEL_CW4 : E1B200_KERNEL_CW2)
+                                        : E1B200_KERNEL_RUN;
     return E1B200_OK;
 }
 

@@ -44,7 +44,13 @@ class Stats(C.Structure):
     _fields_ = [("exact_samples", C.c_uint64), ("planner_errors", C.c_uint64), ("serial_epochs", C.c_uint64),
                 ("hat_epochs", C.c_uint64), ("tile", C.c_int32), ("tiles_per_epoch", C.c_int32),
                 ("batch_epochs", C.c_int32), ("plan_epochs", C.c_int32), ("sm_count", C.c_int32),
-                ("ctas_per_sm", C.c_int32), ("smem_bytes", C.c_int32)]
+                ("ctas_per_sm", C.c_int32), ("smem_bytes", C.c_int32), ("synth_kernel", C.c_int32)]
+
+    @property
+    def kernel_name(self):
+        k, teams = self.synth_kernel & 0xff, self.synth_kernel >> 8
+        return {0: "e1_synth_kernel<R>", 1: "e1_synth_cw_kernel<2,2>", 2: "e1_synth_cw_kernel<4,3>", 3: "e1_synth_float_kernel",
+                4: f"e1_synth_ev_kernel<{teams}>"}.get(k, "?")
 
 
 SYMBOLS = [

@@ -189,7 +189,13 @@ typedef struct e1b200_stats {
     int32_t batch_epochs;      /* epochs per D2H staging slice (host entry points)                */
     int32_t plan_epochs;       /* epochs per planner pass                                         */
     int32_t sm_count, ctas_per_sm, smem_bytes;
+    int32_t synth_kernel;      /* which sample-loop kernel this context launches: E1B200_KERNEL_*  */
 } e1b200_stats;
+#define E1B200_KERNEL_RUN 0    /* e1_synth_kernel<R>: tiles shorter than 8192 samples (fs < ~2.2 MS/s)           */
+#define E1B200_KERNEL_CW2 1    /* e1_synth_cw_kernel<2,2>: carry-walked runs, 32 samples per thread              */
+#define E1B200_KERNEL_CW4 2    /* e1_synth_cw_kernel<4,3>: carry-walked runs, 64 samples per thread (default)    */
+#define E1B200_KERNEL_FLOAT 3  /* e1_synth_float_kernel: E1B200_CFG_CBOC / _GAIN                                 */
+#define E1B200_KERNEL_EV 4     /* e1_synth_ev_kernel<teams>: event-driven, fs >= 10 MS/s; teams = synth_kernel >> 8 */
 int  e1b200_get_stats(e1b200_ctx *ctx, e1b200_stats *out);
 void *e1b200_stream(e1b200_ctx *ctx);          /* cudaStream_t the context launches on           */
 const char *e1b200_last_error(e1b200_ctx *ctx);

@@ -146,9 +146,12 @@ static void ev_tile(const e1_chan_par *par, int nact, const uint32_t *codes, con
         for (int a = 0; a < nact; a++) {
             const uint32_t want = E1_PAR_EV | E1_PAR_CLEAN;
             if ((par[a].misc & want) == want) {
-                if (n == RUN && !(par[a].j_w > j0 && par[a].j_w < j0 + RUN)) // the kernel's inline form
-                    e1_ev_run64(&par[a], codes, e1_sp(lut1), j0, diff, e1_tc_carr_cw(thr_carr, RUN), e1_lim_carr_cw(thr_carr, RUN));
-                else
+                if (n == RUN && !(par[a].j_w > j0 && par[a].j_w < j0 + RUN)) { // the kernel's inline form
+                    uint64_t H;
+                    uint32_t w0, w1;
+                    e1_ev_fetch(&par[a], codes, j0, &H, &w0, &w1);
+                    e1_ev_run64(&par[a], H, w0, w1, e1_sp(lut1), j0, diff, e1_tc_carr_cw(thr_carr, RUN), e1_lim_carr_cw(thr_carr, RUN));
+                } else
                     e1_ev_add<false>(&par[a], codes, e1_sp(lut1), j0, n, diff, 1, thr_carr, lim_code);
                 g_ev_pairs++;
                 // beside it: the same events with the tracking on must not flag anything, and the generic form must give the same terms

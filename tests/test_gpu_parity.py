@@ -130,6 +130,28 @@ def test_device_entry_and_call_splitting():
     s.close(), s2.close()
 
 
+def test_real_time_call_shape_short_spans(monkeypatch):
+    """One 0.1 s block per call (what the patched galileo_task() hands over, tests/test_dropin.py) and calls of a few
+    blocks: such passes are planned with spans of one tile instead of eight (e1b200_capi.cu, enqueue_plan) so that a call
+    costs a quarter of a millisecond instead of one.  Same bytes as the oracle, as one large call, and as the long spans;
+    low Dopplers included (no carrier wrap within reach of a short span: the chain walks those)."""
+    from test_core_hostsim import low_doppler_recs
+    for fs, n_samp, recs in ((FS26, 260000, U.synthetic_recs(9, 7, FS26, seed=21, max_chan=16)),
+                             (FS25, 2500000, U.synthetic_recs(3, 5, FS25, seed=22, max_chan=8)),
+                             (FS26, 65536 * 2 + 1000, low_doppler_recs(9, FS26))):
+        ref, ph = U.oracle_synth(fs, n_samp, recs, threads=8)
+        s = E.Synth(fs, n_samp, recs.shape[1])
+        parts = [s.synth_epochs(recs[i:i + 1]) for i in range(3)] + [s.synth_epochs(recs[3:5])] + [s.synth_epochs(recs[5:])]
+        assert np.array_equal(np.concatenate(parts), ref) and np.array_equal(s.carrier_phases(), ph)
+        s.close()
+        monkeypatch.setenv("E1B200_COARSE_SPANS", "1")
+        s = E.Synth(fs, n_samp, recs.shape[1])
+        parts = [s.synth_epochs(recs[i:i + 1]) for i in range(recs.shape[0])]
+        assert np.array_equal(np.concatenate(parts), ref) and np.array_equal(s.carrier_phases(), ph)
+        s.close()
+        monkeypatch.delenv("E1B200_COARSE_SPANS")
+
+
 def test_internal_batching_and_no_tma_path(monkeypatch):
     """Small internal batches exercise the double-buffered D2H pipeline; E1B200_NO_TMA loads the
     tables with plain loads instead of cp.async.bulk.  Same bytes either way."""
