@@ -50,6 +50,7 @@ def load():
         lib.e1h_page_symbols.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
         lib.e1h_crc24q_bits.argtypes = [C.c_void_p, C.c_int]
         lib.e1h_crc24q_bits.restype = C.c_uint
+        lib.e1h_encode_page.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 

@@ -906,4 +906,19 @@ int e1h_page_symbols(const e1h_scenario *s, int prn, double grx_sec, int week, i
 
 unsigned int e1h_crc24q_bits(const int *bits, int length) { return crc24q_bits(bits, length); }
 
+/* The channel coding of a page on its own (what page_symbols does after the word is laid out): two half pages of
+   114 bits -> 6 tail zeros, rate-1/2 code, 30 x 8 interleaver, sync pattern -> 500 symbols.  For the tests that push
+   live-sky pages (the reference's tv/ vectors) through this encoder and the receiver stand-in's decoder. */
+int e1h_encode_page(const int *even114, const int *odd114, int *symbols500)
+{
+    if (!even114 || !odd114 || !symbols500)
+        return -1;
+    int even[120] = {0}, odd[120] = {0};
+    memcpy(even, even114, 114 * sizeof(int));
+    memcpy(odd, odd114, 114 * sizeof(int));
+    half_page_symbols(even, symbols500);
+    half_page_symbols(odd, symbols500 + 250);
+    return 0;
+}
+
 } /* extern "C" */

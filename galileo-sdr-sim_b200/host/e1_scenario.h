@@ -69,6 +69,7 @@ int e1h_ecef_to_llh_deg(const double *xyz, double *llh_deg);
 /* Pieces exposed for the tests. */
 int e1h_page_symbols(const e1h_scenario *s, int prn, double grx_sec, int week, int *symbols500);
 unsigned int e1h_crc24q_bits(const int *bits, int length);
+int e1h_encode_page(const int *even114, const int *odd114, int *symbols500); /* tails + FEC + interleaver + sync */
 
 #ifdef __cplusplus
 }

@@ -77,11 +77,15 @@ def acquire(x, prn, fs, periods=4, f_max=5000.0, f_step=125.0, cboc=None, raw=Fa
     return peak / (total / cells), fd, code_phase % CODE_LEN
 
 
-def track(x, prn, fs, doppler, code_phase, n_periods, spacing=0.25, bn_pll=25.0, bn_dll=2.0):
+def track(x, prn, fs, doppler, code_phase, n_periods, spacing=0.25, bn_pll=25.0, bn_dll=2.0, pilot=False):
     """Code/carrier tracking from the acquisition estimate.  Returns the complex prompt of every whole
     code period (= I/NAV symbol) after sample `start`, the carrier frequency and code phase histories,
-    and `start` (the sample at which the first whole code period begins)."""
-    hc = halfchips(prn)
+    and `start` (the sample at which the first whole code period begins).
+    pilot=True: the loops run on the E1-C (pilot) replica, as GNSS-SDR does with the bundled configuration
+    (gnss-sdr_Galileo_E1_ishort.conf:60, track_pilot=true); a fifth return value holds the E1-B (data) prompts
+    taken with the same code and carrier NCOs (see pilot_symbols)."""
+    hc = halfchips(prn, 1 if pilot else 0)
+    hc_data = halfchips(prn, 0) if pilot else None
     n = int(round(fs * CODE_LEN / F_CODE))
     T = n / fs
     # second-order loop coefficients (natural frequency from the noise bandwidth, damping 0.707)
@@ -100,6 +104,7 @@ def track(x, prn, fs, doppler, code_phase, n_periods, spacing=0.25, bn_pll=25.0,
     sq = np.array(pr) ** 2
     fd += float(np.angle(np.sum(sq[1:] * np.conj(sq[:-1])))) / (2.0 * 2.0 * np.pi * (q / fs))
     prompts = np.zeros(n_periods, np.complex128)
+    data_prompts = np.zeros(n_periods, np.complex128)
     f_hist, cp_hist = np.zeros(n_periods), np.zeros(n_periods)
     f_int = fd
     # integrate over whole code periods (= symbols): start at the first sample after the next code
@@ -122,6 +127,8 @@ def track(x, prn, fs, doppler, code_phase, n_periods, spacing=0.25, bn_pll=25.0,
         pm = np.vdot(replica(hc, m, fs, cp, f_code), base)
         l = np.vdot(replica(hc, m, fs, cp - spacing, f_code), base)
         prompts[p], f_hist[p], cp_hist[p] = pm, fd, cp
+        if pilot:
+            data_prompts[p] = np.vdot(replica(hc_data, m, fs, cp, f_code), base)
         done = p + 1
         # Costas discriminator (insensitive to the symbol sign), loop filter
         err = np.arctan(pm.imag / pm.real) / (2.0 * np.pi) if pm.real != 0.0 else 0.0
@@ -134,7 +141,37 @@ def track(x, prn, fs, doppler, code_phase, n_periods, spacing=0.25, bn_pll=25.0,
         d = 0.5 * (ae - al) / (ae + al) if ae + al > 0 else 0.0
         cp = cp + m * f_code / fs - CODE_LEN + 1.414 * wn_d * T * d
         pos += m
+    if pilot:
+        return prompts[:done], f_hist[:done], cp_hist[:done], start, data_prompts[:done]
     return prompts[:done], f_hist[:done], cp_hist[:done], start
+
+
+SEC25 = np.array([int(c) for c in "0011100000001010110110010"], np.int8)   # Galileo OS SIS ICD, E1-C secondary code CS25_1
+
+
+def pilot_symbols(pilot_prompts, data_prompts, skip=75):
+    """Secondary-code synchronisation on the pilot and pilot-aided data demodulation.
+    The E1 composite is e_B(t) d - e_C(t) s (ICD: the pilot enters with a minus sign; src/galileo-sdr.cpp:520), so after
+    correlation the pilot prompt is -s e^(j theta) and the data prompt d e^(j theta), with s = +-1 the secondary-code chip
+    (bit 1 -> -1) and d the I/NAV symbol (bit 1 -> -1): the Costas loop leaves theta ambiguous by pi, the secondary code
+    -- a KNOWN sequence -- removes that ambiguity, and the data symbols come out with their absolute sign.
+    -> (page bits (0/1, absolute), secondary-code phase of symbol 0 (0..24), fraction of the pilot prompts after `skip`
+        that agree with the aligned secondary code)."""
+    ps = (pilot_prompts.real < 0).astype(np.int8)               # sign bit of -s e^(j theta), theta in {0, pi}
+    n = len(ps)
+    best = (-1.0, 0, 0)
+    for shift in range(25):
+        exp = SEC25[(np.arange(n) + shift) % 25]                # bit 1 -> s = -1 -> pilot prompt -s = +1 -> sign bit 0 (theta = 0)
+        agree = float(((1 - exp)[skip:] == ps[skip:]).mean())
+        for inv, a in ((0, agree), (1, 1.0 - agree)):
+            if a > best[0]:
+                best = (a, shift, inv)
+    agree, shift, inv = best
+    # wipe the secondary code off the pilot: what is left is the carrier phase, e^(j theta) without ambiguity
+    s = 1.0 - 2.0 * SEC25[(np.arange(n) + shift) % 25]
+    carrier = -pilot_prompts * s
+    d = (data_prompts * np.conj(carrier)).real
+    return (d < 0).astype(np.int8), shift, agree
 
 
 def symbols_from_prompts(prompts):

@@ -91,10 +91,62 @@ def check_stream(iq, recs):
     return found
 
 
+def sent_bits(recs, slot, start, n_sym):
+    """Page bit (0/1) and page symbol index of the receiver's symbols k = 0 .. n_sym-1 (code periods from sample `start`)."""
+    bits_in = np.unpackbits(recs[:, slot]["page_cur"], axis=-1, bitorder="little")[:, :500]
+    nxt_in = np.unpackbits(recs[:, slot]["page_next"], axis=-1, bitorder="little")[:, :500]
+    sent, idx = [], []
+    for k in range(n_sym):
+        mid = start + k * 10400 + 5200
+        e = mid // N
+        r = recs[e, slot]
+        wraps = int(np.floor((r["code_phase0"] + (mid - e * N) * r["f_code"] / FS) / 4092.0))
+        j = int(r["ibit0"]) + wraps
+        sent.append(nxt_in[e, j - 500] if j >= 500 else bits_in[e, j])
+        idx.append(j % 500)
+    return np.array(sent, np.int8), np.array(idx)
+
+
+def check_pilot(iq, recs, found, prns=None):
+    """What GNSS-SDR does with the bundled configuration (track_pilot=true): the loops run on E1-C.  The pilot must carry
+    the 25-chip secondary code, aligned to the page symbols (symbol index mod 25), with the ICD's sign (the composite is
+    e_B d - e_C s); wiping it off resolves the carrier's half-cycle ambiguity, so the data symbols demodulated with the
+    pilot's carrier must equal the page bits that went in ABSOLUTELY, not just up to a global sign -- a sign or
+    secondary-code error in the E1-C half of the generator cannot hide here -- and the pages must still decode."""
+    x = iq[:, 0].astype(np.float32) + 1j * iq[:, 1].astype(np.float32)
+    n_periods = len(x) // 10400
+    for slot, prn in enumerate(recs[0]["prn"]):
+        prn = int(prn)
+        if prn <= 0 or (prns is not None and prn not in prns):
+            continue
+        fd, cp = found[prn] if found else (float(recs[0, slot]["f_carr"]), float(recs[0, slot]["code_phase0"]))
+        pp, f_hist, cp_hist, start, dp = RX.track(x, prn, FS, fd, cp, n_periods, pilot=True)
+        assert len(pp) >= n_periods - 2
+        amp = np.abs(pp[25:])
+        assert amp.min() > 0.7 * amp.mean(), (prn, amp.min(), amp.mean())           # pilot stays in lock
+        f_true = np.repeat(recs[:, slot]["f_carr"], 25)[:len(f_hist)]
+        assert np.abs(f_hist[75:] - f_true[75:]).max() < 5.0, prn
+        bits, shift, agree = RX.pilot_symbols(pp, dp)
+        assert agree == 1.0, (prn, agree)                                            # every pilot prompt is a secondary-code chip
+        sent, idx = sent_bits(recs, slot, start, len(bits))
+        assert shift == idx[0] % 25, (prn, shift, idx[0])                            # ... aligned to the page symbols
+        assert np.array_equal(bits[75:], sent[75:]), (prn, float((bits[75:] == sent[75:]).mean()))   # absolute polarity
+        pages, info = RX.decode_pages(bits)
+        assert not info["inverted"] and info["sync_quality"] == 10.0 and len(pages) >= 1, (prn, info)
+        for pg in pages:
+            assert pg["crc_ok"] and pg["channel_errors"] == 0 and pg["tails_zero"], (prn, pg["start"], pg["word_type"])
+
+
 def test_receiver_acquires_tracks_and_decodes_oracle_stream():
     recs, _ = scenario_records()
     iq, _ = U.oracle_synth(FS, N, recs, threads=8)
     check_stream(iq, recs)
+
+
+def test_pilot_tracking_secondary_code_and_absolute_symbols_oracle_stream():
+    recs, _ = scenario_records()
+    iq, _ = U.oracle_synth(FS, N, recs, threads=8)
+    check_pilot(iq, recs, None)
 
 
 @pytest.mark.gpu
@@ -104,4 +156,5 @@ def test_receiver_acquires_tracks_and_decodes_cuda_stream():
     s = E.Synth(FS, N, 16)
     iq = s.synth_epochs(recs)
     s.close()
-    check_stream(iq, recs)
+    found = check_stream(iq, recs)
+    check_pilot(iq, recs, found)
