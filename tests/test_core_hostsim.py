@@ -466,3 +466,58 @@ def test_records_with_carrier_fields_outside_the_contract_are_rejected():
     ok = good.copy()                                               # an out-of-range init without the flag is never read
     ok[1, 1]["carr_phase_init"] = 7.0
     U.hostsim_synth(fs, n, ok)
+
+
+# ------------------------------------------------------------------ event-driven runs (fs >= 10 MS/s)
+def ev_edge_recs(fs, n_epochs=4):
+    """Everything the event-driven form has to get right in one input: Dopplers of both signs against phases of both
+    signs (all four table walks), zero and near-zero Doppler (no carrier event in a thread's samples), a Doppler that
+    changes sign (the phase runs through zero: generic form), a step of one table entry per sample and beyond (not
+    E1_PAR_SLOW: generic form), a phase reset, an idle slot, the code wrap inside a thread's samples (every block)."""
+    freqs = [3900.0, -3900.0, 2500.0, -2500.0, 0.0, 0.37, -12.0, 900.0, -900.0, fs / 511.0 * 0.98, -fs / 511.0 * 1.02, 11000.0]
+    recs = U.synthetic_recs(n_epochs, len(freqs), fs, seed=77, max_chan=len(freqs) + 1)
+    for c, f in enumerate(freqs):
+        recs[:, c]["f_carr"] = f
+        recs[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+        recs[0, c]["carr_phase_init"] = (0.11 + 0.07 * c) * (1 if c % 3 else -1)
+    for e in range(n_epochs):
+        recs[e, 7]["f_carr"] = (1.5 - e) * 600.0
+        recs[e, 7]["f_code"] = 1.023e6 + recs[e, 7]["f_carr"] * 0.0006493506493506494
+    recs[2, 2]["flags"] = U.E1_REC_SET_PHASE
+    recs[2, 2]["carr_phase_init"] = -0.9999999
+    recs[1:3, 3]["prn"] = 0
+    return recs
+
+
+@pytest.mark.parametrize("fs0,n_samp", [(25e6, 250000), (10.2e6, 102000), (16e6, 70001), (50e6, 200000)])
+def test_event_driven_form_matches_oracle(fs0, n_samp):
+    """e1_ev_run64 / e1_ev_sub / e1_ev_rest_impl through the host build, as e1_synth_ev_kernel drives them: bit-identical to
+    the oracle; the lean form really is what most (thread, channel) pairs take and the out-of-line forms are exercised too."""
+    hs = U.hostsim()
+    fs = U.fs_as_reference(fs0)
+    p0, r0 = hs.hs_ev_pairs(), hs.hs_ev_rest()
+    recs = ev_edge_recs(fs)
+    a, pa = U.oracle_synth(fs, n_samp, recs, threads=8)
+    b, pb, st = U.hostsim_synth(fs, n_samp, recs)          # asserts: no lookup outside the tables, no clean-tile violation
+    assert np.array_equal(a, b) and np.array_equal(pa, pb), (st, int((a != b).any(1).sum()))
+    ev, rest = hs.hs_ev_pairs() - p0, hs.hs_ev_rest() - r0
+    assert ev > rest > 0, (ev, rest)
+
+
+def test_event_driven_and_per_sample_forms_write_the_same_stream():
+    """The same 25 MS/s input through the event-driven kernel's functions and through the carry-walked ones (hs_set_ev_mode)."""
+    hs = U.hostsim()
+    fs, n_samp = FS25, 180000
+    recs = U.synthetic_recs(3, 9, fs, seed=5, max_chan=10)
+    try:
+        hs.hs_set_ev_mode(0)
+        a, pa, _ = U.hostsim_synth(fs, n_samp, recs)
+        hs.hs_set_ev_mode(1)
+        p0 = hs.hs_ev_pairs()
+        b, pb, _ = U.hostsim_synth(fs, n_samp, recs)
+        assert hs.hs_ev_pairs() > p0
+    finally:
+        hs.hs_set_ev_mode(-1)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb)
+    ref, _ = U.oracle_synth(fs, n_samp, recs, threads=8)
+    assert np.array_equal(a, ref)

@@ -152,6 +152,43 @@ def test_real_time_call_shape_short_spans(monkeypatch):
         monkeypatch.delenv("E1B200_COARSE_SPANS")
 
 
+def test_event_driven_kernel_edges_and_team_counts(monkeypatch):
+    """e1_synth_ev_kernel (fs >= 10 MS/s) on the input of tests/test_core_hostsim.py::ev_edge_recs -- all four table walks,
+    zero Doppler, sign changes, steps beyond the carry walk, phase reset, idle slot, code wraps inside a thread's samples,
+    ragged last tile -- at several rates, with 64 slots (fewer teams fit the shared memory), with 2 and 3 teams forced, and
+    against the carry-walked kernel (E1B200_NO_EV): always the oracle's bytes."""
+    from test_core_hostsim import ev_edge_recs
+    for fs0, n_samp in ((25e6, 250000), (10.2e6, 102000), (16e6, 70001)):
+        fs = U.fs_as_reference(fs0)
+        recs = ev_edge_recs(fs)
+        ref, ph = U.oracle_synth(fs, n_samp, recs, threads=8)
+        for env in ({}, {"E1B200_EV_TEAMS": "2"}, {"E1B200_EV_TEAMS": "3"}, {"E1B200_NO_EV": "1"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            s = E.Synth(fs, n_samp, recs.shape[1])
+            want = "e1_synth_cw_kernel<4,3>" if "E1B200_NO_EV" in env else "e1_synth_ev_kernel<%s>" % env.get("E1B200_EV_TEAMS", "5")
+            assert s.stats().kernel_name == want, (s.stats().kernel_name, want)
+            out = s.synth_epochs(recs)
+            assert np.array_equal(out, ref) and np.array_equal(s.carrier_phases(), ph), (fs0, env, int((out != ref).any(1).sum()))
+            s.close()
+            for k in env:
+                monkeypatch.delenv(k)
+    fs = FS25
+    recs = U.synthetic_recs(2, 64, fs, seed=9, max_chan=64)
+    ref, ph = U.oracle_synth(fs, 300000, recs, threads=8)
+    s = E.Synth(fs, 300000, 64)
+    assert s.stats().kernel_name.startswith("e1_synth_ev_kernel<") and s.stats().kernel_name != "e1_synth_ev_kernel<5>"
+    out = s.synth_epochs(recs)
+    assert np.array_equal(out, ref) and np.array_equal(s.carrier_phases(), ph)
+    h = [hashlib.sha256(s.synth_epochs(recs[:0]).tobytes()).hexdigest()]       # and repeated runs are bit-identical
+    s.set_carrier_phases(np.zeros(64))
+    a = s.synth_epochs(recs)
+    s.set_carrier_phases(np.zeros(64))
+    b = s.synth_epochs(recs)
+    assert np.array_equal(a, b) and np.array_equal(a, ref), h
+    s.close()
+
+
 def test_internal_batching_and_no_tma_path(monkeypatch):
     """Small internal batches exercise the double-buffered D2H pipeline; E1B200_NO_TMA loads the
     tables with plain loads instead of cp.async.bulk.  Same bytes either way."""
