@@ -499,7 +499,7 @@ def main():
 
     # ---- strong-scaling arm (N > 1): ONE scenario of this size, time axis sharded over the N GPUs ----------------
     # rank 0's scenario (seed 1000) split into contiguous block ranges (shard.split_epochs).  Per step, timed:
-    #   hand-off  every rank runs the carrier planner over all blocks BEFORE its range (shard.replan_start_phases: no
+    #   hand-off  every rank runs the carrier planner over all blocks BEFORE its range (shard.replan_start_phases_device: no
     #             communication, no serial chain; the alternative, a plan-and-send chain over NCCL, is timed as handoff_chain_ms)
     #   synthesis of the rank's range, its kernel storing straight into rank 0's stream buffer over NVLink (peer memory,
     #             e1b200_peer_*): compute and gather are one kernel, there is no gather step
@@ -512,6 +512,7 @@ def main():
         ranges = S.split_epochs(n_epochs, world)
         lo, hi = ranges[rank]
         d_seg_recs = torch.from_numpy(np.ascontiguousarray(recs_all[lo:hi]).view(np.uint8).reshape(-1)).to(dev)
+        d_recs_all = d_recs if rank == 0 else torch.from_numpy(recs_all.view(np.uint8).reshape(-1)).to(dev)   # the whole scenario's records, resident
         handle = torch.zeros(64, dtype=torch.uint8, device=dev)
         full = None
         if rank == 0:
@@ -534,7 +535,8 @@ def main():
             if chain:
                 S.handoff_start_phases(seg_engine, recs_all, rank, world, dist, dist_device=dev)
             else:
-                S.replan_start_phases(seg_engine, recs_all, rank, world)
+                S.replan_start_phases_device(seg_engine, d_recs_all.data_ptr(), n_epochs, rank, world)
+                seg_engine.sync()                # only so that the hand-off can be timed apart from the synthesis
             t[1].record()
             if fused == "dma":       # slices by the copy engines over NVLink, behind the kernels (records from pinned host memory)
                 seg_engine.synth_epochs_to(seg_recs_view, full.ptr + lo * n_samp * 4)
@@ -606,7 +608,7 @@ def main():
         barrier()
         full.close()
         h_seg_recs.free()
-        del d_seg, d_full, d_seg_recs
+        del d_seg, d_full, d_seg_recs, d_recs_all
 
     # ---- the timed bytes against the oracle (after both timed regions) ---------------------
     parity = None

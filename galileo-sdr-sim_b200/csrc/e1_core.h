@@ -370,7 +370,11 @@ typedef struct e1_chan_par { /* 112 bytes, one per active channel of a tile (HBM
                              ev_* fields are filled in (e1_ev_add)                                                      */
 /* internal bit of the cfg_flags argument of e1_make_par (never in e1b200_config.flags): fill in the event fields */
 #define E1_INT_EV 0x40000000u
-#define E1C_EV_RUN 64 /* consecutive samples per thread of the event-driven kernel (= E1C_LUT_EXT: one carrier start) */
+#if !defined(E1C_EV_RUN)
+#define E1C_EV_RUN 64 /* consecutive samples per thread of the event-driven kernel, walked from ONE carrier start */
+#endif
+#define E1C_EV_EXT E1C_EV_RUN              /* ... so its (single-copy) carrier tables run out that many entries on either side */
+#define E1C_LUT1_IDX (514 + 2 * E1C_EV_EXT) /* entries of one of them (cf. E1C_LUT_IDX) */
 
 /* One tile's parameter block in HBM: header (16 bytes: n_active, 3 x pad) + max_chan e1_chan_par,
  * active channels first. */
@@ -1702,14 +1706,14 @@ E1_HD uint32_t e1_run_fast_pair(const e1_chan_par *p, const uint32_t *codes, con
  * floor(511 U / 2^32) (U: |phase|, 2^-64 cycle), entry in the high word, fraction in the low word.  up = the
  * unmirrored position increases (only then can a carrier wrap fall into the run).  Same layout rules as
  * e1_carrier_start. */
-E1_HD uint64_t e1_carrier_start_p(uint64_t U, uint32_t neg, uint32_t up, uint32_t tc_carr, uint32_t lim_carr)
+E1_HD uint64_t e1_carrier_start_p(uint64_t U, uint32_t neg, uint32_t up, uint32_t tc_carr, uint32_t lim_carr, uint32_t ext = E1C_LUT_EXT)
 {
     const uint64_t lo = (U & 0xffffffffull) * 511ull;
     const uint64_t y0 = (U >> 32) * 511ull + (lo >> 32) + tc_carr;
-    const uint64_t wrap = (up && (uint32_t)(y0 >> 32) >= 511u - E1C_LUT_EXT) ? (511ull << 32) : 0ull;
+    const uint64_t wrap = (up && (uint32_t)(y0 >> 32) >= 511u - ext) ? (511ull << 32) : 0ull;
     if (!neg)
-        return y0 + ((uint64_t)E1C_LUT_EXT << 32) - wrap;
-    return (((uint64_t)(513 + E1C_LUT_EXT) << 32) - 1ull) - y0 + wrap + lim_carr;
+        return y0 + ((uint64_t)ext << 32) - wrap;
+    return (((uint64_t)(513u + ext) << 32) - 1ull) - y0 + wrap + lim_carr;
 }
 
 /* One step of the carry-walked sample loop (see e1_sample_loop_cw), on one run's state. */
@@ -1970,7 +1974,7 @@ E1_HD void e1_ev_next(uint32_t &F, uint32_t &krel, uint32_t E0, uint32_t dF, uin
  * Both event loops run a trip count that is the same for every thread working on the channel (the most carries
  * E1C_EV_RUN - 1 steps can produce) and are straight-line inside: an iteration past the thread's last event adds zero to
  * the column's last entry.  lut1_s: the single-copy carrier table and its two difference tables (e1_build_lut1). */
-#define E1C_LUT1_WORDS ((E1C_LUT_IDX + 3) / 4 * 4)
+#define E1C_LUT1_WORDS ((E1C_LUT1_IDX + 3) / 4 * 4)
 template <bool CHECK>
 E1_HD uint32_t e1_ev_sub(const e1_chan_par *p, const uint32_t *codes, e1_sptr lut1_s, int ka, int kb, int j0, int after, int close, e1_dptr diff,
                          int scale, uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
@@ -1987,7 +1991,7 @@ E1_HD uint32_t e1_ev_sub(const e1_chan_par *p, const uint32_t *codes, e1_sptr lu
     win &= (win << 1) | 0x55555555u; /* fields are now y - x in two's complement (e1_code_window) */
     /* carrier side at ka: the table position of e1_run_cw, one start for the whole sub-range */
     const uint64_t U = p->U0 + (uint64_t)(uint32_t)ka * p->dU;
-    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr);
+    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr, E1C_EV_EXT);
     const uint32_t Ga = down ? ~(uint32_t)y : (uint32_t)y, dG = down ? 0u - Dlo : Dlo;
     const int sstep = down ? -4 : 4; /* bytes per entry of the single-copy table */
     const e1_sptr addr_a = lut1_s + 4u * (uint32_t)(y >> 32);
@@ -1996,7 +2000,7 @@ E1_HD uint32_t e1_ev_sub(const e1_chan_par *p, const uint32_t *codes, e1_sptr lu
 #if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
     {
         const int64_t last = (int64_t)(uint32_t)(y >> 32) + (down ? -1 : 1) * (int64_t)e1_hi_mad(kn - 1u, dG, Ga);
-        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT_IDX || last < 0 || last >= E1C_LUT_IDX)
+        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT1_IDX || last < 0 || last >= E1C_LUT1_IDX)
             e1_lut_oob++;
     }
 #endif
@@ -2120,7 +2124,7 @@ E1_HD void e1_ev_run64(const e1_chan_par *p, uint64_t H, uint32_t cw0, uint32_t 
     uint32_t win = e1_funnel_l(cw1, cw0, 2u * (h0 & 15u)) ^ (after ? p->pat_b : p->pat_a);
     win &= (win << 1) | 0x55555555u;
     const uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * p->dU;
-    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr);
+    const uint64_t y = e1_carrier_start_p(U, neg, neg ? (down || Dlo == 0u) : !down, tc_carr, lim_carr, E1C_EV_EXT);
     const uint32_t Ga = down ? ~(uint32_t)y : (uint32_t)y, dG = down ? 0u - Dlo : Dlo;
     const int sstep = down ? -4 : 4;
     const e1_sptr addr_a = lut1_s + 4u * (uint32_t)(y >> 32);
@@ -2129,7 +2133,7 @@ E1_HD void e1_ev_run64(const e1_chan_par *p, uint64_t H, uint32_t cw0, uint32_t 
 #if !defined(__CUDA_ARCH__) && defined(E1_CHECK_LUT_BOUNDS)
     {
         const int64_t le = (int64_t)(uint32_t)(y >> 32) + (down ? -1 : 1) * (int64_t)e1_hi_mad(last, dG, Ga);
-        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT_IDX || le < 0 || le >= E1C_LUT_IDX)
+        if ((uint32_t)(y >> 32) >= (uint32_t)E1C_LUT1_IDX || le < 0 || le >= E1C_LUT1_IDX)
             e1_lut_oob++;
     }
 #endif
@@ -2244,19 +2248,25 @@ E1_HD void e1_ev_rest_impl(const e1_chan_par *p, e1_sptr lut1_s, const uint32_t 
  * half-chip (a thread's E1C_EV_RUN samples must cross fewer than 15 of them, e1_make_par). */
 E1_HD int e1_ev_context(double fs_hz, int run) { return run == E1C_MAX_RUN && fs_hz >= 10.0e6; }
 
-/* carrier tables of the event-driven kernel, 3 E1C_LUT1_WORDS words: entry E of e1_build_lut, once; behind it the
-   differences walking up, table[E] - table[E - 1]; behind those the differences walking down, table[E] - table[E + 1]
-   (a walk only arrives at an entry from a neighbour: the entries without one are 0 and never read) */
+/* carrier tables of the event-driven kernel, 3 E1C_LUT1_WORDS words: the table of e1_build_lut, one copy, with a run-out of
+   E1C_EV_EXT entries on either side (entry E = e + E1C_EV_EXT, same index map t(e)); behind it the differences walking up,
+   table[E] - table[E - 1]; behind those the differences walking down, table[E] - table[E + 1] (a walk only arrives at an
+   entry from a neighbour: the entries without one are 0 and never read).  lut: the replicated table (its entries
+   E1C_LUT_EXT .. E1C_LUT_EXT + 511 are the reference's 512 values). */
 E1_HD void e1_build_lut1(const int32_t *lut, int32_t *lut1)
 {
     for (int E = 0; E < 3 * E1C_LUT1_WORDS; E++)
         lut1[E] = 0;
-    for (int E = 0; E < E1C_LUT_IDX; E++) {
-        lut1[E] = lut[E * E1C_LUT_REP];
+    for (int E = 0; E < E1C_LUT1_IDX; E++) {
+        const int e = E - E1C_EV_EXT;
+        const int t = e < 0 ? 511 + e : (e <= 512 ? (e & 511) : e - 511);
+        lut1[E] = lut[(t + E1C_LUT_EXT) * E1C_LUT_REP];
+    }
+    for (int E = 0; E < E1C_LUT1_IDX; E++) {
         if (E)
-            lut1[E1C_LUT1_WORDS + E] = lut[E * E1C_LUT_REP] - lut[(E - 1) * E1C_LUT_REP];
-        if (E + 1 < E1C_LUT_IDX)
-            lut1[2 * E1C_LUT1_WORDS + E] = lut[E * E1C_LUT_REP] - lut[(E + 1) * E1C_LUT_REP];
+            lut1[E1C_LUT1_WORDS + E] = lut1[E] - lut1[E - 1];
+        if (E + 1 < E1C_LUT1_IDX)
+            lut1[2 * E1C_LUT1_WORDS + E] = lut1[E] - lut1[E + 1];
     }
 }
 

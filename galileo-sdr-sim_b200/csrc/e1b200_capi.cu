@@ -709,6 +709,16 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
     int chunk = env_int("E1B200_FIRST_PASS", 256);
     if (chunk < 1)
         chunk = 1;
+    {
+        /* a destination in DEVICE memory (this GPU's or a peer's, e1b200_peer_open) is fed over NVLink or HBM, an order
+           of magnitude faster than PCIe: there the kernels bound the call, not the copies, and every extra planner pass
+           (about 1 ms of dependent launches whatever its size) shows -- plan as much as the scratch holds at once */
+        cudaPointerAttributes pa;
+        if (out && cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeDevice)
+            chunk = ctx->plan_epochs;
+        else
+            (void)cudaGetLastError();
+    }
     for (int p0 = 0, np = 0; p0 < n_epochs; p0 += np) {
         np = chunk < ctx->plan_epochs ? chunk : ctx->plan_epochs;
         if (np > n_epochs - p0)

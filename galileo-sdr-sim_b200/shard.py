@@ -80,6 +80,19 @@ def replan_start_phases(engine, recs, rank, world, phases0=None):
     return lo, hi, start
 
 
+def replan_start_phases_device(engine, d_recs_ptr, n_epochs, rank, world, phases0=None):
+    """replan_start_phases with the scenario's records already on the rank's GPU (d_recs_ptr: device address of
+    e1_epoch_rec[n_epochs][max_chan]): the carrier-only planner runs over the blocks before the range straight from
+    there (e1b200_plan_phases_device) -- no H2D of up to the whole record set per step, no read-back of the phases:
+    they stay in the context, and the synthesis call that follows on the same stream starts from them.  Asynchronous;
+    returns (lo, hi)."""
+    lo, hi = split_epochs(n_epochs, world)[rank]
+    engine.set_carrier_phases(np.zeros(engine.max_chan) if phases0 is None else np.asarray(phases0, dtype=np.float64))
+    if lo > 0:
+        engine.plan_phases_device(lo, d_recs_ptr)
+    return lo, hi
+
+
 def synth_shard(engine, recs, rank, world, dist=None, phases0=None, dist_device="cpu", out=None):
     """This rank's segment of the scenario: (lo, hi, int16 [ (hi-lo)*N, 2 ])."""
     lo, hi, _ = handoff_start_phases(engine, recs, rank, world, dist, phases0, dist_device)

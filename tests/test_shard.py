@@ -74,7 +74,8 @@ def _rank_main(rank, world, port, n_samp, n_epochs, n_chan, max_chan, seed, path
             dist.broadcast(h, 0)
             if rank != 0:
                 full = E.PeerBuffer.open(0, h.numpy().tobytes(), nbytes)
-            lo, hi, _ = S.replan_start_phases(eng, recs, rank, world, phases0=phases0)
+            d_recs = torch.from_numpy(recs.view(np.uint8).reshape(-1)).cuda()       # the scenario's records, resident
+            lo, hi = S.replan_start_phases_device(eng, d_recs.data_ptr(), n_epochs, rank, world, phases0=phases0)
             if hi > lo:
                 eng.synth_epochs_to(recs[lo:hi], full.ptr + lo * n_samp * 4)
             dist.barrier()
