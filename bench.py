@@ -642,7 +642,10 @@ def main():
             issue = {"bound": "issue slots (integer pipes; no tensor-core or HBM-bound formulation of this loop exists)",
                      "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-inst/s", "frac": ach_issue / peak_issue,
                      "warp_inst_per_launch": tr[2], "inst_per_channel_sample": tr[2] * 32 / (samples_per_step * n_chan),
-                     "source": f"smsp__inst_executed.sum in profiles/{tr[1]}; peak = {st.sm_count} SMs x 4 schedulers x SM clock under load"}
+                     "source": f"smsp__inst_executed.sum in profiles/{tr[1]}; peak = {st.sm_count} SMs x 4 schedulers x SM clock under load",
+                     "peak_source": "one warp instruction per clock and scheduler, measured on a B200 with tools/ubench/pipe_rates.cu "
+                                    "(profiles/r1_pipe_rates_b200.txt: add.u64 = IADD3 + IADD3.X pairs 0.998, IMAD | SHF pairs 0.969 warp-inst/clk/SMSP; "
+                                    "a single integer pipe -- IMAD, or IADD3 / LOP3 / SHF -- takes 0.50)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -210,32 +210,37 @@ int match_epoch(const GalTime &t, const std::vector<Ephemeris> &v)
     return -1;
 }
 
-/* ------------------------------------------------------------------ geodesy (src/geodesy.cpp) */
+/* ------------------------------------------------------------------ geodesy */
 double norm3(const double *x) { return sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]); }
 
-void ecef_to_llh(const double *xyz, double *llh) /* :7-54 */
+/* Geodetic latitude / longitude / height of an ECEF point by fixed-point iteration on the offset, along the polar
+   axis, between the point and the centre of the prime-vertical circle through its footprint (offset = N e^2 sin(lat));
+   stops when the offset moves by less than a millimetre.  The sequence of operations is the one of the reference's
+   xyz2llh (src/geodesy.cpp:7-54): the records have to come out bit-identical (tests/test_host_scenario.py). */
+void ecef_to_llh(const double *xyz, double *llh)
 {
-    const double a = kWgsA, e = kWgsE, eps = 1.0e-3, e2 = e * e;
-    if (norm3(xyz) < eps) {
-        llh[0] = 0.0, llh[1] = 0.0, llh[2] = -a;
+    const double ecc_sq = kWgsE * kWgsE, tolerance = 1.0e-3;
+    if (norm3(xyz) < tolerance) { /* the Earth's centre: no direction to speak of */
+        llh[0] = 0.0, llh[1] = 0.0, llh[2] = -kWgsA;
         return;
     }
-    const double x = xyz[0], y = xyz[1], z = xyz[2];
-    const double rho2 = x * x + y * y;
-    double dz = e2 * z, zdz, nh, slat, n, dz_new;
-    while (1) {
-        zdz = z + dz;
-        nh = sqrt(rho2 + zdz * zdz);
-        slat = zdz / nh;
-        n = a / sqrt(1.0 - e2 * slat * slat);
-        dz_new = n * e2 * slat;
-        if (fabs(dz - dz_new) < eps)
+    const double axis_dist_sq = xyz[0] * xyz[0] + xyz[1] * xyz[1];
+    double offset = ecc_sq * xyz[2];
+    double z_from_centre, range_from_centre, prime_vertical;
+    for (;;) {
+        z_from_centre = xyz[2] + offset;
+        range_from_centre = sqrt(axis_dist_sq + z_from_centre * z_from_centre);
+        const double sin_lat = z_from_centre / range_from_centre;
+        prime_vertical = kWgsA / sqrt(1.0 - ecc_sq * sin_lat * sin_lat);
+        const double next_offset = prime_vertical * ecc_sq * sin_lat;
+        const bool settled = fabs(offset - next_offset) < tolerance;
+        if (settled)
             break;
-        dz = dz_new;
+        offset = next_offset;
     }
-    llh[0] = atan2(zdz, sqrt(rho2));
-    llh[1] = atan2(y, x);
-    llh[2] = nh - n;
+    llh[0] = atan2(z_from_centre, sqrt(axis_dist_sq));
+    llh[1] = atan2(xyz[1], xyz[0]);
+    llh[2] = range_from_centre - prime_vertical;
 }
 
 void llh_to_ecef(const double *llh, double *xyz) /* :60-91 */
@@ -271,53 +276,87 @@ void az_el(const double *los, double t[3][3], double *azel) /* ecef2neu + neu2az
     azel[1] = atan2(neu[2], ne);
 }
 
-/* broadcast-ephemeris position, velocity, clock (satpos :161-279) */
+/* ---- broadcast orbit (Galileo OS SIS ICD 5.1.1, table 58: the user algorithm for the ephemeris; velocity by
+ * differentiating it).  Split into the three steps of that table; every expression keeps the operand order of the
+ * reference's satpos (src/geodesy.cpp:161-279), because f_carr and code_phase0 of the records are compared bit for bit
+ * with the reference's trace and a last-bit difference in a satellite position shows there. */
+double week_wrapped(double dt) /* time difference folded into half a week either side */
+{
+    if (dt > 302400.0)
+        return dt - 604800.0;
+    if (dt < -302400.0)
+        return dt + 604800.0;
+    return dt;
+}
+
+struct KeplerSolution {
+    double sin_e, cos_e;    /* of the eccentric anomaly */
+    double one_minus_ecos;  /* 1 - e cos E of the last iteration */
+};
+
+/* Newton's iteration on Kepler's equation from E = M, to 1e-14 rad */
+KeplerSolution solve_kepler(double mean_anomaly, double ecc)
+{
+    KeplerSolution k;
+    double anomaly = mean_anomaly, previous = anomaly + 1.0;
+    k.one_minus_ecos = 0;
+    for (int it = 0; fabs(anomaly - previous) > 1.0E-14 && it < 500; it++) {
+        previous = anomaly;
+        k.one_minus_ecos = 1.0 - ecc * cos(previous);
+        anomaly = anomaly + (mean_anomaly - previous + ecc * sin(previous)) / k.one_minus_ecos;
+    }
+    k.sin_e = sin(anomaly);
+    k.cos_e = cos(anomaly);
+    return k;
+}
+
+struct InPlane { /* position in the orbital plane, the plane's orientation, and their rates */
+    double x, y, x_rate, y_rate;
+    double incl, incl_rate;
+    double node;
+};
+
+InPlane in_plane_state(const Ephemeris &eph, double t_since_toe, const KeplerSolution &k)
+{
+    const double anomaly_rate = eph.n / k.one_minus_ecos;
+    const double lat_arg0 = atan2(eph.sq1e2 * k.sin_e, k.cos_e - eph.ecc) + eph.aop;   /* true anomaly + argument of perigee */
+    const double lat_arg0_rate = eph.sq1e2 * anomaly_rate / k.one_minus_ecos;
+    const double s2 = sin(2.0 * lat_arg0), c2 = cos(2.0 * lat_arg0);                    /* second-harmonic corrections */
+    const double lat_arg = lat_arg0 + eph.cus * s2 + eph.cuc * c2;
+    const double sin_u = sin(lat_arg), cos_u = cos(lat_arg);
+    const double lat_arg_rate = lat_arg0_rate * (1.0 + 2.0 * (eph.cus * c2 - eph.cuc * s2));
+    const double radius = eph.A * k.one_minus_ecos + eph.crc * c2 + eph.crs * s2;
+    const double radius_rate = eph.A * eph.ecc * k.sin_e * anomaly_rate + 2.0 * lat_arg0_rate * (eph.crs * c2 - eph.crc * s2);
+    InPlane q;
+    q.incl = eph.inc0 + eph.idot * t_since_toe + eph.cic * c2 + eph.cis * s2;
+    q.incl_rate = eph.idot + 2.0 * lat_arg0_rate * (eph.cis * c2 - eph.cic * s2);
+    q.x = radius * cos_u;
+    q.y = radius * sin_u;
+    q.x_rate = radius_rate * cos_u - q.y * lat_arg_rate;
+    q.y_rate = radius_rate * sin_u + q.x * lat_arg_rate;
+    q.node = eph.omg0 + t_since_toe * eph.omgkdot - kEarthRate * eph.toe.sec;           /* longitude of the node, Earth-fixed */
+    return q;
+}
+
+/* position [m], velocity [m/s] in ECEF and clock bias / drift of a satellite at system time g */
 void sat_state(const Ephemeris &eph, const GalTime &g, double *pos, double *vel, double *clk)
 {
-    double tk = g.sec - eph.toe.sec;
-    if (tk > 302400.0)
-        tk -= 604800.0;
-    else if (tk < -302400.0)
-        tk += 604800.0;
-    const double mk = eph.m0 + eph.n * tk;
-    double ek = mk, ekold = ek + 1.0, omce = 0;
-    for (int it = 0; (fabs(ek - ekold) > 1.0E-14) && it < 500; it++) {
-        ekold = ek;
-        omce = 1.0 - eph.ecc * cos(ekold);
-        ek = ek + (mk - ekold + eph.ecc * sin(ekold)) / omce;
-    }
-    const double sek = sin(ek), cek = cos(ek);
-    const double ekdot = eph.n / omce;
-    const double relativistic = -4.442807633E-10 * eph.ecc * eph.sqrta * sek;
-    const double pk = atan2(eph.sq1e2 * sek, cek - eph.ecc) + eph.aop;
-    const double pkdot = eph.sq1e2 * ekdot / omce;
-    const double s2pk = sin(2.0 * pk), c2pk = cos(2.0 * pk);
-    const double uk = pk + eph.cus * s2pk + eph.cuc * c2pk;
-    const double suk = sin(uk), cuk = cos(uk);
-    const double ukdot = pkdot * (1.0 + 2.0 * (eph.cus * c2pk - eph.cuc * s2pk));
-    const double rk = eph.A * omce + eph.crc * c2pk + eph.crs * s2pk;
-    const double rkdot = eph.A * eph.ecc * sek * ekdot + 2.0 * pkdot * (eph.crs * c2pk - eph.crc * s2pk);
-    const double ik = eph.inc0 + eph.idot * tk + eph.cic * c2pk + eph.cis * s2pk;
-    const double sik = sin(ik), cik = cos(ik);
-    const double ikdot = eph.idot + 2.0 * pkdot * (eph.cis * c2pk - eph.cic * s2pk);
-    const double xpk = rk * cuk, ypk = rk * suk;
-    const double xpkdot = rkdot * cuk - ypk * ukdot, ypkdot = rkdot * suk + xpk * ukdot;
-    const double ok = eph.omg0 + tk * eph.omgkdot - kEarthRate * eph.toe.sec;
-    const double sok = sin(ok), cok = cos(ok);
-    pos[0] = xpk * cok - ypk * cik * sok;
-    pos[1] = xpk * sok + ypk * cik * cok;
-    pos[2] = ypk * sik;
-    const double tmp = ypkdot * cik - ypk * sik * ikdot;
-    vel[0] = -eph.omgkdot * pos[1] + xpkdot * cok - tmp * sok;
-    vel[1] = eph.omgkdot * pos[0] + xpkdot * sok + tmp * cok;
-    vel[2] = ypk * cik * ikdot + ypkdot * sik;
-    tk = g.sec - eph.toc.sec;
-    if (tk > 302400.0)
-        tk -= 604800.0;
-    else if (tk < -302400.0)
-        tk += 604800.0;
-    clk[0] = eph.af0 + tk * (eph.af1 + tk * eph.af2) + relativistic - eph.bgde5b;
-    clk[1] = eph.af1 + 2.0 * tk * eph.af2;
+    const double t_since_toe = week_wrapped(g.sec - eph.toe.sec);
+    const KeplerSolution k = solve_kepler(eph.m0 + eph.n * t_since_toe, eph.ecc);
+    const InPlane q = in_plane_state(eph, t_since_toe, k);
+    const double sin_i = sin(q.incl), cos_i = cos(q.incl), sin_node = sin(q.node), cos_node = cos(q.node);
+    pos[0] = q.x * cos_node - q.y * cos_i * sin_node;
+    pos[1] = q.x * sin_node + q.y * cos_i * cos_node;
+    pos[2] = q.y * sin_i;
+    const double y_rate_in_equator = q.y_rate * cos_i - q.y * sin_i * q.incl_rate;
+    vel[0] = -eph.omgkdot * pos[1] + q.x_rate * cos_node - y_rate_in_equator * sin_node;
+    vel[1] = eph.omgkdot * pos[0] + q.x_rate * sin_node + y_rate_in_equator * cos_node;
+    vel[2] = q.y * cos_i * q.incl_rate + q.y_rate * sin_i;
+    /* clock polynomial + relativistic term (F e sqrt(A) sin E) - the E1/E5b group delay, as the reference applies it */
+    const double relativistic = -4.442807633E-10 * eph.ecc * eph.sqrta * k.sin_e;
+    const double t_since_toc = week_wrapped(g.sec - eph.toc.sec);
+    clk[0] = eph.af0 + t_since_toc * (eph.af1 + t_since_toc * eph.af2) + relativistic - eph.bgde5b;
+    clk[1] = eph.af1 + 2.0 * t_since_toc * eph.af2;
 }
 
 /* obliquity-factor ionosphere (src/iono.cpp:9-19), the model in force with vflg == 0 (:37-40) */
@@ -420,39 +459,20 @@ int unscale_int(double value, int scale)
 }
 unsigned int unscale_uint(double value, int scale) { return (unsigned int)unscale_mag(value, scale); }
 
-uint32_t crc24q_entry(int i) /* include/galileo-sdr.h:3459: the CRC-24Q table, entries shifted left by 8 */
+/* CRC-24Q of a bit string (Galileo OS SIS ICD 5.1.9.3: generator 1864CFBh, zero initial value, bits in transmission
+   order), one bit at a time.  The reference computes the same polynomial division bytewise with a table and a
+   partial last byte (Crc24qEncode, src/inav-msg.cpp:134-162); that the two agree is held by the page symbols of the
+   records (bit-identical to the reference's trace) and by the live-sky pages of tests/test_tv_pages.py. */
+unsigned int crc24q_bits(const int *bits, int length)
 {
-    uint32_t c = (uint32_t)i << 16;
-    for (int k = 0; k < 8; k++)
-        c = (c & 0x800000u) ? ((c << 1) ^ 0x1864CFBu) : (c << 1);
-    return (c & 0xffffffu) << 8;
-}
-
-unsigned int crc24q_bits(const int *bits, int length) /* Crc24qEncode, inav-msg.cpp:134-162 */
-{
-    static uint32_t table[256];
-    static bool ready = false;
-    if (!ready) {
-        for (int i = 0; i < 256; i++)
-            table[i] = crc24q_entry(i);
-        ready = true;
+    uint32_t rem = 0;
+    for (int j = 0; j < length; j++) {
+        rem ^= (uint32_t)(bits[j] & 1) << 23;
+        rem <<= 1;
+        if (rem & 0x1000000u)
+            rem ^= 0x1864CFBu;
     }
-    unsigned int crc = 0;
-    unsigned char byte = 0;
-    int j;
-    for (j = 0; j < length; j++) {
-        if (j > 0 && j % 8 == 0) {
-            crc = ((crc | byte) << 8) ^ table[(crc >> 24) & 0xFF];
-            byte = 0;
-        }
-        byte = (unsigned char)((byte << 1) | (bits[j] & 1));
-    }
-    const unsigned trail = (unsigned)(j % 8);
-    byte = (unsigned char)(byte << (8u - trail));
-    crc = ((crc | byte) << trail) ^ table[(crc >> ((32 - trail) & 31)) & 0xFF];
-    for (int i = 0; i < 3; i++)
-        crc = (crc << 8) ^ table[(crc >> 24) & 0xFF];
-    return crc >> 8;
+    return rem & 0xFFFFFFu;
 }
 
 /* rate-1/2, K = 7 (G1 = 171o, G2 = 133o inverted), zero initial state; 120 bits -> 240 symbols
