@@ -46,6 +46,8 @@ WORKLOADS = {
     "cfg4s": (25e6, 2500000, 36, 300, "BASELINE configs[3] slice: dynamic receiver, 25 MS/s, 36 ch, 30 s (300 blocks), per-block "
                                       "Doppler/code-phase restate on the device from pseudorange records"),
 }
+WORKLOADS["cfg5s"] = (25e6, 2500000, 36, 2400, "BASELINE configs[4] slice: 25 MS/s, 36 ch, 240 s (2400 blocks = 24 GB of int16 I/Q); meant for --gpus N: "
+                                               "the `strong` object is ONE such scenario sharded on the time axis over the N GPUs and assembled in rank 0's HBM")
 WORKLOADS["rt1"] = (2.6e6, 260000, 16, 1, "real-time call shape: ONE 0.1 s block per call (what the reference's galileo_task() loop hands over per iteration), "
                                           "2.6 MS/s, 16 slots, 8 satellites; a step = one call: ms_per_step is the latency of a call")
 METRIC = "E1B/C IQ Msamples/sec"
@@ -627,7 +629,7 @@ def main():
         bytes_per_launch = out_bytes * args.steps / max(synth_launches, 1)
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
         tr = ncu_summary_numbers() if args.workload == "cfg2" else None
-        if args.workload in ("cfg3", "cfg3s", "cfg4s"):            # captured on the 30 s slice (750 M samples per launch): per-sample figures scale
+        if args.workload in ("cfg3", "cfg3s", "cfg4s", "cfg5s"):            # captured on the 30 s slice (750 M samples per launch): per-sample figures scale
             t3 = ncu_summary_numbers("cfg3")
             if t3:
                 k = samples_per_step / (300 * 2500000)
