@@ -516,13 +516,27 @@ def main():
         d_seg_recs = torch.from_numpy(np.ascontiguousarray(recs_all[lo:hi]).view(np.uint8).reshape(-1)).to(dev)
         d_recs_all = d_recs if rank == 0 else torch.from_numpy(recs_all.view(np.uint8).reshape(-1)).to(dev)   # the whole scenario's records, resident
         handle = torch.zeros(64, dtype=torch.uint8, device=dev)
-        full = None
+        full, peer_err = None, ""
         if rank == 0:
-            full = E.PeerBuffer.alloc(local_rank, out_bytes)
-            handle.copy_(torch.frombuffer(bytearray(full.handle), dtype=torch.uint8))
+            try:
+                full = E.PeerBuffer.alloc(local_rank, out_bytes)
+                handle.copy_(torch.frombuffer(bytearray(full.handle), dtype=torch.uint8))
+            except Exception as ex:
+                peer_err = str(ex)
         dist.broadcast(handle, 0)
         if rank != 0:
-            full = E.PeerBuffer.open(local_rank, bytes(handle.cpu().numpy().tobytes()), out_bytes)
+            try:
+                full = E.PeerBuffer.open(local_rank, bytes(handle.cpu().numpy().tobytes()), out_bytes)
+            except Exception as ex:
+                peer_err = str(ex)
+        ok = torch.tensor([0.0 if peer_err else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        peer_ok = bool(ok.item() > 0)
+        if not peer_ok:          # e.g. ranks in separate containers (no CUDA IPC), GPUs that are not peers: the weak line still stands
+            if full is not None:
+                full.close()
+            strong = {"scaling": "strong", "unavailable": "peer memory (CUDA IPC) between the ranks' GPUs: " + (peer_err or "another rank failed to open the handle")}
+    if dist is not None and not use_ranges and strong is None:
         seg_engine = E.Synth(fs, n_samp, n_chan, device=local_rank)
         d_seg = torch.empty((hi - lo) * n_samp, dtype=torch.int32, device=dev)          # NCCL variant: one (I, Q) pair = one int32
         d_full = torch.empty(n_epochs * n_samp, dtype=torch.int32, device=dev) if rank == 0 else None
