@@ -521,3 +521,26 @@ def test_event_driven_and_per_sample_forms_write_the_same_stream():
     assert np.array_equal(a, b) and np.array_equal(pa, pb)
     ref, _ = U.oracle_synth(fs, n_samp, recs, threads=8)
     assert np.array_equal(a, ref)
+
+
+def test_event_driven_form_degenerate_steps_fall_back():
+    """Steps the event form does not take: a code step that divides 2^32 (fs = 32 f_chip at zero Doppler: dF = 2^28 exactly,
+    n0 steps land ON 2^32 and the carry test would miss it), a carrier step of a quarter entry per sample and more
+    (dG >= 2^30: the first-carry remainder test needs 3 dG < 2^32), both next to channels just inside the limits.  Such
+    (tile, channel) sets are not marked E1_PAR_EV and go through the generic form; the stream is the oracle's either way."""
+    hs = U.hostsim()
+    fs = 32.0 * 1.023e6                      # exactly representable in float: fs_as_reference leaves it alone
+    assert U.fs_as_reference(fs) == fs
+    f_edge = 0.25 * fs / 511.0               # dG = 2^30
+    freqs = [0.0, 1e-3, f_edge * 0.999, f_edge * 1.001, -f_edge * 0.999, -f_edge * 1.3, 2000.0]
+    recs = U.synthetic_recs(2, len(freqs), fs, seed=91)
+    for c, f in enumerate(freqs):
+        recs[:, c]["f_carr"] = f
+        recs[:, c]["f_code"] = 1.023e6 + f * 0.0006493506493506494
+    p0, r0 = hs.hs_ev_pairs(), hs.hs_ev_rest()
+    a, pa = U.oracle_synth(fs, 150000, recs, threads=8)
+    b, pb, st = U.hostsim_synth(fs, 150000, recs)
+    assert np.array_equal(a, b) and np.array_equal(pa, pb), st
+    ev, rest = hs.hs_ev_pairs() - p0, hs.hs_ev_rest() - r0
+    # channels 0 (power-of-two code step), 3 and 5 (fast carrier) take the generic form, the other four the event form
+    assert rest >= 3 * (ev // 4) * 0.9 and ev > 0, (ev, rest)
