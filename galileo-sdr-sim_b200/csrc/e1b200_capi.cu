@@ -32,7 +32,8 @@ struct e1b200_ctx {
     int synth_threads;  /* threads per synthesis CTA */
     int tiles_per_epoch;
     int batch_epochs;   /* epochs per D2H staging buffer (host entry points)            */
-    int plan_epochs;    /* epochs per planner pass (bounds scratch)                     */
+    int plan_epochs;    /* epochs per planner pass, at most (bounds scratch)            */
+    int scratch_epochs; /* epochs the scratch arrays hold right now (ensure_plan_scratch) */
     int sm_count, ctas_per_sm, smem_bytes;
     int use_bulk, amb_scale, serial_planner;
     int float_path;     /* E1B200_CFG_CBOC / _GAIN: e1_synth_float_kernel (FP32 accumulate, float -> int16 store) */
@@ -365,14 +366,34 @@ int e1b200_set_carrier_phases(e1b200_ctx *ctx, int n, const double *phases)
     return E1B200_OK;
 }
 
-static int ensure_plan_scratch(e1b200_ctx *ctx)
+/* Planner scratch (checkpoints, parameter blocks, per-span arrays) and the record staging of the host entry points,
+ * for passes of up to scratch_epochs blocks.  Sized by the calls that arrive, not by the largest pass the context may
+ * ever run: the real-time call shape (one block per call) gets along with 64 blocks' worth (a few MB) instead of
+ * plan_epochs' (2 GiB); a larger call grows it, at least doubling, up to plan_epochs. */
+static int ensure_plan_scratch(e1b200_ctx *ctx, int n_epochs)
 {
-    if (ctx->d_ck)
+    int want = n_epochs < 64 ? 64 : n_epochs;
+    if (want > ctx->plan_epochs)
+        want = ctx->plan_epochs;
+    if (want <= ctx->scratch_epochs)
         return E1B200_OK;
-    const size_t nec = (size_t)ctx->plan_epochs * ctx->cfg.max_chan;
+    if (want < 2 * ctx->scratch_epochs)
+        want = 2 * ctx->scratch_epochs < ctx->plan_epochs ? 2 * ctx->scratch_epochs : ctx->plan_epochs;
+    /* work of an earlier asynchronous call may still be using the old arrays */
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->side_stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    void **arrays[] = {(void **)&ctx->d_ck, (void **)&ctx->d_blk, (void **)&ctx->d_delta, (void **)&ctx->d_g, (void **)&ctx->d_dend,
+                       (void **)&ctx->d_est, (void **)&ctx->d_units, (void **)&ctx->d_prep, (void **)&ctx->d_recs, (void **)&ctx->d_ranges};
+    for (void **a : arrays) {
+        cudaFree(*a);
+        *a = nullptr;
+    }
+    ctx->scratch_epochs = 0;
+    const size_t nec = (size_t)want * ctx->cfg.max_chan;
     const size_t ne = nec * ctx->geo.spans_per_epoch; /* planner units */
     CK(cudaMalloc(&ctx->d_ck, sizeof(e1_tile_ck) * nec * ctx->tiles_per_epoch));
-    CK(cudaMalloc(&ctx->d_blk, e1_blk_bytes(ctx->cfg.max_chan) * (size_t)ctx->plan_epochs * ctx->tiles_per_epoch));
+    CK(cudaMalloc(&ctx->d_blk, e1_blk_bytes(ctx->cfg.max_chan) * (size_t)want * ctx->tiles_per_epoch));
     CK(cudaMalloc(&ctx->d_delta, sizeof(e1_trans) * ne));
     CK(cudaMemset(ctx->d_delta, 0, sizeof(e1_trans) * ne));
     if (!ctx->serial_planner) {
@@ -382,6 +403,7 @@ static int ensure_plan_scratch(e1b200_ctx *ctx)
         CK(cudaMalloc(&ctx->d_units, sizeof(e1_unit) * ne));
         CK(cudaMalloc(&ctx->d_prep, sizeof(e1_prep) * ne));
     }
+    ctx->scratch_epochs = want;
     return E1B200_OK;
 }
 
@@ -424,7 +446,7 @@ static int enqueue_plan(e1b200_ctx *ctx, int n, const e1_epoch_rec *d_recs, int 
        Such a pass (up to E1B200_SMALL_PASS = 8 blocks) gets shorter spans, down to one tile, as long as they fit the scratch. */
     e1_span_geo geo = ctx->geo;
     {
-        const long cap = (long)ctx->plan_epochs * ctx->geo.spans_per_epoch; /* units per channel the scratch holds */
+        const long cap = (long)ctx->scratch_epochs * ctx->geo.spans_per_epoch; /* units per channel the scratch holds */
         long units = (long)n * geo.spans_per_epoch * cfg->max_chan;
         const long fill = (long)ctx->sm_count * 128;
         const int small_max = env_int("E1B200_SMALL_PASS", 8); /* blocks; larger passes keep the long spans (their reach back to a
@@ -618,7 +640,7 @@ int e1b200_synth_epochs_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec
     if (!ctx || n_epochs < 0 || (n_epochs && (!d_recs || !d_out)))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_plan_scratch(ctx);
+    int rc = ensure_plan_scratch(ctx, n_epochs);
     if (rc)
         return rc;
     reset_call(ctx);
@@ -647,7 +669,7 @@ int e1b200_sync(e1b200_ctx *ctx)
 static int ensure_staging(e1b200_ctx *ctx, int want_ranges, int want_out)
 {
     const e1b200_config *cfg = &ctx->cfg;
-    size_t nrec = (size_t)ctx->plan_epochs * cfg->max_chan;
+    size_t nrec = (size_t)ctx->scratch_epochs * cfg->max_chan; /* after ensure_plan_scratch: it frees these with the rest when it grows */
     if (!ctx->d_recs)
         CK(cudaMalloc(&ctx->d_recs, nrec * sizeof(e1_epoch_rec)));
     if (want_ranges && !ctx->d_ranges)
@@ -686,7 +708,7 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
     if (!ctx || n_epochs < 0 || (n_epochs && ((!recs && !ranges) || !out)))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_plan_scratch(ctx);
+    int rc = ensure_plan_scratch(ctx, n_epochs);
     if (!rc)
     {
         /* ring slots: a job of many slices wants the kernels far ahead of the copies; a call of one or two slices (the
@@ -804,7 +826,7 @@ int e1b200_plan_phases(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs)
     if (!ctx || n_epochs < 0 || (n_epochs && !recs))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_plan_scratch(ctx);
+    int rc = ensure_plan_scratch(ctx, n_epochs);
     if (!rc)
         rc = ensure_staging(ctx, 0, 0);
     if (rc)
@@ -827,7 +849,7 @@ int e1b200_plan_phases_device(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec 
     if (!ctx || n_epochs < 0 || (n_epochs && !d_recs))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_plan_scratch(ctx);
+    int rc = ensure_plan_scratch(ctx, n_epochs);
     if (rc)
         return rc;
     reset_call(ctx);
@@ -844,7 +866,7 @@ int e1b200_synth_ranges_device(e1b200_ctx *ctx, int n_epochs, const e1_range_rec
     if (!ctx || n_epochs < 0 || (n_epochs && (!d_rr || !d_out)))
         return E1B200_EINVAL;
     CK(cudaSetDevice(ctx->cfg.device));
-    int rc = ensure_plan_scratch(ctx);
+    int rc = ensure_plan_scratch(ctx, n_epochs);
     if (!rc)
         rc = ensure_staging(ctx, 0, 0);
     if (rc)
