@@ -544,3 +544,19 @@ def test_event_driven_form_degenerate_steps_fall_back():
     ev, rest = hs.hs_ev_pairs() - p0, hs.hs_ev_rest() - r0
     # channels 0 (power-of-two code step), 3 and 5 (fast carrier) take the generic form, the other four the event form
     assert rest >= 3 * (ev // 4) * 0.9 and ev > 0, (ev, rest)
+
+
+def test_event_driven_form_independent_of_ambiguity_threshold():
+    """The same at 25 MS/s: with inflated bounds fewer tiles are clean and more threads are flagged, so the tracking form of
+    the events, its take-back and the generic form behind it all run -- and write the bytes of the lean form."""
+    hs = U.hostsim()
+    recs = U.synthetic_recs(2, 8, FS25, seed=21)
+    a, _ = U.oracle_synth(FS25, 120000, recs, threads=8)
+    exact, rest = [], []
+    for scale in (1, 300, 30000):
+        r0 = hs.hs_ev_rest()
+        b, _, st = U.hostsim_synth(FS25, 120000, recs, amb_scale=scale)
+        assert np.array_equal(a, b), scale
+        exact.append(int(st[0]))
+        rest.append(hs.hs_ev_rest() - r0)
+    assert exact == sorted(exact) and exact[-1] > exact[0] and rest == sorted(rest) and rest[-1] > rest[0], (exact, rest)
