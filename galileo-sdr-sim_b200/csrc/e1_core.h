@@ -362,7 +362,7 @@ typedef struct e1_chan_par { /* 112 bytes, one per active channel of a tile (HBM
 #define E1_PAR_HASZ 64u
 #define E1_PAR_CLEAN 128u /* no run of this tile can be ambiguous (e1_par_clean): the sample loop skips its tracking */
 #define E1_PAR_SLOW 256u  /* the carrier moves by less than one table entry per sample (|step| < 1/512 cycle: 5 kHz at
-                             2.6 MS/s) and the tile is regular (no FORCE / HASZ): the paired-run kernel walks the table
+                             2.6 MS/s) and the tile is regular (no FORCE / HASZ): the carry-walked kernel walks the table
                              by CARRIES of the index fraction, one carrier start per 32 or 64 samples (e1_run_cw)      */
 #define E1_PAR_DOWN 512u  /* with E1_PAR_SLOW: the table position decreases from sample to sample                      */
 #define E1_PAR_EV 1024u   /* with E1_PAR_SLOW, set when the context runs the event-driven kernel (E1_INT_EV): a half-chip
@@ -1638,64 +1638,16 @@ E1_HD uint32_t e1_run_fast(const e1_chan_par *p, const uint32_t *codes, const un
     return e1_sample_loop<R>(y, D, e1_sp(lut_lane), F, p->dF, win, acc, lim_carr, lim_code);
 }
 
-/* Two consecutive runs of E1C_MAX_RUN samples (tile samples j0 .. j0 + 2 E1C_MAX_RUN - 1) of one channel,
- * with everything that does not depend on the half done once: parameter loads, the 64-bit products
- * j0 * dH and j0 * dU (the second half adds 16 steps), the carrier step.  What is added to acc and
- * what is flagged is, half by half, exactly what e1_run_fast<E1C_MAX_RUN> at j0 and at
- * j0 + E1C_MAX_RUN adds and flags (same integers), so the caller repairs a flagged half with the
- * single-run machinery.  Irregular channels -- generic form forced, a zero crossing in this tile --
- * simply take the two single runs (the condition is the same for every thread of the tile).
- * Returns the two halves' return codes, first half in bits 0-1, second in bits 2-3.
- * CHECK = false is for the channels of a tile marked E1_PAR_CLEAN (e1_par_clean: no sample of the tile
- * is near an index boundary, so no run can be flagged): the same sums without the ambiguity tracking. */
-template <bool CHECK>
-E1_HD uint32_t e1_run_fast_pair(const e1_chan_par *p, const uint32_t *codes, const unsigned char *lut_lane, int j0, int *acc,
-                                uint32_t tc_carr, uint32_t lim_carr, uint32_t lim_code)
-{
-    const int R = E1C_MAX_RUN;
-    const int jw = p->j_w;
-    const uint32_t misc = p->misc;
-    if (misc & (E1_PAR_FORCE | E1_PAR_HASZ)) {
-        const uint32_t a = e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0, acc, tc_carr, lim_carr, lim_code);
-        const uint32_t b = e1_run_fast<E1C_MAX_RUN>(p, codes, lut_lane, j0 + R, acc + R, tc_carr, lim_carr, lim_code);
-        return a | (b << 2);
-    }
-    const uint64_t dH = p->dH, dU = p->dU;
-    const int after0 = j0 >= jw, after1 = j0 + R >= jw;
-    uint64_t H = (after0 ? p->HB : p->HA) + (uint64_t)(uint32_t)j0 * dH;
-    uint64_t U = p->U0 + (uint64_t)(uint32_t)j0 * dU;
-    const uint32_t dF = p->dF;
-    const uint32_t neg = misc & E1_PAR_NEG;
-    const e1_sptr code = e1_sp(codes) + 4u * p->code_off, lut = e1_sp(lut_lane);
-    uint32_t rc = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int h = 0; h < 2; h++) {
-        const int jh = j0 + h * R;
-        if (h == 1) {
-            U += (uint64_t)R * dU;
-            /* the second half continues the first one's code phase unless the code wrapped in between */
-            H = after1 != after0 ? p->HB + (uint64_t)(uint32_t)jh * dH : H + (uint64_t)R * dH;
-        }
-        const uint32_t win = e1_code_window(p, code, H, jh, R, jw);
-        int64_t D;
-        const uint64_t y = e1_carrier_start(U, dU, neg, tc_carr, lim_carr, &D);
-        rc |= e1_sample_loop<E1C_MAX_RUN, CHECK>(y, D, lut, (uint32_t)(H >> 19), dF, win, acc + h * R, lim_carr, lim_code) << (2 * h);
-    }
-    return rc;
-}
-
-/* ---- paired runs, carrier table walked by carries (E1_PAR_SLOW tiles) -------------------------------------
+/* ---- several runs from one carrier start, the table walked by carries (E1_PAR_SLOW tiles) -------------------------------------
  * The table position of e1_sample_loop is a 64-bit number, entry in the high word, index fraction in the low
  * word, stepped by D per sample.  When |D| < 2^32 (less than one entry per sample) the high word changes by at
  * most one: the loop keeps the fraction and the table ADDRESS instead, adds the low word of D to the fraction
  * with its carry flag, and moves the address by one entry (128 bytes) on a carry (D >= 0) or on a missing carry
  * (D < 0, i.e. a borrow) -- the same integers as the 64-bit add, one instruction per sample less (no
- * multiply-add from entry number to address).  At most 2 R < E1C_LUT_EXT entries are walked from one start, so
- * ONE carrier start serves both halves of the pair (bias and limit for a run of 2 R samples).  The code side is
- * what e1_run_fast_pair does, half by half.  Returns 1 when some sample of the pair is ambiguous (CHECK): the
- * caller takes the terms back out and redoes the samples with the generic form (e1_cw_rest_impl). */
+ * multiply-add from entry number to address).  At most NH R <= E1C_LUT_EXT entries are walked from one start, so
+ * ONE carrier start serves all NH runs of a thread (bias and limit for NH R samples).  The code side is what
+ * e1_run_fast does, run by run.  Returns 1 when some sample is ambiguous (CHECK): the caller drops the terms and
+ * redoes the samples with the generic form (e1_cw_rest_impl). */
 
 /* Sample loop with the table walked by carries: see e1_cw_step below.  `one` is the value 1 in a register ptxas
  * cannot see through (the kernel derives it from a launch argument): the address step is spelled
@@ -1764,7 +1716,7 @@ E1_HD void e1_cw_step(uint32_t &ylo, e1_sptr &addr, uint32_t Dlo, uint32_t &F, u
 
 /* NH consecutive runs of R = 16 samples (NH = 2: 32 samples per thread, NH = 4: 64) from ONE carrier start: every
  * run's table position is the start's plus a multiple of 16 D (|D| < 1 entry per sample and NH R <= E1C_LUT_EXT keep all of
- * them inside the table's extension); the code side is set up run by run as in e1_run_fast_pair.  All set-up comes
+ * them inside the table's extension); the code side is set up run by run as in e1_run_fast.  All set-up comes
  * first, then ONE loop of R iterations steps the NH runs side by side: NH independent dependency chains for the
  * scheduler instead of one of NH R steps.  codes_s / lut_s: the code words and this lane's copy of the carrier table
  * as shared-memory operands (e1_sptr).  Returns 1 when some sample is ambiguous. */

@@ -556,7 +556,7 @@ __device__ __forceinline__ void e1_mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 /* Marks the (tile, channel) parameter sets whose runs cannot be ambiguous (e1_par_clean): one thread per
- * (tile, compacted slot), after e1_finalize_kernel, for the paired-run kernel. */
+ * (tile, compacted slot), after e1_finalize_kernel, for the carry-walked and the event-driven kernel. */
 struct e1_clean_args {
     unsigned char *blk;
     long n_tiles;

@@ -425,7 +425,7 @@ def test_first_hit_equals_brute_force():
 
 
 def test_tiles_marked_clean_never_hold_a_flagged_run():
-    """The paired-run kernel drops the per-sample ambiguity tracking for the channels of a tile that
+    """The carry-walked kernel drops the per-sample ambiguity tracking for the channels of a tile that
     e1_par_clean marks.  The host build runs the tracking loop beside the plain one on every run of
     such a tile: it must flag nothing and add the same terms (hostsim_synth asserts the counter);
     here, that the marking is neither vacuous nor universal, and that flagged runs do occur (in the

@@ -213,7 +213,7 @@ def test_internal_batching_and_no_tma_path(monkeypatch):
 
 def test_clean_tile_marking_does_not_change_the_stream(monkeypatch):
     """e1_clean_kernel marks the (tile, channel) sets without a sample near an index boundary and the
-    paired-run kernel drops the per-sample ambiguity tracking for them.  Same bytes with the marking
+    carry-walked kernel drops the per-sample ambiguity tracking for them.  Same bytes with the marking
     switched off (E1B200_NO_ELIDE: every run is tracked, as before), and both equal the oracle; the
     exact-fallback count is the same too -- the flagged runs all live in unmarked tiles."""
     fs, n_samp, nch = FS26, 260000, 36
