@@ -560,3 +560,19 @@ def test_event_driven_form_independent_of_ambiguity_threshold():
         exact.append(int(st[0]))
         rest.append(hs.hs_ev_rest() - r0)
     assert exact == sorted(exact) and exact[-1] > exact[0] and rest == sorted(rest) and rest[-1] > rest[0], (exact, rest)
+
+
+def test_event_driven_form_random_rates_and_dopplers():
+    """Seeded sweep: 24 sample rates between 10 and 60 MS/s (as the reference would round them: (double)(float)fs), block
+    lengths that are no multiple of anything, Dopplers up to +-12 kHz, a few blocks each: the oracle's bytes every time."""
+    hs = U.hostsim()
+    rng = np.random.default_rng(2024)
+    p0 = hs.hs_ev_pairs()
+    for i in range(24):
+        fs = U.fs_as_reference(float(rng.uniform(10.0e6, 60.0e6)))
+        n_samp = int(rng.integers(30000, 90000))
+        recs = U.synthetic_recs(2, 6, fs, seed=300 + i, max_chan=7, f_max=float(rng.choice([500.0, 4000.0, 12000.0])))
+        a, pa = U.oracle_synth(fs, n_samp, recs, threads=8)
+        b, pb, st = U.hostsim_synth(fs, n_samp, recs)
+        assert np.array_equal(a, b) and np.array_equal(pa, pb), (i, fs, n_samp, st, int((a != b).any(1).sum()))
+    assert hs.hs_ev_pairs() - p0 > 20000
