@@ -129,6 +129,11 @@ typedef struct e1b200_timing {
 int  e1b200_create(const e1b200_config *cfg, e1b200_ctx **out);
 int  e1b200_destroy(e1b200_ctx *ctx);
 
+/* What allocateChannel() leaves in a slot that the sample loop reads (src/channel.cpp:69-99): the carrier phase.
+ * The PRN -- and with it the code tables, which the reference builds per allocation and this library holds for all
+ * 50 PRNs -- travels in every record (e1_epoch_rec.prn), as chan[i].prn does in the reference; `prn` here is only
+ * range-checked.  Equivalent: E1_REC_SET_PHASE + carr_phase_init in the slot's next record.  clear_channel: the slot's
+ * phase is dead state (src/channel.cpp:112-119); records with prn = 0 keep it silent. */
 int  e1b200_set_channel(e1b200_ctx *ctx, int slot, int prn, double carr_phase0);
 int  e1b200_clear_channel(e1b200_ctx *ctx, int slot);
 int  e1b200_get_carrier_phase(e1b200_ctx *ctx, int slot, double *out);
