@@ -728,9 +728,12 @@ static int synth_host(e1b200_ctx *ctx, int n_epochs, const e1_epoch_rec *recs, c
        after a short pass instead of after the whole job's planning, and each pass's copies outlast the
        next pass's planning (a pass costs ~5 ms of dependent walks however small it is, a block's D2H
        ~20 us at 2.6 MS/s); the copies, not the kernels, bound this entry point */
-    int chunk = env_int("E1B200_FIRST_PASS", 256);
-    if (chunk < 1)
-        chunk = 1;
+    /* ... the first pass holds about 256 MB of output (256 blocks at 2.6 MS/s, 26 at 25 MS/s), unless E1B200_FIRST_PASS says otherwise */
+    int chunk = env_int("E1B200_FIRST_PASS", 0);
+    if (chunk < 1) {
+        chunk = (int)(((size_t)256 * 1040000) / ((size_t)cfg->samples_per_epoch * 4));
+        chunk = chunk < 9 ? 9 : (chunk > 256 ? 256 : chunk);
+    }
     {
         /* a destination in DEVICE memory (this GPU's or a peer's, e1b200_peer_open) is fed over NVLink or HBM, an order
            of magnitude faster than PCIe: there the kernels bound the call, not the copies, and every extra planner pass
