@@ -97,6 +97,10 @@ def test_bench_reads_the_newest_ncu_summary():
                     if "cfg3" not in f.name)
     assert name == "r%d_v%d_synth_ncu_summary.txt" % builds[-1] and (root / "profiles" / name).exists()
     assert 3.0e9 < traffic < 4.0e9 and 5.0e9 < inst < 2.0e10
+    # the 25 MS/s family reads the captures of the event-driven kernel on the 30 s slice (750 M samples per launch)
+    t3 = bench.ncu_summary_numbers("cfg3")
+    assert t3 and "cfg3" in t3[1] and t3[1].startswith("r2_") and (root / "profiles" / t3[1]).exists()
+    assert 3.0e9 < t3[0] < 4.0e9 and t3[2] * 32 / (750e6 * 36) < 6.0          # fewer than 6 instruction slots per channel-sample
 
 
 def test_code_wraps_equals_the_literal_loop(lib):
