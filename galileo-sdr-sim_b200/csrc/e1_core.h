@@ -602,11 +602,13 @@ E1_HD double e1_binade_top(double x) { return e1_from_bits(((e1_bits(x) >> 52) +
  *     (o == NULL: no checkpoints),
  *   - narrows tr->[lo,hi) to the translations that keep every visited value in its binade,
  *   - records the last wrap in tr->last_k / last_p and the first tie wrap in tr->tie_k / tie_dir. */
-E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile, int64_t n_emit, e1_tile_ck *o,
+E1_HD double e1_span_walk(double a, double t, int32_t k, int32_t k_end, int tile, int32_t n_emit, e1_tile_ck *o,
                           int stride, int neg, e1_span_track *tr)
 {
-    int64_t ti = k / tile + 1; /* next tile index to checkpoint */
-    int64_t kt = o ? ti * (int64_t)tile : (int64_t)0x7fffffffffffffffLL;
+    /* sample counters are 32-bit: a span is a few hundred thousand samples at most (the 64-bit versions cost two
+       instructions for every compare and add of the walk) */
+    int32_t ti = k / tile + 1; /* next tile index to checkpoint */
+    int32_t kt = o ? ti * tile : 0x7fffffff;
     double lo = tr->lo, hi = tr->hi;
 #define E1_EMIT(val)                                                                                                   \
     do {                                                                                                               \
@@ -656,7 +658,7 @@ E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile
             continue;
         int64_t d = b3 - b2;
         int64_t end = ((b1 >> 52) + 1) << 52;
-        int64_t n;
+        int32_t n;
         k++; /* now at x2 */
         a = x2;
         if (k == kt)
@@ -664,15 +666,14 @@ E1_HD double e1_span_walk(double a, double t, int64_t k, int64_t k_end, int tile
         if (d == 0)
             n = k_end - k; /* stuck for good */
         else {
-            n = e1_div_binade(end - 1 - b2, d);
-            if (n > k_end - k)
-                n = k_end - k;
+            const int64_t nn = e1_div_binade(end - 1 - b2, d);
+            n = nn > (int64_t)(k_end - k) ? k_end - k : (int32_t)nn;
         }
         while (kt <= k + n && kt < n_emit) {
-            double v = e1_from_bits(b2 + (kt - k) * d);
+            double v = e1_from_bits(b2 + (int64_t)(kt - k) * d);
             E1_EMIT(v);
         }
-        a = e1_from_bits(b2 + n * d);
+        a = e1_from_bits(b2 + (int64_t)n * d);
         k += n;
         {
             double up = e1_add(e1_from_bits(end), -a);
