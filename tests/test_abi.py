@@ -137,3 +137,26 @@ def test_code_wraps_equals_the_literal_loop(lib):
         c = c + sc
     assert c >= 4092.0 and lit == 0 and E.code_wraps(fs, n, start, f_code) == 0
     assert E.code_wraps(fs, n + 1, start, f_code) == 1
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) needs no GPU: one JSON line with the
+    B200 arm's metric / unit / config keys, impl = reference, a cpu_baseline describing the run and an e2e of its own.
+    Under torchrun only rank 0 works; the other ranks exit 0 without a line."""
+    import json
+    import os
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--workload", "rt1", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-400:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "E1B/C IQ Msamples/sec" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("real-time call shape")
+    other = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--workload", "rt1", "--steps", "1", "--warmup", "0", "--gpus", "2"],
+                           capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert other.returncode == 0 and not other.stdout.strip()
